@@ -1,0 +1,65 @@
+"""ctypes binding of libaanet_b200.so (the C-ABI declared in include/aanet_b200.h).
+
+There is no fallback: if the shared library is missing the import of any op raises, and every op
+raises NotImplementedError for non-CUDA tensors exactly like the reference op
+(nets/deform_conv/deform_conv.py:135-136).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libaanet_b200.so")
+ABI_VERSION = 1
+
+_vp, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+
+# symbol -> (restype, argtypes); must list every function include/aanet_b200.h declares
+SIGNATURES = {
+    "aanet_abi_version": (_i, []),
+    "aanet_status_string": (ctypes.c_char_p, [_i]),
+    "aanet_last_cuda_error": (ctypes.c_char_p, []),
+    "aanet_corr_fwd": (_i, [_vp, _vp, _vp] + [_i] * 5 + [_vp]),
+    "aanet_corr_bwd": (_i, [_vp] * 5 + [_i] * 5 + [_vp]),
+    "aanet_softargmin_fwd": (_i, [_vp, _vp] + [_i] * 5 + [_vp]),
+    "aanet_softargmin_bwd": (_i, [_vp, _vp, _vp] + [_i] * 5 + [_vp]),
+    "aanet_mdcn_workspace_bytes": (_sz, [_i] * 13),
+    "aanet_mdcn_fwd": (_i, [_vp] * 6 + [_i] * 12 + [_vp, _vp, _i, _vp, _sz, _vp]),
+    "aanet_mdcn_bwd": (_i, [_vp] * 10 + [_i] * 12 + [_vp, _sz, _vp]),
+    "aanet_csa_fuse_fwd": (_i, [_vp, _vp, _vp, _i, _vp] + [_i] * 4 + [_f, _vp]),
+    "aanet_csa_fuse_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i] + [_i] * 4 + [_f, _vp]),
+}
+
+_lib = None
+
+
+class AanetError(RuntimeError):
+    """Non-zero aanet_status from the C-ABI (the reference raises RuntimeError via TORCH_CHECK)."""
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "aanet_b200: %s is missing -- build it with `python -m aanet_b200.build` "
+            "(or __graft_entry__.build()). There is no CPU or PyTorch fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)     # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    if lib.aanet_abi_version() != ABI_VERSION:
+        raise ImportError("aanet_b200: ABI version mismatch (library %d, binding %d)"
+                          % (lib.aanet_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        lib = load()
+        msg = lib.aanet_status_string(status).decode()
+        if status == 5:
+            msg += ": " + lib.aanet_last_cuda_error().decode()
+        raise AanetError("%s failed: %s (status %d)" % (what, msg, status))

@@ -1,0 +1,27 @@
+// Status strings / version for the C-ABI (include/aanet_b200.h).
+#include <string.h>
+#include "common.cuh"
+
+namespace aanet {
+static thread_local char g_last_err[256] = "";
+void set_last_cuda_error(const char *msg) {
+    strncpy(g_last_err, msg ? msg : "", sizeof(g_last_err) - 1);
+    g_last_err[sizeof(g_last_err) - 1] = 0;
+}
+}  // namespace aanet
+
+extern "C" int aanet_abi_version(void) { return AANET_B200_ABI_VERSION; }
+
+extern "C" const char *aanet_status_string(int s) {
+    switch (s) {
+        case AANET_OK: return "ok";
+        case AANET_ERR_NULL: return "required pointer is NULL";
+        case AANET_ERR_SHAPE: return "invalid or inconsistent shape";
+        case AANET_ERR_UNSUPPORTED: return "configuration not supported by the sm_100a kernels";
+        case AANET_ERR_WORKSPACE: return "workspace missing or too small";
+        case AANET_ERR_LAUNCH: return "CUDA launch failed";
+        default: return "unknown status";
+    }
+}
+
+extern "C" const char *aanet_last_cuda_error(void) { return aanet::g_last_err; }

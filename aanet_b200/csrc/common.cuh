@@ -1,0 +1,45 @@
+// Shared helpers for the aanet_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/aanet_b200.h"
+
+namespace aanet {
+
+constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
+
+// Records the CUDA error text of a failed launch for aanet_last_cuda_error().
+void set_last_cuda_error(const char *msg);
+
+// Checks cudaGetLastError() after a launch; never synchronises.
+inline int check_launch() {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_last_cuda_error(cudaGetErrorString(e));
+        return AANET_ERR_LAUNCH;
+    }
+    return AANET_OK;
+}
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+template <typename T>
+__host__ __device__ inline bool aligned16(const T *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// Streaming (read-once) 128-bit and 32-bit loads that do not pollute L1.
+__device__ __forceinline__ float4 ldg_stream4(const float *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ldg_stream(const float *p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+
+}  // namespace aanet

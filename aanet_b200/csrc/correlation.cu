@@ -1,0 +1,181 @@
+// Correlation cost volume, forward and backward.
+//
+// Replaces CostVolume.forward, correlation branch (reference nets/cost.py:40-48): the reference
+// loops over the D disparities in Python, each iteration materialising a [B,C,H,W-d] product, a
+// channel mean and a strided store (~100x the algorithmic HBM traffic, ~340 launches per pair).
+// Here one launch per scale computes, per image row, the banded contraction
+//     cost[d,w] = (1/C) * sum_c L[c,w] * R[c,w-d],   0 <= w-d,  0 <= d < D
+// reading L and R once.
+//
+// Forward tiling: a CTA owns (b, h, 128 w's, 64 d's).  Channels are streamed through shared
+// memory in chunks of 8; the R window for the tile is 128+64 wide so every (w,d) pair in the
+// tile finds R[w-d] in shared memory.  A thread accumulates an 8(w) x 8(d) register tile: per
+// channel it needs 8 L values and the 15-wide R diagonal band, fetched as 2+4 LDS.128 for 64 FMAs.
+// The w<d triangle is written as exact zeros (the reference's new_zeros, cost.py:41).
+#include "common.cuh"
+
+namespace aanet {
+
+constexpr int kTW = 128;            // w per CTA
+constexpr int kTD = 64;             // d per CTA
+constexpr int kCK = 8;              // channels per smem stage
+constexpr int kRW = kTW + kTD;      // R window width (192)
+constexpr int kCorrThreads = 128;   // 16 (w groups of 8) x 8 (d groups of 8)
+
+__global__ void __launch_bounds__(kCorrThreads)
+corr_fwd_kernel(const float *__restrict__ L, const float *__restrict__ R, float *__restrict__ cost,
+                int C, int H, int W, int D, int n_wtiles) {
+    __shared__ __align__(16) float sL[2][kCK][kTW];
+    __shared__ __align__(16) float sR[2][kCK][kRW];
+
+    const int wt = blockIdx.x % n_wtiles, dt = blockIdx.x / n_wtiles;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int w0 = wt * kTW, d0 = dt * kTD;
+    const int tid = threadIdx.x;
+    const int tw = (tid & 15) * 8, td = (tid >> 4) * 8;
+    const long HW = (long)H * W;
+    const float *Lrow = L + (long)b * C * HW + (long)h * W;
+    const float *Rrow = R + (long)b * C * HW + (long)h * W;
+    // smem R index r  <->  global column  w0 - d0 - kTD + r
+    const int rbase = w0 - d0 - kTD;
+
+    // A whole tile above the diagonal band (all w < d) is zeros.
+    const bool all_zero = (w0 + kTW - 1) < d0;
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    auto load_stage = [&](int buf, int c0) {
+        // L: kCK x kTW floats, R: kCK x kRW floats; coalesced along w, zero-filled out of range
+        for (int i = tid; i < kCK * kTW; i += kCorrThreads) {
+            const int c = i / kTW, x = i % kTW, w = w0 + x;
+            sL[buf][c][x] = (c0 + c < C && w < W) ? Lrow[(long)(c0 + c) * HW + w] : 0.f;
+        }
+        for (int i = tid; i < kCK * kRW; i += kCorrThreads) {
+            const int c = i / kRW, x = i % kRW, w = rbase + x;
+            sR[buf][c][x] = (c0 + c < C && w >= 0 && w < W) ? Rrow[(long)(c0 + c) * HW + w] : 0.f;
+        }
+    };
+
+    if (!all_zero) {
+        const int nchunk = ceil_div(C, kCK);
+        load_stage(0, 0);
+        __syncthreads();
+        for (int ck = 0; ck < nchunk; ++ck) {
+            const int buf = ck & 1;
+            if (ck + 1 < nchunk) load_stage(buf ^ 1, (ck + 1) * kCK);
+#pragma unroll
+            for (int c = 0; c < kCK; ++c) {
+                float l[8], r[16];
+                *reinterpret_cast<float4 *>(&l[0]) = *reinterpret_cast<const float4 *>(&sL[buf][c][tw]);
+                *reinterpret_cast<float4 *>(&l[4]) = *reinterpret_cast<const float4 *>(&sL[buf][c][tw + 4]);
+                // thread's R band: columns (tw+i) - (td+j) + kTD, i,j in 0..7  ->  [tw-td+kTD-7, tw-td+kTD+7]
+                const int rb = tw - td + kTD - 8;       // multiple of 8 -> 16B aligned
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<float4 *>(&r[4 * q]) = *reinterpret_cast<const float4 *>(&sR[buf][c][rb + 4 * q]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(l[i], r[8 + i - j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+    }
+
+    const float inv = 1.f / (float)C;
+    const bool vec_ok = (W % 4 == 0) && aligned16(cost);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int d = d0 + td + j;
+        if (d >= D) continue;
+        float *orow = cost + (((long)b * D + d) * H + h) * W;
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int w = w0 + tw + i;
+            o[i] = (w >= d) ? acc[i][j] * inv : 0.f;
+        }
+        const int w = w0 + tw;
+        if (vec_ok && w + 8 <= W) {
+            *reinterpret_cast<float4 *>(orow + w) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4 *>(orow + w + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (w + i < W) orow[w + i] = o[i];
+        }
+    }
+}
+
+// Backward (autograd of cost.py:45-48):
+//   gL[c,w]  = (1/C) sum_{d<=w}    g[d,w]    * R[c,w-d]
+//   gR[c,w'] = (1/C) sum_{w'+d<W}  g[d,w'+d] * L[c,w'+d]
+// A CTA owns (b, h, 64 w's): it stages g[0..D) for the columns [w0, w0+64+D) once in shared memory
+// and then walks the channels, each thread producing gL and gR for one (c, w).
+constexpr int kBW = 64;
+constexpr int kBwdThreads = 256;   // 64 w x 4 channel lanes
+
+__global__ void __launch_bounds__(kBwdThreads)
+corr_bwd_kernel(const float *__restrict__ L, const float *__restrict__ R, const float *__restrict__ g,
+                float *__restrict__ gL, float *__restrict__ gR, int C, int H, int W, int D) {
+    extern __shared__ float sg[];          // [D][kBW + D]  (row stride GW)
+    const int GW = kBW + D;
+    const int w0 = blockIdx.x * kBW, h = blockIdx.y, b = blockIdx.z;
+    const long HW = (long)H * W;
+    for (int i = threadIdx.x; i < D * GW; i += kBwdThreads) {
+        const int d = i / GW, x = i % GW, w = w0 + x;
+        sg[i] = (w < W) ? g[(((long)b * D + d) * H + h) * W + w] : 0.f;
+    }
+    __syncthreads();
+    const int x = threadIdx.x % kBW, cl = threadIdx.x / kBW;
+    const int w = w0 + x;
+    if (w >= W) return;
+    const float inv = 1.f / (float)C;
+    for (int c = cl; c < C; c += kBwdThreads / kBW) {
+        const float *lrow = L + ((long)b * C + c) * HW + (long)h * W;
+        const float *rrow = R + ((long)b * C + c) * HW + (long)h * W;
+        float al = 0.f, ar = 0.f;
+        const int dl = min(D - 1, w);            // d <= w
+        for (int d = 0; d <= dl; ++d) al = fmaf(sg[d * GW + x], rrow[w - d], al);
+        const int dr = min(D - 1, W - 1 - w);    // w + d < W
+        for (int d = 0; d <= dr; ++d) ar = fmaf(sg[d * GW + x + d], lrow[w + d], ar);
+        gL[((long)b * C + c) * HW + (long)h * W + w] = al * inv;
+        gR[((long)b * C + c) * HW + (long)h * W + w] = ar * inv;
+    }
+}
+
+}  // namespace aanet
+
+using namespace aanet;
+
+extern "C" int aanet_corr_fwd(const float *L, const float *R, float *cost, int B, int C, int H, int W,
+                              int D, void *stream) {
+    if (!L || !R || !cost) return AANET_ERR_NULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || D <= 0) return AANET_ERR_SHAPE;
+    if (H > 65535 || B > 65535) return AANET_ERR_UNSUPPORTED;
+    const int n_wtiles = ceil_div(W, kTW), n_dtiles = ceil_div(D, kTD);
+    const dim3 grid(n_wtiles * n_dtiles, H, B);
+    corr_fwd_kernel<<<grid, kCorrThreads, 0, as_stream(stream)>>>(L, R, cost, C, H, W, D, n_wtiles);
+    return check_launch();
+}
+
+extern "C" int aanet_corr_bwd(const float *L, const float *R, const float *gcost, float *gL, float *gR,
+                              int B, int C, int H, int W, int D, void *stream) {
+    if (!L || !R || !gcost || !gL || !gR) return AANET_ERR_NULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || D <= 0) return AANET_ERR_SHAPE;
+    if (H > 65535 || B > 65535) return AANET_ERR_UNSUPPORTED;
+    const size_t smem = sizeof(float) * (size_t)D * (kBW + D);
+    if (smem > 200 * 1024) return AANET_ERR_UNSUPPORTED;
+    static bool attr_set = false;   // idempotent; benign if raced
+    if (!attr_set) {
+        cudaFuncSetAttribute(corr_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    const dim3 grid(ceil_div(W, kBW), H, B);
+    corr_bwd_kernel<<<grid, kBwdThreads, smem, as_stream(stream)>>>(L, R, gcost, gL, gR, C, H, W, D);
+    return check_launch();
+}

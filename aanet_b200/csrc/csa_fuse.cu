@@ -1,0 +1,184 @@
+// Cross-scale aggregation fuse: resize + ordered sum + LeakyReLU in one pass (HBM-bound).
+//
+// Replaces the tail of AdaptiveAggregationModule.forward (reference nets/aggregation.py:387-400),
+// which per output scale runs F.interpolate (one kernel per coarser term), two adds and an in-place
+// LeakyReLU -- every intermediate makes a round trip through HBM.  Here each output element is
+// produced once: same-size terms are read with 128-bit loads, coarser terms are sampled with ATen's
+// align_corners=False bilinear rule (aggregation.py:395-396; src = (dst+0.5)*in/out - 0.5 clamped at
+// 0, i1 = min(i0+1, in-1)), and the sum keeps the reference's order j = 0, 1, 2.
+#include "common.cuh"
+
+namespace aanet {
+
+struct CsaTerms {
+    const float *ptr[AANET_CSA_MAX_TERMS];
+    int th[AANET_CSA_MAX_TERMS], tw[AANET_CSA_MAX_TERMS];
+    int n;
+};
+struct CsaGrads {
+    float *ptr[AANET_CSA_MAX_TERMS];
+    int th[AANET_CSA_MAX_TERMS], tw[AANET_CSA_MAX_TERMS];
+    int n;
+};
+
+// ATen area_pixel_compute_source_index + guard (float arithmetic, as for float tensors).
+__device__ __forceinline__ void src_index(int dst, int in, float scale, int &i0, int &i1, float &l0, float &l1) {
+    float src = scale * ((float)dst + 0.5f) - 0.5f;
+    src = src < 0.f ? 0.f : src;
+    i0 = min((int)src, in - 1);
+    i1 = i0 + (i0 < in - 1 ? 1 : 0);
+    l1 = src - (float)i0;
+    l0 = 1.f - l1;
+}
+
+__device__ __forceinline__ float sample_term(const float *__restrict__ src, int th, int tw, int H, int W,
+                                             int h, int w) {
+    int h0, h1, w0, w1; float a0, a1, b0, b1;
+    src_index(h, th, (float)th / (float)H, h0, h1, a0, a1);
+    src_index(w, tw, (float)tw / (float)W, w0, w1, b0, b1);
+    const float *r0 = src + (long)h0 * tw, *r1 = src + (long)h1 * tw;
+    return a0 * (b0 * __ldg(r0 + w0) + b1 * __ldg(r0 + w1)) + a1 * (b0 * __ldg(r1 + w0) + b1 * __ldg(r1 + w1));
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+csa_fuse_fwd_kernel(CsaTerms t, float *__restrict__ out, int H, int W, long n_vec, float slope) {
+    const int Wv = W / VEC;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long)gridDim.x * blockDim.x) {
+        const int wv = (int)(i % Wv);
+        const long r = i / Wv;
+        const int h = (int)(r % H);
+        const long bc = r / H;
+        const int w = wv * VEC;
+        float acc[VEC];
+#pragma unroll
+        for (int k = 0; k < AANET_CSA_MAX_TERMS; ++k) {
+            if (k >= t.n) break;
+            float v[VEC];
+            if (t.th[k] == H && t.tw[k] == W) {
+                const float *p = t.ptr[k] + (bc * H + h) * W + w;
+                if (VEC == 4) {
+                    const float4 q = ldg_stream4(p);
+                    v[0] = q.x; v[1 % VEC] = q.y; v[2 % VEC] = q.z; v[3 % VEC] = q.w;
+                } else {
+                    v[0] = ldg_stream(p);
+                }
+            } else {
+                const float *src = t.ptr[k] + bc * t.th[k] * t.tw[k];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) v[e] = sample_term(src, t.th[k], t.tw[k], H, W, h, w + e);
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[e] = (k == 0) ? v[e] : acc[e] + v[e];
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[e] = acc[e] > 0.f ? acc[e] : acc[e] * slope;
+        float *o = out + (bc * H + h) * W + w;
+        if (VEC == 4) *reinterpret_cast<float4 *>(o) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
+        else o[0] = acc[0];
+    }
+}
+
+// Backward, same-size term: g * LeakyReLU'(pre); sign(pre) == sign(out) because slope > 0.
+__global__ void __launch_bounds__(256)
+csa_bwd_same_kernel(const float *__restrict__ out, const float *__restrict__ gout, float *__restrict__ gt,
+                    long n, float slope) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        gt[i] = gout[i] * (out[i] > 0.f ? 1.f : slope);
+}
+
+// Backward, resized term: adjoint of the bilinear resize in gather form.  For a source row hs the
+// destination rows that reference it satisfy floor(src(h)) in {hs-1, hs}; a conservative window is
+// scanned and every candidate is re-derived with the forward's exact arithmetic.
+__global__ void __launch_bounds__(256)
+csa_bwd_resize_kernel(const float *__restrict__ out, const float *__restrict__ gout, float *__restrict__ gt,
+                      int th, int tw, int H, int W, long n_src, float slope) {
+    const float sh = (float)th / (float)H, sw = (float)tw / (float)W;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_src; i += (long)gridDim.x * blockDim.x) {
+        const int ws = (int)(i % tw);
+        const long r = i / tw;
+        const int hs = (int)(r % th);
+        const long bc = r / th;
+        const int h_lo = max(0, (int)floorf(((float)hs - 0.5f) / sh - 0.5f) - 1);
+        const int h_hi = min(H - 1, (int)ceilf(((float)hs + 1.5f) / sh - 0.5f) + 1);
+        const int w_lo = max(0, (int)floorf(((float)ws - 0.5f) / sw - 0.5f) - 1);
+        const int w_hi = min(W - 1, (int)ceilf(((float)ws + 1.5f) / sw - 0.5f) + 1);
+        const float *o_b = out + bc * H * W, *g_b = gout + bc * H * W;
+        float acc = 0.f;
+        for (int h = h_lo; h <= h_hi; ++h) {
+            int h0, h1; float a0, a1;
+            src_index(h, th, sh, h0, h1, a0, a1);
+            const float wh = (h0 == hs ? a0 : 0.f) + (h1 == hs ? a1 : 0.f);
+            if (wh == 0.f) continue;
+            float row = 0.f;
+            for (int w = w_lo; w <= w_hi; ++w) {
+                int w0, w1; float b0, b1;
+                src_index(w, tw, sw, w0, w1, b0, b1);
+                const float ww = (w0 == ws ? b0 : 0.f) + (w1 == ws ? b1 : 0.f);
+                if (ww == 0.f) continue;
+                const long q = (long)h * W + w;
+                row = fmaf(ww, g_b[q] * (o_b[q] > 0.f ? 1.f : slope), row);
+            }
+            acc = fmaf(wh, row, acc);
+        }
+        gt[i] = acc;
+    }
+}
+
+inline unsigned grid_for(long n, int block) {
+    long g = ceil_div_ll(n, block);
+    const long cap = (long)kNumSMs * 16;   // grid-stride beyond 16 CTAs per SM
+    return (unsigned)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+}  // namespace aanet
+
+using namespace aanet;
+
+extern "C" int aanet_csa_fuse_fwd(const float *const *terms, const int *th, const int *tw, int n_terms,
+                                  float *out, int B, int C, int H, int W, float slope, void *stream) {
+    if (!terms || !th || !tw || !out) return AANET_ERR_NULL;
+    if (n_terms < 1 || n_terms > AANET_CSA_MAX_TERMS || B <= 0 || C <= 0 || H <= 0 || W <= 0)
+        return AANET_ERR_SHAPE;
+    CsaTerms t;
+    t.n = n_terms;
+    bool vec = (W % 4 == 0) && aligned16(out);
+    for (int k = 0; k < AANET_CSA_MAX_TERMS; ++k) {
+        t.ptr[k] = nullptr; t.th[k] = t.tw[k] = 0;
+        if (k >= n_terms) continue;
+        if (!terms[k]) return AANET_ERR_NULL;
+        if (th[k] <= 0 || tw[k] <= 0) return AANET_ERR_SHAPE;
+        t.ptr[k] = terms[k]; t.th[k] = th[k]; t.tw[k] = tw[k];
+        if (th[k] == H && tw[k] == W && !aligned16(terms[k])) vec = false;
+    }
+    const long n = (long)B * C * H * W;
+    if (vec)
+        csa_fuse_fwd_kernel<4><<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(t, out, H, W, n / 4, slope);
+    else
+        csa_fuse_fwd_kernel<1><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(t, out, H, W, n, slope);
+    return check_launch();
+}
+
+extern "C" int aanet_csa_fuse_bwd(const float *out, const float *gout, float *const *gterms, const int *th,
+                                  const int *tw, int n_terms, int B, int C, int H, int W, float slope,
+                                  void *stream) {
+    if (!out || !gout || !gterms || !th || !tw) return AANET_ERR_NULL;
+    if (n_terms < 1 || n_terms > AANET_CSA_MAX_TERMS || B <= 0 || C <= 0 || H <= 0 || W <= 0)
+        return AANET_ERR_SHAPE;
+    if (!(slope > 0.f)) return AANET_ERR_UNSUPPORTED;
+    for (int k = 0; k < n_terms; ++k) {
+        if (!gterms[k]) continue;           // gradient not requested for this term
+        if (th[k] <= 0 || tw[k] <= 0) return AANET_ERR_SHAPE;
+        if (th[k] == H && tw[k] == W) {
+            const long n = (long)B * C * H * W;
+            csa_bwd_same_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(out, gout, gterms[k], n, slope);
+        } else {
+            const long n = (long)B * C * th[k] * tw[k];
+            csa_bwd_resize_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(out, gout, gterms[k], th[k],
+                                                                                  tw[k], H, W, n, slope);
+        }
+        const int rc = check_launch();
+        if (rc) return rc;
+    }
+    return AANET_OK;
+}

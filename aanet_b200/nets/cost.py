@@ -1,0 +1,38 @@
+"""Correlation cost volume modules -- drop-in for the reference's nets/cost.py.
+
+`CostVolume(max_disp, feature_similarity='correlation')` and `CostVolumePyramid(...)` keep the
+reference constructors and call conventions (nets/cost.py:5-76).  Only the correlation branch
+(cost.py:40-48) is on the hot path and implemented; 'difference' / 'concat' (cost.py:22-38) build
+5-D volumes for the StereoNet/PSMNet/GC-Net ablations and are out of scope.
+"""
+import torch.nn as nn
+
+from .. import ops
+
+
+class CostVolume(nn.Module):
+    def __init__(self, max_disp, feature_similarity='correlation'):
+        super().__init__()
+        self.max_disp = max_disp
+        self.feature_similarity = feature_similarity
+
+    def forward(self, left_feature, right_feature):
+        if self.feature_similarity != 'correlation':
+            # cost.py:50-51 raises for unknown names; the two 5-D variants are not provided here
+            raise NotImplementedError("aanet_b200 implements feature_similarity='correlation' only")
+        return ops.correlation(left_feature, right_feature, self.max_disp)
+
+
+class CostVolumePyramid(nn.Module):
+    """One correlation volume per pyramid level, level s using max_disp // 2**s (cost.py:64-76)."""
+
+    def __init__(self, max_disp, feature_similarity='correlation'):
+        super().__init__()
+        self.max_disp = max_disp
+        self.feature_similarity = feature_similarity
+
+    def forward(self, left_feature_pyramid, right_feature_pyramid):
+        if self.feature_similarity != 'correlation':
+            raise NotImplementedError("aanet_b200 implements feature_similarity='correlation' only")
+        return [ops.correlation(l, r, self.max_disp // (2 ** s))
+                for s, (l, r) in enumerate(zip(left_feature_pyramid, right_feature_pyramid))]

@@ -1,0 +1,281 @@
+"""torch.autograd front-ends of the C-ABI kernels.
+
+PyTorch is plumbing here (device memory, streams, autograd graph); the arithmetic is in
+libaanet_b200.so.  Every function requires CUDA float32 tensors and raises NotImplementedError for
+CPU tensors, mirroring nets/deform_conv/deform_conv.py:135-136,153-154 of the reference.
+"""
+import ctypes
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+
+LAUNCHES = 0   # number of C-ABI kernels-launching calls made by this process (bench bookkeeping)
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _prep(t, name):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NotImplementedError("aanet_b200.%s: CUDA tensors only (no CPU fallback)" % name)
+    if t.dtype != torch.float32:
+        raise TypeError("aanet_b200.%s: float32 only, got %s" % (name, t.dtype))
+    return t.contiguous()
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+# ------------------------------------------------------------------------------------ correlation
+class _Correlation(Function):
+    @staticmethod
+    def forward(ctx, left, right, max_disp):
+        left, right = _prep(left, "correlation"), _prep(right, "correlation")
+        if left.dim() != 4 or left.shape != right.shape:
+            raise ValueError("correlation: left/right must be [B,C,H,W] of equal shape")
+        B, C, H, W = left.shape
+        out = left.new_empty(B, max_disp, H, W)
+        with torch.cuda.device(left.device):
+            _lib.check(_lib.load().aanet_corr_fwd(_ptr(left), _ptr(right), _ptr(out), B, C, H, W,
+                                                  max_disp, _stream(left)), "aanet_corr_fwd")
+        _count()
+        ctx.save_for_backward(left, right)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        left, right = ctx.saved_tensors
+        g = _prep(g, "correlation")
+        B, C, H, W = left.shape
+        gl, gr = torch.empty_like(left), torch.empty_like(right)
+        with torch.cuda.device(left.device):
+            _lib.check(_lib.load().aanet_corr_bwd(_ptr(left), _ptr(right), _ptr(g), _ptr(gl), _ptr(gr),
+                                                  B, C, H, W, g.shape[1], _stream(left)), "aanet_corr_bwd")
+        _count()
+        return gl, gr, None
+
+
+def correlation(left, right, max_disp):
+    """cost[b,d,h,w] = mean_c left[b,c,h,w]*right[b,c,h,w-d], 0 where w<d (nets/cost.py:40-48)."""
+    return _Correlation.apply(left, right, int(max_disp))
+
+
+# ------------------------------------------------------------------------------------ soft-argmin
+class _SoftArgmin(Function):
+    @staticmethod
+    def forward(ctx, cost, similarity):
+        cost = _prep(cost, "soft_argmin")
+        B, D, H, W = cost.shape
+        disp = cost.new_empty(B, H, W)
+        with torch.cuda.device(cost.device):
+            _lib.check(_lib.load().aanet_softargmin_fwd(_ptr(cost), _ptr(disp), B, D, H, W,
+                                                        int(similarity), _stream(cost)),
+                       "aanet_softargmin_fwd")
+        _count()
+        ctx.save_for_backward(cost)
+        ctx.similarity = int(similarity)
+        return disp
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        cost, = ctx.saved_tensors
+        g = _prep(g, "soft_argmin")
+        B, D, H, W = cost.shape
+        gc = torch.empty_like(cost)
+        with torch.cuda.device(cost.device):
+            _lib.check(_lib.load().aanet_softargmin_bwd(_ptr(cost), _ptr(g), _ptr(gc), B, D, H, W,
+                                                        ctx.similarity, _stream(cost)),
+                       "aanet_softargmin_bwd")
+        _count()
+        return gc, None
+
+
+def soft_argmin(cost, similarity=True):
+    """disp = sum_d d*softmax_d(+-cost) (nets/estimation.py:13-30)."""
+    return _SoftArgmin.apply(cost, bool(similarity))
+
+
+# ------------------------------------------------------------------------------------ mdconv
+def _out_hw(H, W, kh, kw, stride, pad, dil):
+    return ((H + 2 * pad - (dil * (kh - 1) + 1)) // stride + 1,
+            (W + 2 * pad - (dil * (kw - 1) + 1)) // stride + 1)
+
+
+def _mdcn_forward(x, offset, mask, weight, bias, stride, pad, dil, groups, dg,
+                  post_scale=None, post_shift=None, relu=False):
+    B, Cin, H, W = x.shape
+    Cout, cg, kh, kw = weight.shape
+    if Cin != cg * groups:
+        raise _lib.AanetError("Input shape and kernel channels wont match: (%d vs %d)." % (Cin, cg * groups))
+    Ho, Wo = _out_hw(H, W, kh, kw, stride, pad, dil)
+    if Ho <= 0 or Wo <= 0:
+        raise ValueError("convolution input is too small (output would be %dx%d)" % (Ho, Wo))
+    if tuple(offset.shape) != (B, dg * 2 * kh * kw, Ho, Wo):
+        raise _lib.AanetError("offset must be [%d,%d,%d,%d], got %s" % (B, dg * 2 * kh * kw, Ho, Wo,
+                                                                         tuple(offset.shape)))
+    if mask is not None and tuple(mask.shape) != (B, dg * kh * kw, Ho, Wo):
+        raise _lib.AanetError("mask must be [%d,%d,%d,%d], got %s" % (B, dg * kh * kw, Ho, Wo,
+                                                                       tuple(mask.shape)))
+    out = x.new_empty(B, Cout, Ho, Wo)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().aanet_mdcn_fwd(
+            _ptr(x), _ptr(offset), _ptr(mask), _ptr(weight), _ptr(bias), _ptr(out),
+            B, Cin, H, W, Cout, kh, kw, stride, pad, dil, groups, dg,
+            _ptr(post_scale), _ptr(post_shift), int(relu), None, 0, _stream(x)), "aanet_mdcn_fwd")
+    _count()
+    return out
+
+
+def _mdcn_backward(x, offset, mask, weight, with_bias, g, stride, pad, dil, groups, dg):
+    B, Cin, H, W = x.shape
+    Cout, _, kh, kw = weight.shape
+    gx, goff = torch.empty_like(x), torch.empty_like(offset)
+    gmask = torch.empty_like(mask) if mask is not None else None
+    gw = torch.empty_like(weight)
+    gb = weight.new_empty(Cout) if with_bias else None
+    lib = _lib.load()
+    nbytes = lib.aanet_mdcn_workspace_bytes(1, B, Cin, H, W, Cout, kh, kw, stride, pad, dil, groups, dg)
+    ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.aanet_mdcn_bwd(
+            _ptr(x), _ptr(offset), _ptr(mask), _ptr(weight), _ptr(g), _ptr(gx), _ptr(goff), _ptr(gmask),
+            _ptr(gw), _ptr(gb), B, Cin, H, W, Cout, kh, kw, stride, pad, dil, groups, dg,
+            _ptr(ws), nbytes, _stream(x)), "aanet_mdcn_bwd")
+    _count(4)
+    return gx, goff, gmask, gw, gb
+
+
+def _single_int(v, name):
+    if isinstance(v, (tuple, list)):
+        if len(set(v)) != 1:
+            raise _lib.AanetError("%s must be the same in h and w, got %s" % (name, (v,)))
+        v = v[0]
+    return int(v)
+
+
+class ModulatedDeformConvFunction(Function):
+    """Same call signature as the reference's (nets/deform_conv/deform_conv.py:113-171)."""
+
+    @staticmethod
+    def forward(ctx, input, offset, mask, weight, bias=None, stride=1, padding=0, dilation=1, groups=1,
+                deformable_groups=1):
+        ctx.cfg = (_single_int(stride, "stride"), _single_int(padding, "padding"),
+                   _single_int(dilation, "dilation"), int(groups), int(deformable_groups))
+        ctx.with_bias = bias is not None
+        input, offset, mask = _prep(input, "mdconv"), _prep(offset, "mdconv"), _prep(mask, "mdconv")
+        weight, bias = _prep(weight, "mdconv"), _prep(bias, "mdconv")
+        ctx.save_for_backward(input, offset, mask, weight)
+        return _mdcn_forward(input, offset, mask, weight, bias, *ctx.cfg)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        input, offset, mask, weight = ctx.saved_tensors
+        g = _prep(grad_output, "mdconv")
+        gx, goff, gmask, gw, gb = _mdcn_backward(input, offset, mask, weight, ctx.with_bias, g, *ctx.cfg)
+        return gx, goff, gmask, gw, gb, None, None, None, None, None
+
+
+class DeformConvFunction(Function):
+    """DCNv1 (nets/deform_conv/deform_conv.py:12-110): the same kernels with mask == 1.  The
+    reference's im2col_step batching constraint (B % step == 0, :47-49) does not exist here; the
+    argument is accepted and ignored."""
+
+    @staticmethod
+    def forward(ctx, input, offset, weight, stride=1, padding=0, dilation=1, groups=1,
+                deformable_groups=1, im2col_step=64):
+        if input is not None and input.dim() != 4:
+            raise ValueError("Expected 4D tensor as input, got {}D tensor instead.".format(input.dim()))
+        ctx.cfg = (_single_int(stride, "stride"), _single_int(padding, "padding"),
+                   _single_int(dilation, "dilation"), int(groups), int(deformable_groups))
+        input, offset, weight = _prep(input, "deform_conv"), _prep(offset, "deform_conv"), \
+            _prep(weight, "deform_conv")
+        ctx.save_for_backward(input, offset, weight)
+        return _mdcn_forward(input, offset, None, weight, None, *ctx.cfg)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        input, offset, weight = ctx.saved_tensors
+        g = _prep(grad_output, "deform_conv")
+        gx, goff, _, gw, _ = _mdcn_backward(input, offset, None, weight, False, g, *ctx.cfg)
+        return gx, goff, gw, None, None, None, None, None, None
+
+
+modulated_deform_conv = ModulatedDeformConvFunction.apply
+deform_conv = DeformConvFunction.apply
+
+
+def modulated_deform_conv_fused(x, offset, mask, weight, bias, stride, padding, dilation, groups,
+                                deformable_groups, post_scale, post_shift, relu):
+    """Inference-only: mdconv with a per-channel affine (folded BatchNorm) + ReLU epilogue."""
+    x, offset, mask = _prep(x, "mdconv"), _prep(offset, "mdconv"), _prep(mask, "mdconv")
+    return _mdcn_forward(x, offset, mask, _prep(weight, "mdconv"), _prep(bias, "mdconv"), stride, padding,
+                         dilation, groups, deformable_groups, _prep(post_scale, "mdconv"),
+                         _prep(post_shift, "mdconv"), relu)
+
+
+# ------------------------------------------------------------------------------------ CSA fuse
+def _term_arrays(tensors):
+    n = len(tensors)
+    ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() if t is not None else None for t in tensors])
+    return ptrs
+
+
+class _CsaFuse(Function):
+    @staticmethod
+    def forward(ctx, slope, *terms):
+        terms = [_prep(t, "csa_fuse") for t in terms]
+        B, C, H, W = terms[0].shape
+        for t in terms:
+            if t.shape[:2] != terms[0].shape[:2]:
+                raise ValueError("csa_fuse: all terms must share [B,C]")
+        n = len(terms)
+        th = (ctypes.c_int * n)(*[t.shape[2] for t in terms])
+        tw = (ctypes.c_int * n)(*[t.shape[3] for t in terms])
+        out = terms[0].new_empty(B, C, H, W)
+        with torch.cuda.device(out.device):
+            _lib.check(_lib.load().aanet_csa_fuse_fwd(_term_arrays(terms), th, tw, n, _ptr(out), B, C, H, W,
+                                                      float(slope), _stream(out)), "aanet_csa_fuse_fwd")
+        _count()
+        ctx.save_for_backward(out)
+        ctx.meta = (slope, [tuple(t.shape) for t in terms])
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        out, = ctx.saved_tensors
+        slope, shapes = ctx.meta
+        g = _prep(g, "csa_fuse")
+        B, C, H, W = out.shape
+        n = len(shapes)
+        grads = [out.new_empty(s) if ctx.needs_input_grad[i + 1] else None for i, s in enumerate(shapes)]
+        th = (ctypes.c_int * n)(*[s[2] for s in shapes])
+        tw = (ctypes.c_int * n)(*[s[3] for s in shapes])
+        with torch.cuda.device(out.device):
+            _lib.check(_lib.load().aanet_csa_fuse_bwd(_ptr(out), _ptr(g), _term_arrays(grads), th, tw, n,
+                                                      B, C, H, W, float(slope), _stream(out)),
+                       "aanet_csa_fuse_bwd")
+        _count(n)
+        return (None,) + tuple(grads)
+
+
+def csa_fuse(terms, slope=0.2):
+    """LeakyReLU(sum_j resize(terms[j]) to terms[0]'s size), reference order
+    (nets/aggregation.py:387-400)."""
+    return _CsaFuse.apply(float(slope), *terms)

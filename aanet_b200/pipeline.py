@@ -1,0 +1,117 @@
+"""HotPath: the slice of AANet.forward this package accelerates, as one callable.
+
+    cost pyramid (nets/aanet.py:216) -> AdaptiveAggregation (:217) -> DisparityEstimation (:156-167)
+
+It owns no new arithmetic -- it wires the drop-in modules exactly like the reference's AANet does --
+but adds what a B=1 latency-bound path needs on a B200: fp32 (non-TF32) cuDNN glue so results meet the
+1e-4 parity bar, CUDA-graph capture of the whole path (hundreds of small launches per pair), and a
+double-buffered host entry point (pinned H2D copy of the next pair overlapped with the current one).
+"""
+import contextlib
+
+import torch
+import torch.nn as nn
+
+from .nets import AdaptiveAggregation, CostVolumePyramid, DisparityEstimation
+
+
+@contextlib.contextmanager
+def exact_fp32():
+    """cuDNN/cuBLAS TF32 off: the reference's convs would otherwise wobble at ~1e-3 on B200."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        yield
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+class HotPath(nn.Module):
+    def __init__(self, max_disp=192, num_scales=3, num_fusions=6, num_stage_blocks=1, num_deform_blocks=3,
+                 deformable_groups=2, mdconv_dilation=2, intermediate_supervision=False):
+        super().__init__()
+        self.max_disp = max_disp // 3                       # aanet.py:59
+        self.cost_volume = CostVolumePyramid(self.max_disp)
+        self.aggregation = AdaptiveAggregation(self.max_disp, num_scales=num_scales, num_fusions=num_fusions,
+                                               num_stage_blocks=num_stage_blocks,
+                                               num_deform_blocks=num_deform_blocks,
+                                               mdconv_dilation=mdconv_dilation,
+                                               deformable_groups=deformable_groups,
+                                               intermediate_supervision=intermediate_supervision)
+        self.disparity_estimation = DisparityEstimation(self.max_disp, True)
+        self._graphs = {}
+
+    def forward(self, left_pyramid, right_pyramid):
+        """Feature pyramids (finest first) -> list of disparities, coarse to fine (aanet.py:156-167)."""
+        with exact_fp32():
+            cost = self.cost_volume(list(left_pyramid), list(right_pyramid))
+            agg = self.aggregation(cost)
+            return [self.disparity_estimation(a) for a in reversed(agg)]
+
+    # ------------------------------------------------------------------ CUDA graph
+    @torch.no_grad()
+    def capture(self, left_pyramid, right_pyramid, warmup=3):
+        """Capture forward() on the given STATIC input tensors; returns (graph, outputs).  Replaying the
+        graph recomputes `outputs` in place from whatever the input tensors hold."""
+        assert not self.training
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.forward(left_pyramid, right_pyramid)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            outs = self.forward(left_pyramid, right_pyramid)
+        return graph, outs
+
+
+class HostPipeline:
+    """Host-buffer entry point: pinned feature pyramids in, pinned disparity out, H2D/D2H inside.
+
+    Two device slots; while slot k computes (graph replay on the compute stream), slot k^1 receives the
+    next pair on the copy stream.  `submit()` enqueues one pair and returns; `result(i)` synchronises on
+    that pair's event and returns its pinned disparity."""
+
+    def __init__(self, hot_path, shapes, device, n_slots=2):
+        self.hp, self.device, self.n = hot_path, device, n_slots
+        self.copy_stream = torch.cuda.Stream(device)
+        self.compute_stream = torch.cuda.Stream(device)
+        self.slots = []
+        for _ in range(n_slots):
+            L = [torch.zeros(s, device=device) for s in shapes]
+            R = [torch.zeros(s, device=device) for s in shapes]
+            with torch.cuda.stream(self.compute_stream):
+                graph, outs = hot_path.capture(L, R)
+            torch.cuda.synchronize(device)
+            host_out = torch.empty(outs[-1].shape, pin_memory=True)
+            self.slots.append(dict(L=L, R=R, graph=graph, out=outs[-1], host=host_out,
+                                   copied=torch.cuda.Event(), done=torch.cuda.Event(),
+                                   free=torch.cuda.Event()))
+            self.slots[-1]["free"].record(self.compute_stream)
+        self.i = 0
+        self.h2d_bytes = 2 * sum(4 * int(torch.tensor(s).prod()) for s in shapes)
+        self.d2h_bytes = 4 * self.slots[0]["out"].numel()
+
+    def submit(self, left_host, right_host):
+        s = self.slots[self.i % self.n]
+        self.i += 1
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(s["free"])          # previous user of this slot has finished
+            for dst, src in zip(s["L"] + s["R"], list(left_host) + list(right_host)):
+                dst.copy_(src, non_blocking=True)
+            s["copied"].record(self.copy_stream)
+        with torch.cuda.stream(self.compute_stream):
+            self.compute_stream.wait_event(s["copied"])
+            s["graph"].replay()
+            s["host"].copy_(s["out"], non_blocking=True)
+            s["done"].record(self.compute_stream)
+            s["free"].record(self.compute_stream)
+        return s
+
+    @staticmethod
+    def result(slot):
+        slot["done"].synchronize()
+        return slot["host"]

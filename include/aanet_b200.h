@@ -1,0 +1,143 @@
+/*
+ * aanet_b200 -- C-ABI of the B200-native AANet hot path (libaanet_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every entry point
+ *   - takes raw DEVICE pointers to caller-owned, contiguous NCHW fp32 buffers,
+ *   - writes its outputs completely (no pre-zero requirement, unlike the reference whose
+ *     callee zeroes `output`, deform_conv_cuda.cpp:530, and whose caller passes zeros_like
+ *     gradients, deform_conv.py:156-160),
+ *   - never allocates, never synchronises the device, keeps no global mutable state,
+ *   - enqueues its kernels on `stream` (a cudaStream_t / CUstream passed as void*; NULL is the
+ *     legacy default stream) and is safe under CUDA-graph capture,
+ *   - returns an aanet_status (0 = ok).  Launch failures are returned, not printf'd and
+ *     swallowed as in deform_conv_cuda_kernel.cu:794-798.
+ *
+ * Reference citations (path:line) are relative to the upstream repository
+ * wuzhongwulidong/aanet.  INTEGRATION.md shows the reference-side binding.
+ */
+#ifndef AANET_B200_H_
+#define AANET_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AANET_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define AANET_API __attribute__((visibility("default")))
+#else
+#define AANET_API
+#endif
+
+enum aanet_status {
+    AANET_OK = 0,
+    AANET_ERR_NULL = 1,        /* a required pointer is NULL                                   */
+    AANET_ERR_SHAPE = 2,       /* non-positive / inconsistent dimensions (cpp:497-516 checks)  */
+    AANET_ERR_UNSUPPORTED = 3, /* legal for the reference but outside what the kernels cover   */
+    AANET_ERR_WORKSPACE = 4,   /* workspace NULL or smaller than *_workspace_bytes()           */
+    AANET_ERR_LAUNCH = 5       /* cudaGetLastError() != cudaSuccess after a launch             */
+};
+
+/* ABI version of the loaded library, and a static string for a status code. */
+AANET_API int aanet_abi_version(void);
+AANET_API const char *aanet_status_string(int status);
+/* Last CUDA error string recorded by a failing launch on this host thread ("" if none). */
+AANET_API const char *aanet_last_cuda_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Correlation cost volume.  Replaces CostVolume.forward, correlation branch
+ * (nets/cost.py:40-48), called per scale by CostVolumePyramid.forward (nets/cost.py:64-76).
+ *   cost[b,d,h,w] = (1/C) * sum_c L[b,c,h,w] * R[b,c,h,w-d]   for w >= d,  exactly 0 for w < d
+ * L, R: [B,C,H,W]   cost: [B,D,H,W]
+ * ------------------------------------------------------------------------------------------- */
+AANET_API int aanet_corr_fwd(const float *L, const float *R, float *cost,
+                   int B, int C, int H, int W, int D, void *stream);
+
+/* Gradient of the above (the reference gets it from autograd of cost.py:45-48).
+ * gcost: [B,D,H,W]   gL, gR: [B,C,H,W] (overwritten) */
+AANET_API int aanet_corr_bwd(const float *L, const float *R, const float *gcost, float *gL, float *gR,
+                   int B, int C, int H, int W, int D, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Soft-argmin disparity regression.  Replaces DisparityEstimation.forward
+ * (nets/estimation.py:13-30):  disp[b,h,w] = sum_d d * softmax_d(sign * cost[b,:,h,w]),
+ * sign = +1 when `similarity` != 0 (match_similarity=True, aanet.py:113), else -1.
+ * cost: [B,D,H,W]   disp: [B,H,W]
+ * ------------------------------------------------------------------------------------------- */
+AANET_API int aanet_softargmin_fwd(const float *cost, float *disp,
+                         int B, int D, int H, int W, int similarity, void *stream);
+
+/* gcost[b,d,h,w] = sign * gdisp[b,h,w] * p_d * (d - disp[b,h,w])  (overwritten) */
+AANET_API int aanet_softargmin_bwd(const float *cost, const float *gdisp, float *gcost,
+                         int B, int D, int H, int W, int similarity, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Modulated deformable convolution (DCNv2), the ISA operator.  Replaces the pybind entry points
+ * modulated_deform_conv_cuda_forward / _backward (nets/deform_conv/src/deform_conv_cuda.cpp:490-
+ * 569, :571-685, bound at :687-701) and the three kernels behind them
+ * (deform_conv_cuda_kernel.cu:570-633, :635-693, :695-767).  With mask == NULL it is DCNv1
+ * (deform_conv_forward_cuda & co., cpp:152-488; mask == 1).
+ *
+ *   x      [B, Cin, H, W]
+ *   offset [B, dg*2*kh*kw, Ho, Wo]   channel (g*kh*kw + k)*2 + {0: dh, 1: dw}
+ *   mask   [B, dg*kh*kw,   Ho, Wo]   or NULL
+ *   weight [Cout, Cin/groups, kh, kw]
+ *   bias   [Cout] or NULL (the reference passes a fake 1-element tensor, deform_conv.py:133)
+ *   out    [B, Cout, Ho, Wo],  Ho = (H + 2*pad - (dil*(kh-1)+1))/stride + 1, same for Wo
+ * A sampling point contributes 0 unless -1 < h < H and -1 < w < W; each of its four corners is
+ * zero-padded individually (cu:467-497, :618).
+ *
+ * Epilogue extension (not in the reference op; used by the drop-in's fused inference path,
+ * SURVEY.md 8f rank 1): when post_scale/post_shift are non-NULL the result is
+ * out = act(out * post_scale[o] + post_shift[o]) with act = ReLU if relu != 0.  Pass
+ * NULL, NULL, 0 for the reference semantics.
+ *
+ * Workspace: query with aanet_mdcn_workspace_bytes(); may be 0, then ws may be NULL.
+ * ------------------------------------------------------------------------------------------- */
+AANET_API size_t aanet_mdcn_workspace_bytes(int backward, int B, int Cin, int H, int W, int Cout,
+                                  int kh, int kw, int stride, int pad, int dil,
+                                  int groups, int dg);
+
+AANET_API int aanet_mdcn_fwd(const float *x, const float *offset, const float *mask,
+                   const float *weight, const float *bias, float *out,
+                   int B, int Cin, int H, int W, int Cout, int kh, int kw,
+                   int stride, int pad, int dil, int groups, int dg,
+                   const float *post_scale, const float *post_shift, int relu,
+                   void *ws, size_t ws_bytes, void *stream);
+
+/* All five gradients are overwritten.  gmask may be NULL iff mask is NULL; gbias may be NULL.
+ * gx's summation order is not fixed (float atomics, as in the reference, cu:688). */
+AANET_API int aanet_mdcn_bwd(const float *x, const float *offset, const float *mask,
+                   const float *weight, const float *gout,
+                   float *gx, float *goffset, float *gmask, float *gweight, float *gbias,
+                   int B, int Cin, int H, int W, int Cout, int kh, int kw,
+                   int stride, int pad, int dil, int groups, int dg,
+                   void *ws, size_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Cross-scale aggregation fuse.  Replaces the resize + sum + LeakyReLU tail of
+ * AdaptiveAggregationModule.forward (nets/aggregation.py:387-400):
+ *   out = LeakyReLU_slope( (t0 + r(t1)) + r(t2) ... ),  r = bilinear resize to (H,W) with
+ *   align_corners=False when the term's (th,tw) differs from (H,W) (:394-396), identity
+ *   otherwise.  Summation order is the reference's (j = 0, 1, 2).
+ * terms / gterms: HOST arrays of n_terms (<= AANET_CSA_MAX_TERMS) DEVICE pointers, term t being
+ * [B, C, th[t], tw[t]];  th, tw: HOST int arrays.   out: [B,C,H,W].
+ * ------------------------------------------------------------------------------------------- */
+#define AANET_CSA_MAX_TERMS 4
+
+AANET_API int aanet_csa_fuse_fwd(const float *const *terms, const int *th, const int *tw, int n_terms,
+                       float *out, int B, int C, int H, int W, float slope, void *stream);
+
+/* gterms[t] (NULL = not wanted) = adjoint of term t's path applied to gout * LeakyReLU'(pre-activation); the sign of
+ * the pre-activation is read from `out` (slope must be > 0).  Deterministic (gather form). */
+AANET_API int aanet_csa_fuse_bwd(const float *out, const float *gout, float *const *gterms,
+                       const int *th, const int *tw, int n_terms,
+                       int B, int C, int H, int W, float slope, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AANET_B200_H_ */

@@ -1,0 +1,120 @@
+"""GPU tests of the drop-in modules (reference API) against golden outputs of the reference's own
+modules and against the CPU port (oracle/torch_port.py) at larger sizes."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import torch_port as port
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _fp32_convs():
+    """The parity bar (1e-4) needs true fp32 in the cuDNN glue convs (SURVEY.md section 7 pitfalls)."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _sd(z, pre):
+    return {k[len(pre):]: torch.from_numpy(v) for k, v in z.items() if k.startswith(pre)}
+
+
+def npy(t):
+    return t.detach().float().cpu().numpy()
+
+
+def test_deform_conv2d_golden(golden):
+    import aanet_b200.nets as n
+    z = golden("deform_layer")
+    layer = n.DeformConv2d(8, 8, dilation=2, deformable_groups=2)
+    layer.load_state_dict(_sd(z, "dc2d_sd/"), strict=True)
+    layer.cuda()
+    out = layer(torch.from_numpy(z["dc2d_x"]).cuda())
+    assert rel_err(npy(out), z["dc2d_out"]) < 1e-4
+
+
+@pytest.mark.parametrize("grad", [False, True])
+def test_deform_bottleneck_golden(golden, grad):
+    import aanet_b200.nets as n
+    z = golden("deform_layer")
+    blk = n.DeformSimpleBottleneck(8, 8, mdconv_dilation=2, deformable_groups=2)
+    blk.load_state_dict(_sd(z, "blk_sd/"), strict=True)
+    blk.cuda().eval()
+    x = torch.from_numpy(z["blk_x"]).cuda()
+    with torch.set_grad_enabled(grad):        # grad=False takes the fused BN+ReLU epilogue
+        out = blk(x)
+    assert rel_err(npy(out), z["blk_out"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["agg", "agg_inter"])
+@pytest.mark.parametrize("grad", [False, True])
+def test_hot_path_golden(golden, name, grad):
+    """CostVolumePyramid -> AdaptiveAggregation -> DisparityEstimation vs the reference's outputs."""
+    import aanet_b200.nets as n
+    z = golden(name)
+    D0, inter = int(z["D0"]), bool(z["inter"])
+    agg = n.AdaptiveAggregation(D0, num_scales=3, num_fusions=6, num_stage_blocks=1, num_deform_blocks=3,
+                                intermediate_supervision=inter, deformable_groups=2, mdconv_dilation=2)
+    missing, unexpected = agg.load_state_dict(_sd(z, "sd/"), strict=False)
+    assert not unexpected and all(k.endswith("num_batches_tracked") for k in missing)
+    agg.cuda().eval()
+    Ls = [torch.from_numpy(z["L%d" % s]).cuda() for s in range(3)]
+    Rs = [torch.from_numpy(z["R%d" % s]).cuda() for s in range(3)]
+    with torch.set_grad_enabled(grad):
+        costs = n.CostVolumePyramid(D0)(Ls, Rs)
+        for s in range(3):
+            assert rel_err(npy(costs[s]), z["cost%d" % s]) < 1e-4
+        outs = agg(costs)
+        est = n.DisparityEstimation(D0)
+        disps = [est(o) for o in reversed(outs)]
+    assert len(outs) == (3 if inter else 1)
+    for i, o in enumerate(outs):
+        assert rel_err(npy(o), z["agg%d" % i]) < 1e-4
+    for i, d in enumerate(disps):
+        assert np.abs(npy(d) - z["disp%d" % i]).max() < 1e-3
+
+
+def test_hot_path_vs_port_midsize():
+    """Random-init AANet-shaped aggregation (D0=32, 48x96 at the 1/3 scale) against the CPU port."""
+    import aanet_b200.nets as n
+    torch.manual_seed(326)
+    D0, H, W, C = 32, 48, 96, 32
+    agg = n.AdaptiveAggregation(D0, num_deform_blocks=3, intermediate_supervision=False).eval()
+    for name, m in agg.named_modules():       # non-trivial offsets / BN statistics
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.8, 1.2)
+        if name.endswith("offset_conv"):
+            torch.nn.init.normal_(m.weight, std=0.05); torch.nn.init.normal_(m.bias, std=0.5)
+    Ls = [torch.relu(torch.randn(2, C, H >> s, W >> s)) for s in range(3)]
+    Rs = [torch.relu(torch.randn(2, C, H >> s, W >> s)) for s in range(3)]
+    sd = {k: v.clone() for k, v in agg.state_dict().items()}
+    ref = port.hot_path(Ls, Rs, sd, D0, corr_c=True)
+    agg.cuda()
+    with torch.no_grad():
+        costs = n.CostVolumePyramid(D0)([t.cuda() for t in Ls], [t.cuda() for t in Rs])
+        outs = agg(costs)
+        disp = n.DisparityEstimation(D0)(outs[0])
+    assert np.abs(npy(disp) - ref[-1].numpy()).max() < 1e-3
+
+
+def test_training_step_runs():
+    """fwd + bwd through the drop-in modules in train mode (BN batch statistics, autograd kernels)."""
+    import aanet_b200.nets as n
+    torch.manual_seed(0)
+    agg = n.AdaptiveAggregation(16, num_deform_blocks=3, intermediate_supervision=True).cuda().train()
+    for name, m in agg.named_modules():
+        if name.endswith("offset_conv"):
+            torch.nn.init.normal_(m.weight, std=0.05)
+    Ls = [torch.relu(torch.randn(2, 8, 24 >> s, 36 >> s, device="cuda")).requires_grad_() for s in range(3)]
+    Rs = [torch.relu(torch.randn(2, 8, 24 >> s, 36 >> s, device="cuda")) for s in range(3)]
+    outs = agg(n.CostVolumePyramid(16)(Ls, Rs))
+    loss = sum(n.DisparityEstimation(16)(o).mean() for o in outs)
+    loss.backward()
+    assert all(torch.isfinite(l.grad).all() for l in Ls)
+    g = agg.fusions[3].branches[0][0].conv2.offset_conv.weight.grad
+    assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0

@@ -1,0 +1,252 @@
+"""GPU parity tests: the sm_100a kernels (through the C-ABI / drop-in modules) against the CPU oracle
+and the golden fixtures made from the reference's own code.
+
+Tolerances (BASELINE.json north_star): fp32 volumes within 1e-4 relative (max|a-b| / max|b|),
+disparity within 1e-3 px max abs.  Gradients: 1e-4 relative against the float64-accumulating oracle
+(the reference's own grad_input uses float atomics, SURVEY.md section 7 "Backward determinism").
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+VOL_TOL = 1e-4
+GRAD_TOL = 1e-4
+DISP_TOL = 1e-3
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+def npy(t):
+    return t.detach().float().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import aanet_b200.ops as o
+    return o
+
+
+# ------------------------------------------------------------------------------------ correlation
+@pytest.mark.parametrize("tag", ["a", "narrow", "c1", "c128"])
+def test_corr_golden(ops, golden, tag):
+    z = golden("corr")
+    L, R = cu(z[tag + "_L"]).requires_grad_(), cu(z[tag + "_R"]).requires_grad_()
+    out = ops.correlation(L, R, int(z[tag + "_D"]))
+    assert rel_err(npy(out), z[tag + "_out"]) < VOL_TOL
+    gL, gR = torch.autograd.grad(out, (L, R), cu(z[tag + "_g"]))
+    assert rel_err(npy(gL), z[tag + "_gL"]) < GRAD_TOL
+    assert rel_err(npy(gR), z[tag + "_gR"]) < GRAD_TOL
+
+
+@pytest.mark.parametrize("shape", [(1, 32, 6, 200, 64), (2, 16, 3, 131, 96), (1, 8, 4, 30, 48),
+                                   (1, 128, 2, 416, 64), (3, 5, 1, 257, 7)])
+def test_corr_oracle(ops, shape):
+    B, C, H, W, D = shape
+    rng = np.random.default_rng(326)
+    L = np.maximum(rng.standard_normal((B, C, H, W)), 0).astype(np.float32)
+    R = np.maximum(rng.standard_normal((B, C, H, W)), 0).astype(np.float32)
+    g = rng.standard_normal((B, D, H, W)).astype(np.float32)
+    Lc, Rc = cu(L).requires_grad_(), cu(R).requires_grad_()
+    out = ops.correlation(Lc, Rc, D)
+    ref = orc.corr_fwd(L, R, D)
+    assert rel_err(npy(out), ref) < VOL_TOL
+    o = npy(out)
+    for d in range(1, D):      # the w<d triangle is exactly zero (cost.py:41 new_zeros)
+        assert np.all(o[:, d, :, :min(d, W)] == 0.0)
+    gL, gR = torch.autograd.grad(out, (Lc, Rc), cu(g))
+    rL, rR = orc.corr_bwd(L, R, g)
+    assert rel_err(npy(gL), rL) < GRAD_TOL
+    assert rel_err(npy(gR), rR) < GRAD_TOL
+
+
+def test_corr_full_size_properties(ops):
+    """KITTI 1/3 scale (BASELINE config 2): linearity in L, zero band, d=0 plane = channel mean."""
+    torch.manual_seed(326)
+    L = torch.relu(torch.randn(1, 128, 128, 416, device="cuda"))
+    L2 = torch.relu(torch.randn(1, 128, 128, 416, device="cuda"))
+    R = torch.relu(torch.randn(1, 128, 128, 416, device="cuda"))
+    a, b2 = ops.correlation(L, R, 64), ops.correlation(L2, R, 64)
+    s = ops.correlation(L + 2 * L2, R, 64)
+    assert rel_err(npy(s), npy(a + 2 * b2)) < 1e-5
+    assert rel_err(npy(a[:, 0]), npy((L * R).mean(1))) < 1e-5
+    for d in (1, 17, 63):
+        assert torch.all(a[:, d, :, :d] == 0)
+        assert rel_err(npy(a[:, d, :, d:]), npy((L[..., d:] * R[..., :-d]).mean(1))) < 1e-5
+
+
+# ------------------------------------------------------------------------------------ soft-argmin
+@pytest.mark.parametrize("tag", ["sim", "cost", "d1", "peaky"])
+def test_softargmin_golden(ops, golden, tag):
+    z = golden("softargmin")
+    c = cu(z[tag + "_cost"]).requires_grad_()
+    disp = ops.soft_argmin(c, bool(z[tag + "_sim"]))
+    assert np.abs(npy(disp) - z[tag + "_disp"]).max() < DISP_TOL
+    gc, = torch.autograd.grad(disp, c, cu(z[tag + "_g"]))
+    assert rel_err(npy(gc), z[tag + "_gcost"]) < GRAD_TOL
+
+
+@pytest.mark.parametrize("shape", [(1, 64, 128, 416), (2, 32, 7, 9), (1, 16, 32, 104), (1, 96, 5, 13),
+                                   (1, 3, 1, 1)])
+@pytest.mark.parametrize("sim", [True, False])
+def test_softargmin_oracle(ops, shape, sim):
+    rng = np.random.default_rng(7)
+    c = (rng.standard_normal(shape) * 4).astype(np.float32)
+    g = rng.standard_normal((shape[0],) + shape[2:]).astype(np.float32)
+    cc = cu(c).requires_grad_()
+    disp = ops.soft_argmin(cc, sim)
+    assert np.abs(npy(disp) - orc.softargmin_fwd(c, sim)).max() < DISP_TOL
+    gc, = torch.autograd.grad(disp, cc, cu(g))
+    assert rel_err(npy(gc), orc.softargmin_bwd(c, g, sim)) < GRAD_TOL
+
+
+def test_softargmin_properties(ops):
+    torch.manual_seed(1)
+    c = torch.randn(1, 64, 128, 416, device="cuda") * 3
+    d0 = ops.soft_argmin(c, True)
+    assert torch.all((d0 >= 0) & (d0 <= 63))
+    assert (ops.soft_argmin(c + 5.0, True) - d0).abs().max() < 1e-3      # shift invariance
+    onehot = torch.full((1, 64, 4, 8), -1e4, device="cuda")
+    onehot[:, 37] = 0
+    assert (ops.soft_argmin(onehot, True) - 37).abs().max() < 1e-5
+
+
+# ------------------------------------------------------------------------------------ mdconv
+def _mdcn_case(z, tag):
+    st, pad, dil, grp, dg, has_b = [int(v) for v in z[tag + "_cfg"]]
+    return dict(stride=st, pad=pad, dil=dil, groups=grp, dg=dg, has_b=has_b)
+
+
+@pytest.mark.parametrize("tag", ["isa", "s2", "grp", "far", "k1", "v1"])
+def test_mdcn_golden(ops, golden, tag):
+    z = golden("mdcn")
+    c = _mdcn_case(z, tag)
+    x = cu(z[tag + "_x_f64"]).requires_grad_()
+    off = cu(z[tag + "_off_f64"]).requires_grad_()
+    w = cu(z[tag + "_w_f64"]).requires_grad_()
+    b = cu(z[tag + "_b_f64"]).requires_grad_() if c["has_b"] else None
+    if tag == "v1":
+        out = ops.deform_conv(x, off, w, c["stride"], c["pad"], c["dil"], c["groups"], c["dg"])
+        params = (x, off, w)
+    else:
+        m = cu(z[tag + "_mask_f64"]).requires_grad_()
+        out = ops.modulated_deform_conv(x, off, m, w, b, c["stride"], c["pad"], c["dil"], c["groups"], c["dg"])
+        params = (x, off, m, w) + ((b,) if b is not None else ())
+    assert rel_err(npy(out), z[tag + "_out_f64"]) < VOL_TOL
+    grads = torch.autograd.grad(out, params, cu(z[tag + "_g_f64"]))
+    names = ["gx", "goff", "gw"] if tag == "v1" else ["gx", "goff", "gmask", "gw"] + (["gb"] if b is not None else [])
+    for n, g in zip(names, grads):
+        assert rel_err(npy(g), z["%s_%s_f64" % (tag, n)]) < GRAD_TOL, n
+
+
+@pytest.mark.parametrize("cfg", [
+    # B, Cin, Cout, H, W, stride, dil, groups, dg, bias
+    (1, 64, 64, 24, 52, 1, 2, 1, 2, False),      # ISA shape, small plane
+    (2, 32, 32, 16, 26, 1, 2, 1, 2, False),
+    (1, 16, 16, 8, 13, 1, 2, 1, 2, False),
+    (1, 24, 40, 15, 17, 2, 1, 1, 4, True),       # stride 2, Cin != Cout
+    (1, 96, 96, 9, 11, 1, 2, 1, 8, False),
+    (2, 12, 18, 10, 10, 1, 1, 3, 2, True),       # conv groups straddling deformable groups
+    (1, 128, 128, 6, 20, 1, 2, 1, 1, False),     # two output tiles
+])
+def test_mdcn_oracle(ops, cfg):
+    B, Ci, Co, H, W, st, dil, grp, dg, bias = cfg
+    rng = np.random.default_rng(11)
+    k, pad = 3, dil
+    Ho, Wo = orc.mdcn_out_hw(H, W, k, st, pad, dil)
+    x = rng.standard_normal((B, Ci, H, W)).astype(np.float32)
+    off = (2 * rng.standard_normal((B, dg * 18, Ho, Wo))).astype(np.float32)
+    msk = (2 / (1 + np.exp(-rng.standard_normal((B, dg * 9, Ho, Wo))))).astype(np.float32)
+    w = (rng.standard_normal((Co, Ci // grp, k, k)) / np.sqrt(Ci * 9)).astype(np.float32)
+    b = rng.standard_normal(Co).astype(np.float32) if bias else None
+    g = rng.standard_normal((B, Co, Ho, Wo)).astype(np.float32)
+    xc, oc, mc, wc = [cu(a).requires_grad_() for a in (x, off, msk, w)]
+    bc = cu(b).requires_grad_() if bias else None
+    out = ops.modulated_deform_conv(xc, oc, mc, wc, bc, st, pad, dil, grp, dg)
+    ref = orc.mdcn_fwd(x, off, msk, w, b, st, pad, dil, grp, dg)
+    assert rel_err(npy(out), ref) < VOL_TOL
+    grads = torch.autograd.grad(out, (xc, oc, mc, wc) + ((bc,) if bias else ()), cu(g))
+    rg = orc.mdcn_bwd(x, off, msk, w, g, bias, st, pad, dil, grp, dg)
+    for n, a, r in zip(["gx", "goff", "gmask", "gw", "gb"], grads, rg):
+        assert rel_err(npy(a), r) < GRAD_TOL, n
+
+
+def test_mdcn_zero_offset_is_dilated_conv(ops):
+    """Full ISA size: with offset = 0 and mask = 1 the op is an ordinary dilated conv (deform.py:75-76)."""
+    torch.manual_seed(3)
+    x = torch.randn(1, 64, 128, 416, device="cuda")
+    w = torch.randn(64, 64, 3, 3, device="cuda") / 24
+    off = torch.zeros(1, 36, 128, 416, device="cuda")
+    m = torch.ones(1, 18, 128, 416, device="cuda")
+    out = ops.modulated_deform_conv(x, off, m, w, None, 1, 2, 2, 1, 2)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = torch.nn.functional.conv2d(x, w, padding=2, dilation=2)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert rel_err(npy(out), npy(ref)) < VOL_TOL
+
+
+def test_mdcn_fused_epilogue(ops):
+    torch.manual_seed(5)
+    x = torch.randn(2, 16, 9, 12, device="cuda")
+    off = torch.randn(2, 36, 9, 12, device="cuda")
+    m = torch.rand(2, 18, 9, 12, device="cuda") * 2
+    w = torch.randn(16, 16, 3, 3, device="cuda") / 12
+    sc, sh = torch.rand(16, device="cuda") + 0.5, torch.randn(16, device="cuda")
+    plain = ops.modulated_deform_conv(x, off, m, w, None, 1, 2, 2, 1, 2)
+    fused = ops.modulated_deform_conv_fused(x, off, m, w, None, 1, 2, 2, 1, 2, sc, sh, True)
+    ref = torch.relu(plain * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1))
+    assert rel_err(npy(fused), npy(ref)) < 1e-5
+
+
+# ------------------------------------------------------------------------------------ CSA fuse
+@pytest.mark.parametrize("tag", ["x2x4", "odd", "same", "two"])
+def test_csa_golden(ops, golden, tag):
+    z = golden("csa")
+    n = int(z[tag + "_n"])
+    terms = [cu(z["%s_t%d" % (tag, i)]).requires_grad_() for i in range(n)]
+    out = ops.csa_fuse(terms, 0.2)
+    assert rel_err(npy(out), z[tag + "_out"]) < 1e-5
+    grads = torch.autograd.grad(out, terms, cu(z[tag + "_g"]))
+    for i in range(n):
+        assert rel_err(npy(grads[i]), z["%s_gt%d" % (tag, i)]) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [((1, 64, 128, 416), [(128, 416), (64, 208), (32, 104)]),
+                                   ((2, 5, 31, 45), [(31, 45), (16, 23), (8, 12)]),
+                                   ((1, 16, 32, 104), [(32, 104), (32, 104), (32, 104)])])
+def test_csa_oracle(ops, shape):
+    (B, C, H, W), ths = shape
+    rng = np.random.default_rng(2)
+    terms = [rng.standard_normal((B, C, h, w)).astype(np.float32) for h, w in ths]
+    g = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    tc = [cu(t).requires_grad_() for t in terms]
+    out = ops.csa_fuse(tc, 0.2)
+    ref = orc.csa_fuse_fwd(terms, (H, W), 0.2)
+    assert rel_err(npy(out), ref) < 1e-5
+    grads = torch.autograd.grad(out, tc, cu(g))
+    rg = orc.csa_fuse_bwd(ref, g, ths, 0.2)
+    for a, r in zip(grads, rg):
+        assert rel_err(npy(a), r) < 1e-5
+
+
+# ------------------------------------------------------------------------------------ error behaviour
+def test_errors(ops):
+    x = torch.randn(1, 4, 5, 5)
+    with pytest.raises(NotImplementedError):          # deform_conv.py:135-136
+        ops.modulated_deform_conv(x, x, x, x, None, 1, 1, 1, 1, 1)
+    xc = torch.randn(1, 4, 5, 5, device="cuda")
+    with pytest.raises(RuntimeError):                 # cpp:512-516 channel mismatch
+        ops.modulated_deform_conv(xc, torch.zeros(1, 18, 5, 5, device="cuda"),
+                                  torch.ones(1, 9, 5, 5, device="cuda"),
+                                  torch.randn(4, 3, 3, 3, device="cuda"), None, 1, 1, 1, 1, 1)
+    with pytest.raises(TypeError):
+        ops.soft_argmin(xc.double(), True)
