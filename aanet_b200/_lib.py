@@ -25,6 +25,8 @@ SIGNATURES = {
     "aanet_mdcn_workspace_bytes": (_sz, [_i] * 13),
     "aanet_mdcn_fwd": (_i, [_vp] * 6 + [_i] * 12 + [_vp, _vp, _i, _vp, _sz, _vp]),
     "aanet_mdcn_bwd": (_i, [_vp] * 10 + [_i] * 12 + [_vp, _sz, _vp]),
+    "aanet_conv2d_workspace_bytes": (_sz, [_i] * 11),
+    "aanet_conv2d_fwd": (_i, [_vp] * 6 + [_i, _f, _vp] + [_i] * 11 + [_vp, _sz, _vp]),
     "aanet_csa_fuse_fwd": (_i, [_vp, _vp, _vp, _i, _vp] + [_i] * 4 + [_f, _vp]),
     "aanet_csa_fuse_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i] + [_i] * 4 + [_f, _vp]),
 }

@@ -13,6 +13,7 @@ from torch.autograd.function import once_differentiable
 from . import _lib
 
 LAUNCHES = 0   # number of C-ABI kernels-launching calls made by this process (bench bookkeeping)
+FORCE_GENERIC_MDCN = False   # tests: route mdconv forward to the shape-generic FFMA kernel (ws = NULL)
 
 
 def _count(n=1):
@@ -131,12 +132,16 @@ def _mdcn_forward(x, offset, mask, weight, bias, stride, pad, dil, groups, dg,
         raise _lib.AanetError("mask must be [%d,%d,%d,%d], got %s" % (B, dg * kh * kw, Ho, Wo,
                                                                        tuple(mask.shape)))
     out = x.new_empty(B, Cout, Ho, Wo)
+    lib = _lib.load()
+    nbytes = 0 if FORCE_GENERIC_MDCN else lib.aanet_mdcn_workspace_bytes(
+        0, B, Cin, H, W, Cout, kh, kw, stride, pad, dil, groups, dg)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device) if nbytes else None
     with torch.cuda.device(x.device):
-        _lib.check(_lib.load().aanet_mdcn_fwd(
+        _lib.check(lib.aanet_mdcn_fwd(
             _ptr(x), _ptr(offset), _ptr(mask), _ptr(weight), _ptr(bias), _ptr(out),
             B, Cin, H, W, Cout, kh, kw, stride, pad, dil, groups, dg,
-            _ptr(post_scale), _ptr(post_shift), int(relu), None, 0, _stream(x)), "aanet_mdcn_fwd")
-    _count()
+            _ptr(post_scale), _ptr(post_shift), int(relu), _ptr(ws), nbytes, _stream(x)), "aanet_mdcn_fwd")
+    _count(2 if nbytes else 1)
     return out
 
 
@@ -227,6 +232,37 @@ def modulated_deform_conv_fused(x, offset, mask, weight, bias, stride, padding, 
     return _mdcn_forward(x, offset, mask, _prep(weight, "mdconv"), _prep(bias, "mdconv"), stride, padding,
                          dilation, groups, deformable_groups, _prep(post_scale, "mdconv"),
                          _prep(post_shift, "mdconv"), relu)
+
+
+# ------------------------------------------------------------------------------------ dense conv
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+
+
+def conv2d_fused(x, weight, bias=None, scale=None, shift=None, residual=None, act=ACT_NONE, slope=0.2,
+                 stride=1, padding=0, dilation=1, groups=1):
+    """Inference-only dense convolution on the tcgen05 engine:
+    act((conv(x, w) + bias) * scale + shift + residual).  Replaces cuDNN conv + BatchNorm(eval) +
+    activation (+ residual add) of the ISA block / CSA exchange paths with one kernel."""
+    x, weight = _prep(x, "conv2d"), _prep(weight, "conv2d")
+    bias, scale, shift, residual = (_prep(t, "conv2d") for t in (bias, scale, shift, residual))
+    B, Cin, H, W = x.shape
+    Cout, cg, kh, kw = weight.shape
+    if Cin != cg * groups:
+        raise _lib.AanetError("Input shape and kernel channels wont match: (%d vs %d)." % (Cin, cg * groups))
+    Ho, Wo = _out_hw(H, W, kh, kw, stride, padding, dilation)
+    out = x.new_empty(B, Cout, Ho, Wo)
+    if residual is not None and residual.shape != out.shape:
+        raise ValueError("conv2d_fused: residual must have the output's shape")
+    lib = _lib.load()
+    nbytes = lib.aanet_conv2d_workspace_bytes(B, Cin, H, W, Cout, kh, kw, stride, padding, dilation, groups)
+    ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.aanet_conv2d_fwd(_ptr(x), _ptr(weight), _ptr(bias), _ptr(scale), _ptr(shift),
+                                        _ptr(residual), int(act), float(slope), _ptr(out), B, Cin, H, W, Cout,
+                                        kh, kw, stride, padding, dilation, groups, _ptr(ws), nbytes,
+                                        _stream(x)), "aanet_conv2d_fwd")
+    _count(2)
+    return out
 
 
 # ------------------------------------------------------------------------------------ CSA fuse

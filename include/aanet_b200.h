@@ -95,7 +95,10 @@ AANET_API int aanet_softargmin_bwd(const float *cost, const float *gdisp, float 
  * out = act(out * post_scale[o] + post_shift[o]) with act = ReLU if relu != 0.  Pass
  * NULL, NULL, 0 for the reference semantics.
  *
- * Workspace: query with aanet_mdcn_workspace_bytes(); may be 0, then ws may be NULL.
+ * Workspace: query with aanet_mdcn_workspace_bytes().  Forward: the workspace receives the tf32
+ * hi/lo-split, swizzled weights that the tcgen05 kernel streams; passing ws == NULL is legal and
+ * selects the shape-generic FFMA kernel instead (same results within fp32 rounding).  Backward: the
+ * workspace holds grad_weight partials and is required.
  * ------------------------------------------------------------------------------------------- */
 AANET_API size_t aanet_mdcn_workspace_bytes(int backward, int B, int Cin, int H, int W, int Cout,
                                   int kh, int kw, int stride, int pad, int dil,
@@ -116,6 +119,26 @@ AANET_API int aanet_mdcn_bwd(const float *x, const float *offset, const float *m
                    int B, int Cin, int H, int W, int Cout, int kh, int kw,
                    int stride, int pad, int dil, int groups, int dg,
                    void *ws, size_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense convolution with fused epilogue on the same tcgen05 engine (the
+ * 1x1 / 3x3 / strided / dilated / grouped convolutions of the ISA block and the CSA exchange paths,
+ * nets/deform.py:216-236, nets/aggregation.py:346-371, :443-450, which the reference runs as
+ * cuDNN conv + BatchNorm + activation kernels).
+ *   out = act( (conv(x, weight) + bias[o]) * scale[o] + shift[o] + residual )
+ * bias, scale/shift (both or neither), residual ([B,Cout,Ho,Wo]) may be NULL.
+ * act: 0 none, 1 ReLU, 2 LeakyReLU(slope).  pad is explicit (not derived from dil).
+ * Requires Cin/groups % 4 == 0 (else AANET_ERR_UNSUPPORTED) and the workspace.
+ * ------------------------------------------------------------------------------------------- */
+AANET_API size_t aanet_conv2d_workspace_bytes(int B, int Cin, int H, int W, int Cout, int kh, int kw,
+                                              int stride, int pad, int dil, int groups);
+
+AANET_API int aanet_conv2d_fwd(const float *x, const float *weight, const float *bias,
+                               const float *scale, const float *shift, const float *residual,
+                               int act, float slope, float *out,
+                               int B, int Cin, int H, int W, int Cout, int kh, int kw,
+                               int stride, int pad, int dil, int groups,
+                               void *ws, size_t ws_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Cross-scale aggregation fuse.  Replaces the resize + sum + LeakyReLU tail of

@@ -123,8 +123,17 @@ def _mdcn_case(z, tag):
     return dict(stride=st, pad=pad, dil=dil, groups=grp, dg=dg, has_b=has_b)
 
 
+@pytest.fixture(params=["umma", "generic"])
+def mdcn_path(request, ops):
+    """Run every mdconv forward test through both the tcgen05 engine (when the shape qualifies) and the
+    shape-generic FFMA kernel (workspace = NULL)."""
+    ops.FORCE_GENERIC_MDCN = request.param == "generic"
+    yield request.param
+    ops.FORCE_GENERIC_MDCN = False
+
+
 @pytest.mark.parametrize("tag", ["isa", "s2", "grp", "far", "k1", "v1"])
-def test_mdcn_golden(ops, golden, tag):
+def test_mdcn_golden(ops, golden, tag, mdcn_path):
     z = golden("mdcn")
     c = _mdcn_case(z, tag)
     x = cu(z[tag + "_x_f64"]).requires_grad_()
@@ -155,7 +164,7 @@ def test_mdcn_golden(ops, golden, tag):
     (2, 12, 18, 10, 10, 1, 1, 3, 2, True),       # conv groups straddling deformable groups
     (1, 128, 128, 6, 20, 1, 2, 1, 1, False),     # two output tiles
 ])
-def test_mdcn_oracle(ops, cfg):
+def test_mdcn_oracle(ops, cfg, mdcn_path):
     B, Ci, Co, H, W, st, dil, grp, dg, bias = cfg
     rng = np.random.default_rng(11)
     k, pad = 3, dil
@@ -177,7 +186,7 @@ def test_mdcn_oracle(ops, cfg):
         assert rel_err(npy(a), r) < GRAD_TOL, n
 
 
-def test_mdcn_zero_offset_is_dilated_conv(ops):
+def test_mdcn_zero_offset_is_dilated_conv(ops, mdcn_path):
     """Full ISA size: with offset = 0 and mask = 1 the op is an ordinary dilated conv (deform.py:75-76)."""
     torch.manual_seed(3)
     x = torch.randn(1, 64, 128, 416, device="cuda")
@@ -205,6 +214,43 @@ def test_mdcn_fused_epilogue(ops):
     fused = ops.modulated_deform_conv_fused(x, off, m, w, None, 1, 2, 2, 1, 2, sc, sh, True)
     ref = torch.relu(plain * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1))
     assert rel_err(npy(fused), npy(ref)) < 1e-5
+
+
+# ------------------------------------------------------------------------------------ dense conv engine
+@pytest.mark.parametrize("cfg", [
+    # B, Cin, Cout, H, W, k, stride, pad, dil, groups
+    (1, 64, 64, 128, 416, 1, 1, 0, 1, 1),     # ISA conv1 / conv3 at the 1/3 scale
+    (1, 64, 64, 40, 52, 3, 1, 1, 1, 1),       # SimpleBottleneck conv2
+    (2, 64, 54, 24, 40, 3, 1, 2, 2, 2),       # offset_conv: grouped, dilated, bias
+    (1, 64, 32, 33, 47, 3, 2, 1, 1, 1),       # CSA down path, stride 2, odd size
+    (1, 16, 64, 16, 26, 1, 1, 0, 1, 1),       # CSA up path 1x1
+    (2, 32, 32, 9, 300, 3, 1, 1, 1, 1),
+    (1, 8, 24, 7, 9, 3, 1, 1, 1, 1),
+    (1, 128, 128, 12, 20, 3, 1, 1, 1, 1),     # BN = 128
+    (1, 96, 96, 10, 14, 1, 1, 0, 1, 1),       # BN = 96
+])
+def test_conv2d_fused(ops, cfg):
+    B, Ci, Co, H, W, k, st, pad, dil, grp = cfg
+    torch.manual_seed(13)
+    x = torch.randn(B, Ci, H, W, device="cuda")
+    w = torch.randn(Co, Ci // grp, k, k, device="cuda") / (Ci * k * k / grp) ** 0.5
+    bias = torch.randn(Co, device="cuda")
+    scale, shift = torch.rand(Co, device="cuda") + 0.5, torch.randn(Co, device="cuda")
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = torch.nn.functional.conv2d(x.double(), w.double(), bias.double(), st, pad, dil, grp)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    res = torch.randn_like(ref).float()
+    out = ops.conv2d_fused(x, w, bias, None, None, None, ops.ACT_NONE, 0.2, st, pad, dil, grp)
+    assert rel_err(npy(out), npy(ref)) < 1e-5
+    full = ops.conv2d_fused(x, w, bias, scale, shift, res, ops.ACT_LEAKY, 0.2, st, pad, dil, grp)
+    ref2 = torch.nn.functional.leaky_relu(ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) + res, 0.2)
+    assert rel_err(npy(full), npy(ref2)) < 1e-5
+    relu = ops.conv2d_fused(x, w, None, scale, shift, None, ops.ACT_RELU, 0.0, st, pad, dil, grp)
+    ref3 = torch.relu((ref - bias.view(1, -1, 1, 1).double()) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    assert rel_err(npy(relu), npy(ref3)) < 1e-5
 
 
 # ------------------------------------------------------------------------------------ CSA fuse
