@@ -1,7 +1,6 @@
-// tcgen05 implicit-GEMM convolution engine (3xTF32), dense or deformable A-operand producer.
+// tcgen05 implicit-GEMM convolution engine (3xTF32) -- persistent, warp-specialised, channels-last.
 //
-// One CTA computes a [128 output pixels] x [BN output channels] tile of
-//      out[p, o] = sum_{tap, c} A[p, (tap,c)] * W[o, c, tap]
+// One launch computes  out[p, o] = epilogue( sum_{tap, c} A[p, (tap,c)] * W[o, c, tap] )  for all pixels,
 // where A is never materialised in HBM:
 //   * DEFORM: A[p,(tap,c)] = mask * bilinear(x[c], p*stride - pad + tap*dil + offset)   -- the ISA
 //     operator, replacing modulated_deformable_im2col + cuBLAS SGEMM of the reference
@@ -10,49 +9,69 @@
 //     strided / dilated / grouped convolutions around it (nets/deform.py:216-236, nets/aggregation.py:
 //     346-371, :443-450), with folded-BN scale/shift, bias, residual and activation in the epilogue.
 //
-// Blackwell mapping.  M = 128 pixels is the UMMA M (one TMEM lane per pixel), N = BN channels, K walks
-// (tap, channel) in blocks of 32 tf32 = one 128-byte swizzle row.  Warps 0-3 (one thread per pixel)
-// produce the A tile: they gather/interpolate, split every value into tf32 hi + lo (cvt.rna, exact
-// remainder) and store both as SWIZZLE_128B K-major tiles in shared memory; warp 5 streams the matching
-// pre-split, pre-swizzled weight block with one cp.async.bulk per stage; one thread of warp 4 issues
-// tcgen05.mma.kind::tf32 three times per K step (lo*hi + hi*lo + hi*hi -> fp32-grade accuracy, the
-// parity bar is 1e-4) into a TMEM accumulator and frees the stage with tcgen05.commit.  When the last
-// commit lands, warps 0-3 read the accumulator back with tcgen05.ld (lane = pixel -> coalesced NCHW
-// stores) and apply the epilogue.  Stages are handed over with mbarriers only; there is no
-// __syncthreads in the main loop.  Two CTAs fit per SM (96 KB each at BN<=64) so one tile's epilogue
-// overlaps the other's main loop.
+// Layout.  The engine reads x channels-last, [B][H*W][Cin]: the eight 16-byte chunks of one K row
+// (32 consecutive channels of one tap) are one contiguous 128-byte line per source pixel, so a gather
+// costs one L1 wavefront per (pixel, corner) whatever the learned offsets are, and a tile's input and
+// output are contiguous in HBM.  (Measured on the first, NCHW / one-thread-per-pixel version: 81 M
+// sectors per call for uncorrelated offsets, 1.7 TB/s on the dense 1x1, 15 k cycles to the first MMA.)
+// The epilogue writes channels-last or NCHW; the NCHW <-> NHWC conversions needed at the reference-
+// shaped boundary are done by transpose_kernel.
+//
+// Blackwell mapping.  A CTA is persistent (grid = #SMs) and walks 128-pixel tiles.  M = 128 pixels is
+// the UMMA M (one TMEM lane per pixel), N = BN output channels, K walks (tap, channel) in blocks of
+// 32 tf32 = one 128-byte swizzle row.  Warp roles:
+//   warps 0-7   A producers: lane = (pixel row, 16-byte chunk); LDG.128 (4 per item for DEFORM, 1 for
+//               DENSE), bilinear combine, split into tf32 hi + lo (cvt.rna + exact remainder), two
+//               STS.128 into SWIZZLE_128B K-major tiles; fence.proxy.async + mbarrier arrive.
+//   warp 13     streams the pre-split, pre-swizzled weight block of the stage with one cp.async.bulk.
+//   warp 12     one thread issues tcgen05.mma.kind::tf32 three times per K step (lo*hi + hi*lo + hi*hi:
+//               fp32-grade accuracy, the parity bar is 1e-4) into one of two TMEM accumulators and
+//               releases the stage with tcgen05.commit.
+//   warps 8-11  epilogue: tcgen05.ld (lane = pixel), bias / folded-BN affine / residual / activation,
+//               128-bit channels-last stores (or coalesced NCHW stores); runs one tile behind the MMA.
+// All hand-offs are mbarriers; the ring (4 stages at BN = 64) runs across tile boundaries.
 #include "mdcn_common.cuh"
 #include "umma.cuh"
 
 namespace aanet {
 
-constexpr int kUM = 128;            // pixels per tile (UMMA M)
-constexpr int kUK = 32;             // K per stage (one 128-byte swizzle row of tf32)
-constexpr int kUStages = 2;
-constexpr int kUThreads = 192;      // 4 producer/epilogue warps + MMA warp + weight-loader warp
-constexpr int kATileBytes = kUM * kUK * 4;   // 16 KB (hi) ; same for lo
+constexpr int kUM = 128;                 // pixels per tile (UMMA M)
+constexpr int kUK = 32;                  // K per stage (one 128-byte swizzle row of tf32)
+constexpr int kProdWarps = 8;
+constexpr int kMmaWarp = 12, kLoadWarp = 13;   // warps 8..11 are the epilogue (warp % 4 = TMEM lane quarter)
+constexpr int kUThreads = 14 * 32;
+constexpr int kATileBytes = kUM * kUK * 4;   // 16 KB (hi); same for lo
+constexpr int kSmemBudget = 200 * 1024;
 
 enum ConvAct { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_OFFSET_MASK = 3 };
 
 struct ConvParams {
-    const float *x, *offset, *mask;     // offset/mask only for DEFORM (mask may be NULL: DCNv1)
+    const float *x;                     // channels-last input [B][H*W][Cin]
+    const float *offset, *mask;         // DEFORM only; mask may be NULL (DCNv1)
+    long off_bs, off_ps, off_cs;        // offset strides in floats: batch, pixel, channel
+    long mask_bs, mask_ps, mask_cs;
     const float *wpack;                 // packed weights, see conv_pack_weights_kernel
-    float *out;
-    const float *bias, *scale, *shift, *residual;
-    int act; float slope; int n_offset_ch;       // ACT_OFFSET_MASK: channels >= n_offset_ch get 2*sigmoid
-    float mask_scale;
+    float *out;                         // [B][P][Cout] (out_nchw == 0) or [B][Cout][P]
+    int out_nchw;
+    const float *bias, *scale, *shift;  // per output channel, optional
+    const float *residual;              // same layout as out, optional
+    int act; float slope; int n_offset_ch; float mask_scale;
     MdcnDims d;
     int K, KB;                          // K = kh*kw*Cg, KB = ceil(K / 32)
     int n_tiles_n;                      // ceil(Og / BN)
     int tiles_per_img;                  // ceil(P / 128)
+    int n_ptiles;                       // B * tiles_per_img
+    int total_tiles;                    // groups * n_tiles_n * n_ptiles
 };
 
-template <int BN> struct TmemCols { static constexpr uint32_t value = BN <= 32 ? 32 : BN <= 64 ? 64 : 128; };
-
-template <int BN>
-constexpr size_t conv_umma_smem_bytes() {
-    return (size_t)kUStages * (2 * kATileBytes + 2 * BN * kUK * 4) + 1024;   // + alignment slack
-}
+template <int BN> struct EngineCfg {
+    static constexpr int kBTileBytes = BN * kUK * 4;
+    static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;
+    static constexpr int kStages = (kSmemBudget / kStageBytes) > 6 ? 6 : (kSmemBudget / kStageBytes);
+    static constexpr int kAccStride = BN <= 32 ? 32 : BN <= 64 ? 64 : 128;   // TMEM columns per accumulator
+    static constexpr uint32_t kTmemCols = 2 * kAccStride;                     // two accumulators
+    static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024;
+};
 
 // Swizzled position (in floats) of element (row, k) inside a [rows x 32] SWIZZLE_128B K-major tile.
 __host__ __device__ inline int sw128_index(int row, int k) {
@@ -85,180 +104,282 @@ __global__ void conv_pack_weights_kernel(const float *__restrict__ w, float *__r
     }
 }
 
+// [B][R][Cc] -> [B][Cc][R] through a 32x33 shared tile (both sides coalesced).  NCHW -> NHWC is
+// (R = C, Cc = HW) and NHWC -> NCHW is (R = HW, Cc = C).
+__global__ void __launch_bounds__(256)
+transpose_kernel(const float *__restrict__ src, float *__restrict__ dst, int R, long Cc) {
+    __shared__ float tile[32][33];
+    const long c0 = (long)blockIdx.x * 32;
+    const int r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+    const float *sb = src + (long)blockIdx.z * R * Cc;
+    float *db = dst + (long)blockIdx.z * R * Cc;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty + i * 8;
+        const long c = c0 + tx;
+        tile[ty + i * 8][tx] = (r < R && c < Cc) ? sb[(long)r * Cc + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long c = c0 + ty + i * 8;
+        const int r = r0 + tx;
+        if (r < R && c < Cc) db[c * R + r] = tile[tx][ty + i * 8];
+    }
+}
+
+struct TileCoord { int grp, nt, b; int p0; };
+
+__device__ __forceinline__ TileCoord tile_coord(const ConvParams &p, int t) {
+    TileCoord c;
+    const int pt = t % p.n_ptiles, gn = t / p.n_ptiles;
+    c.grp = gn / p.n_tiles_n; c.nt = gn % p.n_tiles_n;
+    c.b = pt / p.tiles_per_img;
+    c.p0 = (pt % p.tiles_per_img) * kUM;
+    return c;
+}
+
 template <int BN, bool DEFORM>
-__global__ void __launch_bounds__(kUThreads, BN <= 64 ? 2 : 1)
+__global__ void __launch_bounds__(kUThreads, 1)
 conv_umma_kernel(const ConvParams p) {
+    using Cfg = EngineCfg<BN>;
+    constexpr int S = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full_a[kUStages], bar_full_b[kUStages], bar_empty[kUStages], bar_accum;
+    __shared__ __align__(8) uint64_t bar_full_a[S], bar_full_b[S], bar_empty[S];
+    __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2];
     __shared__ uint32_t s_tmem;
 
     const MdcnDims &d = p.d;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int kBTileBytes = BN * kUK * 4;
-    constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;
     uint8_t *smem = smem_raw + ((1024 - (umma::smem_u32(smem_raw) & 1023)) & 1023);   // 1024-byte aligned
 
-    const int b = blockIdx.x / p.tiles_per_img;
-    const long p0 = (long)(blockIdx.x % p.tiles_per_img) * kUM;
-    const int grp = blockIdx.y / p.n_tiles_n, nt = blockIdx.y % p.n_tiles_n;
-
     if (tid == 0) {
-        for (int s = 0; s < kUStages; ++s) {
-            umma::mbar_init(&bar_full_a[s], 4);     // one arrival per producer warp
-            umma::mbar_init(&bar_full_b[s], 1);     // expect_tx arrival + bulk-copy bytes
-            umma::mbar_init(&bar_empty[s], 1);      // tcgen05.commit
+        for (int s = 0; s < S; ++s) {
+            umma::mbar_init(&bar_full_a[s], kProdWarps);   // one arrival per producer warp
+            umma::mbar_init(&bar_full_b[s], 1);            // expect_tx arrival + bulk-copy bytes
+            umma::mbar_init(&bar_empty[s], 1);             // tcgen05.commit
         }
-        umma::mbar_init(&bar_accum, 1);
+        for (int a = 0; a < 2; ++a) {
+            umma::mbar_init(&bar_acc_full[a], 1);          // tcgen05.commit after a tile's last MMA
+            umma::mbar_init(&bar_acc_empty[a], 4);         // one arrival per epilogue warp
+        }
         umma::fence_mbar_init();
     }
-    if (warp == 4) umma::tmem_alloc<TmemCols<BN>::value>(&s_tmem);
+    if (warp == kMmaWarp) umma::tmem_alloc<Cfg::kTmemCols>(&s_tmem);
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem_base = s_tmem;
 
-    if (warp < 4) {
-        // ================================ A producer: one thread per output pixel ================
-        const long pix = p0 + tid;
-        const bool p_ok = pix < d.P;
-        const long pc = p_ok ? pix : 0;
-        const int ho = (int)(pc / d.Wo), wo = (int)(pc % d.Wo);
-        const float *x_b = p.x + (long)b * d.Cin * d.HW;
-        const float *off_b = DEFORM ? p.offset + (long)b * d.dg * 2 * d.K * d.P : nullptr;
-        const float *mask_b = (DEFORM && p.mask) ? p.mask + (long)b * d.dg * d.K * d.P : nullptr;
-        const int row_sw = tid & 7;
-        int cur_tap = -1, cur_g = -1;
-        int si[4] = {0, 0, 0, 0};
-        float sw[4] = {0.f, 0.f, 0.f, 0.f};
-        bool dense_ok = false; int dense_idx = 0;
+    if (warp < kProdWarps) {
+        // ================================ A producers ===========================================
+        // item = (row, 16-byte chunk): chunk j = tid % 8 (fixed), rows r0 + 32*u, u = 0..3
+        const int j = tid & 7, r0 = tid >> 3;
+        const int P32 = (int)d.P;
+        uint32_t it = 0;                                   // K-block counter across tiles
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const TileCoord tc = tile_coord(p, t);
+            const float *x_b = p.x + (long)tc.b * d.HW * d.Cin;
+            int oh[4], ow[4];
+            bool rok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int px = tc.p0 + r0 + 32 * u;
+                rok[u] = px < P32;
+                const int pc = rok[u] ? px : P32 - 1;
+                oh[u] = pc / d.Wo;
+                ow[u] = pc - oh[u] * d.Wo;
+            }
+            const float *off_b = DEFORM ? p.offset + (long)tc.b * p.off_bs : nullptr;
+            const float *mask_b = (DEFORM && p.mask) ? p.mask + (long)tc.b * p.mask_bs : nullptr;
 
-        for (int kb = 0; kb < p.KB; ++kb) {
-            const int s = kb % kUStages;
-            const uint32_t ph = (kb / kUStages) & 1;
-            umma::mbar_wait(&bar_empty[s], ph ^ 1);
-            float *a_hi = reinterpret_cast<float *>(smem + (size_t)s * kStageBytes) + tid * kUK;
-            float *a_lo = a_hi + kATileBytes / 4;
-#pragma unroll 2
-            for (int j = 0; j < 8; ++j) {
+            for (int kb = 0; kb < p.KB; ++kb, ++it) {
+                const int s = it % S;
+                const uint32_t ph = (it / S) & 1;
                 const int kk = kb * kUK + j * 4;
-                float v[4] = {0.f, 0.f, 0.f, 0.f};
-                if (kk < p.K && p_ok) {
-                    const int tap = kk / d.Cg, c = kk - tap * d.Cg;
-                    const int c_abs = grp * d.Cg + c;
-                    if (DEFORM) {
-                        const int g = c_abs / d.Cd;
-                        if (tap != cur_tap || g != cur_g) {
-                            cur_tap = tap; cur_g = g;
-                            const Sample sm = sample_at(d, off_b, g, tap, ho, wo, pc);
-                            const float m = mask_b ? mask_b[(long)(g * d.K + tap) * d.P + pc] : 1.f;
+                const bool k_ok = kk < p.K;
+                const int tap = k_ok ? kk / d.Cg : 0;
+                const int c_abs = tc.grp * d.Cg + (k_ok ? kk - tap * d.Cg : 0);
+                const int ki = tap / d.kw, kj = tap - ki * d.kw;
+                float *a_hi = reinterpret_cast<float *>(smem + (size_t)s * Cfg::kStageBytes);
+                float *a_lo = a_hi + kATileBytes / 4;
+                float v[4][4];
+                if (DEFORM) {
+                    const int g = c_abs / d.Cd;
+                    const long ch = (long)(g * d.K + tap);
+                    float gh[4], gw[4], gm[4];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) { si[q] = sm.i[q]; sw[q] = sm.w[q] * m; }
-                        }
-                        const float *im = x_b + (long)c_abs * d.HW;
+                    for (int u = 0; u < 4; ++u) {
+                        const long pc = oh[u] * d.Wo + ow[u];
+                        gh[u] = __ldg(off_b + pc * p.off_ps + (ch * 2) * p.off_cs);
+                        gw[u] = __ldg(off_b + pc * p.off_ps + (ch * 2 + 1) * p.off_cs);
+                        gm[u] = mask_b ? __ldg(mask_b + pc * p.mask_ps + ch * p.mask_cs) : 1.f;
+                    }
+                    float4 q[4][4];
+                    float wgt[4][4];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float *ime = im + (long)e * d.HW;
-                            v[e] = sw[0] * __ldg(ime + si[0]) + sw[1] * __ldg(ime + si[1]) +
-                                   sw[2] * __ldg(ime + si[2]) + sw[3] * __ldg(ime + si[3]);
-                        }
-                    } else {
-                        if (tap != cur_tap) {
-                            cur_tap = tap;
-                            const int hi_ = ho * d.stride - d.pad + (tap / d.kw) * d.dil;
-                            const int wi_ = wo * d.stride - d.pad + (tap % d.kw) * d.dil;
-                            dense_ok = hi_ >= 0 && hi_ < d.H && wi_ >= 0 && wi_ < d.W;
-                            dense_idx = dense_ok ? hi_ * d.W + wi_ : 0;
-                        }
-                        if (dense_ok) {
-                            const float *im = x_b + (long)c_abs * d.HW + dense_idx;
+                    for (int u = 0; u < 4; ++u) {
+                        const float h = (float)(oh[u] * d.stride - d.pad + ki * d.dil) + gh[u];
+                        const float w = (float)(ow[u] * d.stride - d.pad + kj * d.dil) + gw[u];
+                        const Sample sm = make_sample(h, w, d.H, d.W);
+                        const float m = (k_ok && rok[u]) ? gm[u] : 0.f;
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) v[e] = __ldg(im + (long)e * d.HW);
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            wgt[u][c4] = sm.w[c4] * m;
+                            q[u][c4] = __ldg(reinterpret_cast<const float4 *>(x_b + (long)sm.i[c4] * d.Cin + c_abs));
                         }
                     }
-                }
-                float4 h4, l4;
-                umma::split_tf32(v[0], h4.x, l4.x); umma::split_tf32(v[1], h4.y, l4.y);
-                umma::split_tf32(v[2], h4.z, l4.z); umma::split_tf32(v[3], h4.w, l4.w);
-                const int chunk = (j ^ row_sw) << 2;
-                *reinterpret_cast<float4 *>(a_hi + chunk) = h4;
-                *reinterpret_cast<float4 *>(a_lo + chunk) = l4;
-            }
-            umma::fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) umma::mbar_arrive(&bar_full_a[s]);
-        }
-
-        // ================================ epilogue: TMEM -> registers -> NCHW =====================
-        umma::mbar_wait(&bar_accum, 0);
-        umma::tc_fence_after();
-        const long out_b = (long)b * d.Cout * d.P;
-#pragma unroll 1
-        for (int n0 = 0; n0 < BN; n0 += 16) {
-            float acc[16];
-            umma::tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + n0, acc);
-            if (!p_ok) continue;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int ol = nt * BN + n0 + i;
-                if (ol >= d.Og) break;
-                const int o = grp * d.Og + ol;
-                float t = acc[i];
-                if (p.bias) t += __ldg(p.bias + o);
-                if (p.scale) t = fmaf(t, __ldg(p.scale + o), __ldg(p.shift + o));
-                const long oi = out_b + (long)o * d.P + pix;
-                if (p.residual) t += __ldg(p.residual + oi);
-                if (p.act == ACT_RELU) t = fmaxf(t, 0.f);
-                else if (p.act == ACT_LEAKY) t = t > 0.f ? t : t * p.slope;
-                else if (p.act == ACT_OFFSET_MASK && o >= p.n_offset_ch) t = p.mask_scale / (1.f + __expf(-t));
-                p.out[oi] = t;
+                    for (int u = 0; u < 4; ++u) {
+                        v[u][0] = wgt[u][0] * q[u][0].x + wgt[u][1] * q[u][1].x + wgt[u][2] * q[u][2].x + wgt[u][3] * q[u][3].x;
+                        v[u][1] = wgt[u][0] * q[u][0].y + wgt[u][1] * q[u][1].y + wgt[u][2] * q[u][2].y + wgt[u][3] * q[u][3].y;
+                        v[u][2] = wgt[u][0] * q[u][0].z + wgt[u][1] * q[u][1].z + wgt[u][2] * q[u][2].z + wgt[u][3] * q[u][3].z;
+                        v[u][3] = wgt[u][0] * q[u][0].w + wgt[u][1] * q[u][1].w + wgt[u][2] * q[u][2].w + wgt[u][3] * q[u][3].w;
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int hi_ = oh[u] * d.stride - d.pad + ki * d.dil;
+                        const int wi_ = ow[u] * d.stride - d.pad + kj * d.dil;
+                        const bool ok = k_ok && rok[u] && hi_ >= 0 && hi_ < d.H && wi_ >= 0 && wi_ < d.W;
+                        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ok) q = __ldg(reinterpret_cast<const float4 *>(x_b + ((long)hi_ * d.W + wi_) * d.Cin + c_abs));
+                        v[u][0] = q.x; v[u][1] = q.y; v[u][2] = q.z; v[u][3] = q.w;
+                    }
+                }
+                umma::mbar_wait(&bar_empty[s], ph ^ 1);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int row = r0 + 32 * u;
+                    float4 h4, l4;
+                    umma::split_tf32(v[u][0], h4.x, l4.x); umma::split_tf32(v[u][1], h4.y, l4.y);
+                    umma::split_tf32(v[u][2], h4.z, l4.z); umma::split_tf32(v[u][3], h4.w, l4.w);
+                    const int at = row * kUK + ((j ^ (row & 7)) << 2);
+                    *reinterpret_cast<float4 *>(a_hi + at) = h4;
+                    *reinterpret_cast<float4 *>(a_lo + at) = l4;
+                }
+                umma::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&bar_full_a[s]);
             }
         }
-        umma::tc_fence_before();
-    } else if (warp == 5) {
+    } else if (warp < kMmaWarp) {
+        // ================================ epilogue: TMEM -> registers -> global ==================
+        const int q = warp & 3;                                  // TMEM lane quarter
+        const int row = q * 32 + lane;
+        uint32_t ti = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
+            const TileCoord tc = tile_coord(p, t);
+            const int a = ti & 1;
+            const int pix = tc.p0 + row;
+            const bool p_ok = pix < (int)d.P;
+            umma::mbar_wait_sleep(&bar_acc_full[a], (ti >> 1) & 1);
+            umma::tc_fence_after();
+            const int o_base = tc.grp * d.Og + tc.nt * BN;          // first global out channel of the tile
+            const int n_valid = min(BN, d.Og - tc.nt * BN);
+            const long pix_g = (long)tc.b * d.P + pix;
+            const bool vec_ok = !p.out_nchw && ((d.Cout | o_base) & 3) == 0;
+#pragma unroll 1
+            for (int n0 = 0; n0 < BN; n0 += 16) {
+                float acc[16];
+                umma::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + a * Cfg::kAccStride + n0, acc);
+                if (!p_ok || n0 >= n_valid) continue;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int o = o_base + n0 + i;
+                    if (n0 + i < n_valid) {
+                        float tv = acc[i];
+                        if (p.bias) tv += __ldg(p.bias + o);
+                        if (p.scale) tv = fmaf(tv, __ldg(p.scale + o), __ldg(p.shift + o));
+                        if (p.residual)
+                            tv += p.out_nchw ? __ldg(p.residual + ((long)tc.b * d.Cout + o) * d.P + pix)
+                                             : __ldg(p.residual + pix_g * d.Cout + o);
+                        if (p.act == ACT_RELU) tv = fmaxf(tv, 0.f);
+                        else if (p.act == ACT_LEAKY) tv = tv > 0.f ? tv : tv * p.slope;
+                        else if (p.act == ACT_OFFSET_MASK && o >= p.n_offset_ch)
+                            tv = p.mask_scale / (1.f + __expf(-tv));
+                        acc[i] = tv;
+                    }
+                }
+                if (p.out_nchw) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (n0 + i < n_valid) p.out[((long)tc.b * d.Cout + o_base + n0 + i) * d.P + pix] = acc[i];
+                } else {
+                    float *dst = p.out + pix_g * d.Cout + o_base + n0;
+                    if (vec_ok && n0 + 16 <= n_valid) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            *reinterpret_cast<float4 *>(dst + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (n0 + i < n_valid) dst[i] = acc[i];
+                    }
+                }
+            }
+            umma::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(&bar_acc_empty[a]);
+        }
+    } else if (warp == kLoadWarp) {
         // ================================ weight loader (bulk async copy) ========================
         if (lane == 0) {
-            const uint8_t *src = reinterpret_cast<const uint8_t *>(p.wpack) +
-                                 (size_t)(grp * p.n_tiles_n + nt) * p.KB * (2 * kBTileBytes);
-            for (int kb = 0; kb < p.KB; ++kb) {
-                const int s = kb % kUStages;
-                const uint32_t ph = (kb / kUStages) & 1;
-                umma::mbar_wait(&bar_empty[s], ph ^ 1);
-                umma::mbar_expect_tx(&bar_full_b[s], 2 * kBTileBytes);
-                umma::bulk_g2s(smem + (size_t)s * kStageBytes + 2 * kATileBytes, src + (size_t)kb * 2 * kBTileBytes,
-                               2 * kBTileBytes, &bar_full_b[s]);
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const TileCoord tc = tile_coord(p, t);
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(p.wpack) +
+                                     (size_t)(tc.grp * p.n_tiles_n + tc.nt) * p.KB * (2 * Cfg::kBTileBytes);
+                for (int kb = 0; kb < p.KB; ++kb, ++it) {
+                    const int s = it % S;
+                    const uint32_t ph = (it / S) & 1;
+                    umma::mbar_wait_sleep(&bar_empty[s], ph ^ 1);
+                    umma::mbar_expect_tx(&bar_full_b[s], 2 * Cfg::kBTileBytes);
+                    umma::bulk_g2s(smem + (size_t)s * Cfg::kStageBytes + 2 * kATileBytes,
+                                   src + (size_t)kb * 2 * Cfg::kBTileBytes, 2 * Cfg::kBTileBytes, &bar_full_b[s]);
+                }
             }
         }
     } else {
         // ================================ MMA issuer (one thread) ================================
         if (lane == 0) {
             constexpr uint32_t idesc = umma::make_idesc_tf32(kUM, BN);
-            for (int kb = 0; kb < p.KB; ++kb) {
-                const int s = kb % kUStages;
-                const uint32_t ph = (kb / kUStages) & 1;
-                umma::mbar_wait(&bar_full_a[s], ph);
-                umma::mbar_wait(&bar_full_b[s], ph);
+            uint32_t it = 0, ti = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
+                const int a = ti & 1;
+                umma::mbar_wait_sleep(&bar_acc_empty[a], ((ti >> 1) & 1) ^ 1);   // epilogue drained this accumulator
                 umma::tc_fence_after();
-                const uint32_t a0 = umma::smem_u32(smem + (size_t)s * kStageBytes);
-                const uint64_t a_hi = umma::make_desc_sw128(a0), a_lo = umma::make_desc_sw128(a0 + kATileBytes);
-                const uint64_t b_hi = umma::make_desc_sw128(a0 + 2 * kATileBytes);
-                const uint64_t b_lo = umma::make_desc_sw128(a0 + 2 * kATileBytes + kBTileBytes);
+                const uint32_t d_tmem = tmem_base + a * Cfg::kAccStride;
+                for (int kb = 0; kb < p.KB; ++kb, ++it) {
+                    const int s = it % S;
+                    const uint32_t ph = (it / S) & 1;
+                    umma::mbar_wait_sleep(&bar_full_a[s], ph);
+                    umma::mbar_wait_sleep(&bar_full_b[s], ph);
+                    umma::tc_fence_after();
+                    const uint32_t a0 = umma::smem_u32(smem + (size_t)s * Cfg::kStageBytes);
+                    const uint64_t a_hi = umma::make_desc_sw128(a0), a_lo = umma::make_desc_sw128(a0 + kATileBytes);
+                    const uint64_t b_hi = umma::make_desc_sw128(a0 + 2 * kATileBytes);
+                    const uint64_t b_lo = umma::make_desc_sw128(a0 + 2 * kATileBytes + Cfg::kBTileBytes);
 #pragma unroll
-                for (int k = 0; k < kUK / 8; ++k) {
-                    const uint32_t adv = k * 32;     // 8 tf32 = 32 bytes along K inside the swizzle row
-                    umma::mma_tf32(tmem_base, umma::desc_advance(a_lo, adv), umma::desc_advance(b_hi, adv), idesc,
-                                   (kb | k) != 0);
-                    umma::mma_tf32(tmem_base, umma::desc_advance(a_hi, adv), umma::desc_advance(b_lo, adv), idesc, 1);
-                    umma::mma_tf32(tmem_base, umma::desc_advance(a_hi, adv), umma::desc_advance(b_hi, adv), idesc, 1);
+                    for (int k = 0; k < kUK / 8; ++k) {
+                        const uint32_t adv = k * 32;     // 8 tf32 = 32 bytes along K inside the swizzle row
+                        umma::mma_tf32(d_tmem, umma::desc_advance(a_lo, adv), umma::desc_advance(b_hi, adv), idesc,
+                                       (kb | k) != 0);
+                        umma::mma_tf32(d_tmem, umma::desc_advance(a_hi, adv), umma::desc_advance(b_lo, adv), idesc, 1);
+                        umma::mma_tf32(d_tmem, umma::desc_advance(a_hi, adv), umma::desc_advance(b_hi, adv), idesc, 1);
+                    }
+                    umma::tc_commit(&bar_empty[s]);      // frees this stage when the MMAs above retire
                 }
-                umma::tc_commit(&bar_empty[s]);      // frees this stage when the MMAs above retire
+                umma::tc_commit(&bar_acc_full[a]);       // accumulator of this tile complete
             }
-            umma::tc_commit(&bar_accum);             // accumulator complete
         }
     }
+    umma::tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kMmaWarp) {
         umma::tc_fence_after();
-        umma::tmem_dealloc<TmemCols<BN>::value>(tmem_base);
+        umma::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
     }
 }
 
@@ -274,9 +395,10 @@ int conv_umma_pick_bn(int Og) {
 }
 
 bool conv_umma_supported(const MdcnDims &d, bool deform) {
-    if (d.Cg % 4) return false;
+    if (d.Cg % 4 || d.Cin % 4) return false;
     if (deform && (d.Cd % 4)) return false;
-    if (d.P > 0x7fffffffLL || d.HW > 0x7fffffffLL) return false;
+    if (d.P > 0x3fffffffLL || d.HW > 0x3fffffffLL) return false;
+    if ((long)d.B * ceil_div_ll(d.P, kUM) > 0x3fffffffLL) return false;
     return true;
 }
 
@@ -298,10 +420,18 @@ int conv_umma_pack(const float *weight, void *wpack, const MdcnDims &d, cudaStre
     return check_launch();
 }
 
+// [B][R][Cc] -> [B][Cc][R]
+int conv_umma_transpose(const float *src, float *dst, int B, int R, long Cc, cudaStream_t stream) {
+    const dim3 grid((unsigned)ceil_div_ll(Cc, 32), ceil_div(R, 32), B);
+    transpose_kernel<<<grid, 256, 0, stream>>>(src, dst, R, Cc);
+    return check_launch();
+}
+
 template <int BN, bool DEFORM>
-static int launch_one(const ConvParams &p, dim3 grid, cudaStream_t stream) {
-    constexpr size_t smem = conv_umma_smem_bytes<BN>();
+static int launch_one(const ConvParams &p, cudaStream_t stream) {
+    constexpr size_t smem = EngineCfg<BN>::kSmemBytes;
     cudaFuncSetAttribute(conv_umma_kernel<BN, DEFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
     conv_umma_kernel<BN, DEFORM><<<grid, kUThreads, smem, stream>>>(p);
     return check_launch();
 }
@@ -313,13 +443,13 @@ int conv_umma_launch(ConvParams p, bool deform, cudaStream_t stream) {
     p.K = d.K * d.Cg;
     p.KB = ceil_div(p.K, kUK);
     p.tiles_per_img = (int)ceil_div_ll(d.P, kUM);
-    const long gx = (long)d.B * p.tiles_per_img;
-    const int gy = d.groups * p.n_tiles_n;
-    if (gx > 0x7fffffffLL || gy > 65535) return AANET_ERR_UNSUPPORTED;
-    const dim3 grid((unsigned)gx, gy);
+    p.n_ptiles = d.B * p.tiles_per_img;
+    const long total = (long)d.groups * p.n_tiles_n * p.n_ptiles;
+    if (total > 0x7fffffffLL) return AANET_ERR_UNSUPPORTED;
+    p.total_tiles = (int)total;
 #define AANET_CONV_CASE(bn)                                                              \
     case bn:                                                                             \
-        return deform ? launch_one<bn, true>(p, grid, stream) : launch_one<bn, false>(p, grid, stream);
+        return deform ? launch_one<bn, true>(p, stream) : launch_one<bn, false>(p, stream);
     switch (BN) {
         AANET_CONV_CASE(16)
         AANET_CONV_CASE(32)

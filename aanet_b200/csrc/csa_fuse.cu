@@ -79,6 +79,45 @@ csa_fuse_fwd_kernel(CsaTerms t, float *__restrict__ out, int H, int W, long n_ve
     }
 }
 
+// Channels-last variant for the fused inference path: terms and out are [B][h][w][C], C % 4 == 0.
+__global__ void __launch_bounds__(256)
+csa_fuse_nhwc_kernel(CsaTerms t, float *__restrict__ out, int H, int W, int C, long n_vec, float slope) {
+    const int Cv = C / 4;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % Cv);
+        long r = i / Cv;
+        const int w = (int)(r % W); r /= W;
+        const int h = (int)(r % H);
+        const long b = r / H;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < AANET_CSA_MAX_TERMS; ++k) {
+            if (k >= t.n) break;
+            const int th = t.th[k], tw = t.tw[k];
+            const float4 *src = reinterpret_cast<const float4 *>(t.ptr[k]) + b * th * tw * Cv + cv;
+            float4 v;
+            if (th == H && tw == W) {
+                v = __ldg(src + ((long)h * W + w) * Cv);
+            } else {
+                int h0, h1, w0, w1; float a0, a1, b0, b1;
+                src_index(h, th, (float)th / (float)H, h0, h1, a0, a1);
+                src_index(w, tw, (float)tw / (float)W, w0, w1, b0, b1);
+                const float4 v00 = __ldg(src + ((long)h0 * tw + w0) * Cv), v01 = __ldg(src + ((long)h0 * tw + w1) * Cv);
+                const float4 v10 = __ldg(src + ((long)h1 * tw + w0) * Cv), v11 = __ldg(src + ((long)h1 * tw + w1) * Cv);
+                v.x = a0 * (b0 * v00.x + b1 * v01.x) + a1 * (b0 * v10.x + b1 * v11.x);
+                v.y = a0 * (b0 * v00.y + b1 * v01.y) + a1 * (b0 * v10.y + b1 * v11.y);
+                v.z = a0 * (b0 * v00.z + b1 * v01.z) + a1 * (b0 * v10.z + b1 * v11.z);
+                v.w = a0 * (b0 * v00.w + b1 * v01.w) + a1 * (b0 * v10.w + b1 * v11.w);
+            }
+            if (k == 0) acc = v;
+            else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+        }
+        acc.x = acc.x > 0.f ? acc.x : acc.x * slope; acc.y = acc.y > 0.f ? acc.y : acc.y * slope;
+        acc.z = acc.z > 0.f ? acc.z : acc.z * slope; acc.w = acc.w > 0.f ? acc.w : acc.w * slope;
+        reinterpret_cast<float4 *>(out)[i] = acc;
+    }
+}
+
 // Backward, same-size term: g * LeakyReLU'(pre); sign(pre) == sign(out) because slope > 0.
 __global__ void __launch_bounds__(256)
 csa_bwd_same_kernel(const float *__restrict__ out, const float *__restrict__ gout, float *__restrict__ gt,
@@ -156,6 +195,27 @@ extern "C" int aanet_csa_fuse_fwd(const float *const *terms, const int *th, cons
         csa_fuse_fwd_kernel<4><<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(t, out, H, W, n / 4, slope);
     else
         csa_fuse_fwd_kernel<1><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(t, out, H, W, n, slope);
+    return check_launch();
+}
+
+extern "C" int aanet_csa_fuse_nhwc(const float *const *terms, const int *th, const int *tw, int n_terms,
+                                   float *out, int B, int C, int H, int W, float slope, void *stream) {
+    if (!terms || !th || !tw || !out) return AANET_ERR_NULL;
+    if (n_terms < 1 || n_terms > AANET_CSA_MAX_TERMS || B <= 0 || C <= 0 || H <= 0 || W <= 0)
+        return AANET_ERR_SHAPE;
+    if (C % 4 || !aligned16(out)) return AANET_ERR_UNSUPPORTED;
+    CsaTerms t;
+    t.n = n_terms;
+    for (int k = 0; k < AANET_CSA_MAX_TERMS; ++k) {
+        t.ptr[k] = nullptr; t.th[k] = t.tw[k] = 0;
+        if (k >= n_terms) continue;
+        if (!terms[k]) return AANET_ERR_NULL;
+        if (th[k] <= 0 || tw[k] <= 0) return AANET_ERR_SHAPE;
+        if (!aligned16(terms[k])) return AANET_ERR_UNSUPPORTED;
+        t.ptr[k] = terms[k]; t.th[k] = th[k]; t.tw[k] = tw[k];
+    }
+    const long n = (long)B * H * W * (C / 4);
+    csa_fuse_nhwc_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(t, out, H, W, C, n, slope);
     return check_launch();
 }
 

@@ -1,0 +1,142 @@
+"""Fused, channels-last inference executor for AdaptiveAggregation.
+
+Same arithmetic as AdaptiveAggregation.forward in eval mode (reference nets/aggregation.py:452-464 and
+the modules below it), but every convolution -- the 1x1 / 3x3 convs of the bottlenecks (deform.py:164-184,
+:216-236), the offset/mask head (deform.py:80-89), the CSA exchange convs (aggregation.py:346-371) and the
+final 1x1 (aggregation.py:443-450) -- runs on the tcgen05 engine with eval-mode BatchNorm folded into a
+per-channel (scale, shift) epilogue, ReLU / LeakyReLU / residual add fused, and activations kept
+channels-last between kernels.  ~125 launches per stereo pair instead of ~320.
+
+This is SURVEY.md 8(f) ranks 1-2.  It is used automatically by AdaptiveAggregation.forward when the module
+is in eval mode, autograd is off and every channel count is a multiple of 4; otherwise the module-by-module
+path (torch convs + the same sm_100a operators) runs.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .nets.deform import DeformSimpleBottleneck, SimpleBottleneck, bn_affine
+
+
+class _Conv:
+    """A convolution prepared for the engine: packed weights + epilogue vectors + geometry."""
+
+    def __init__(self, conv, bn=None, act=ops.ACT_NONE, slope=0.2):
+        w = conv.weight
+        self.Cout, _, self.kh, self.kw = w.shape
+        self.groups = conv.groups
+        self.stride, self.pad, self.dil = conv.stride[0], conv.padding[0], conv.dilation[0]
+        self.wpack = ops.pack_conv_weight(w, conv.groups)
+        self.bias = None if conv.bias is None else conv.bias.detach().float().contiguous()
+        self.scale, self.shift = (None, None) if bn is None else bn_affine(bn)
+        self.act, self.slope = act, slope
+
+    def __call__(self, x, residual=None, out_nchw=False, n_offset_ch=0, mask_scale=1.0, act=None):
+        return ops.conv2d_nhwc(x, self.wpack, self.Cout, self.kh, self.kw, self.bias, self.scale, self.shift,
+                               residual, self.act if act is None else act, self.slope, self.stride, self.pad,
+                               self.dil, self.groups, out_nchw, n_offset_ch, mask_scale)
+
+
+class _Deform:
+    """DeformConv2d (offset/mask head + DCNv2) with bn2 + ReLU folded into the DCN epilogue."""
+
+    def __init__(self, dc2d, bn):
+        dc = dc2d.deform_conv
+        self.head = _Conv(dc2d.offset_conv)
+        self.n_off = dc2d.deformable_groups * 2 * dc2d.kernel_size * dc2d.kernel_size
+        self.mask_scale = 2.0 if dc2d.double_mask else 1.0
+        self.Cout, _, self.kh, self.kw = dc.weight.shape
+        self.wpack = ops.pack_conv_weight(dc.weight, dc.groups)
+        self.bias = None if dc.bias is None else dc.bias.detach().float().contiguous()
+        self.scale, self.shift = bn_affine(bn)
+        self.stride, self.pad, self.dil = dc.stride, dc.padding, dc.dilation
+        self.groups, self.dg = dc.groups, dc.deformable_groups
+
+    def __call__(self, x):
+        # offsets pass through, mask channels get mask_scale * sigmoid (deform.py:82-89), one tensor
+        om = self.head(x, act=ops.ACT_OFFSET_MASK, n_offset_ch=self.n_off, mask_scale=self.mask_scale)
+        return ops.mdcn_nhwc(x, om, self.wpack, self.Cout, self.kh, self.kw, self.bias, self.scale, self.shift,
+                             True, self.stride, self.pad, self.dil, self.groups, self.dg)
+
+
+class _Bottleneck:
+    def __init__(self, blk):
+        self.c1 = _Conv(blk.conv1, blk.bn1, ops.ACT_RELU)
+        if isinstance(blk, DeformSimpleBottleneck):
+            self.c2 = _Deform(blk.conv2, blk.bn2)
+        else:
+            self.c2 = _Conv(blk.conv2, blk.bn2, ops.ACT_RELU)
+        self.c3 = _Conv(blk.conv3, blk.bn3, ops.ACT_RELU)     # relu(bn3(conv3) + identity)
+
+    def __call__(self, x):
+        return self.c3(self.c2(self.c1(x)), residual=x)
+
+
+def _exchange(seq):
+    """fuse_layers[i][j]: Identity, Sequential(conv, bn) or a chain of Sequential(conv, bn[, LeakyReLU])."""
+    if isinstance(seq, nn.Identity):
+        return []
+    if isinstance(seq[0], nn.Conv2d):
+        return [_Conv(seq[0], seq[1])]
+    return [_Conv(s[0], s[1], ops.ACT_LEAKY if len(s) > 2 else ops.ACT_NONE,
+                  s[2].negative_slope if len(s) > 2 else 0.2) for s in seq]
+
+
+def supported(agg):
+    """All engine constraints: plain BatchNorm2d, every channel count % 4 == 0, modulated deform convs."""
+    for m in agg.modules():
+        if isinstance(m, nn.Conv2d) and (m.in_channels % 4 or (m.in_channels // m.groups) % 4):
+            return False
+        if isinstance(m, (SimpleBottleneck, DeformSimpleBottleneck)):
+            if m.downsample is not None or not isinstance(m.bn1, nn.BatchNorm2d):
+                return False
+        if isinstance(m, DeformSimpleBottleneck):
+            dc = m.conv2.deform_conv
+            if not m.conv2.modulation or dc.in_channels % (4 * dc.deformable_groups) or \
+                    (dc.in_channels // dc.groups) % 4:
+                return False
+    return True
+
+
+def _state_key(agg):
+    return tuple((t.data_ptr(), t._version) for t in list(agg.parameters()) + list(agg.buffers()))
+
+
+class FusedAggregation:
+    def __init__(self, agg):
+        self.key = _state_key(agg)
+        self.stages = []
+        for mod in agg.fusions:
+            branches = [[_Bottleneck(b) for b in br] for br in mod.branches]
+            fuse = [[_exchange(mod.fuse_layers[i][j]) for j in range(mod.num_scales)]
+                    for i in range(len(mod.fuse_layers))] if mod.num_scales > 1 else None
+            self.stages.append((branches, fuse, mod.relu.negative_slope))
+        self.final = [_Conv(c) for c in agg.final_conv]
+
+    def __call__(self, cost_volume):
+        xs = [ops.nchw_to_nhwc(c) for c in cost_volume]
+        for branches, fuse, slope in self.stages:
+            for s, blocks in enumerate(branches):
+                for blk in blocks:
+                    xs[s] = blk(xs[s])
+            if fuse is None:
+                continue
+            outs = []
+            for row in fuse:
+                terms = []
+                for j, chain in enumerate(row):
+                    t = xs[j]
+                    for conv in chain:
+                        t = conv(t)
+                    terms.append(t)
+                outs.append(ops.csa_fuse_nhwc(terms, slope))
+            xs = outs
+        return [conv(xs[s], out_nchw=True) for s, conv in enumerate(self.final)]
+
+
+def run(agg, cost_volume):
+    fused = getattr(agg, "_aanet_fused", None)
+    if fused is None or fused.key != _state_key(agg):
+        fused = FusedAggregation(agg)
+        agg._aanet_fused = fused
+    return fused(cost_volume)

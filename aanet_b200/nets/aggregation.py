@@ -9,8 +9,10 @@ sm_100a kernel (aanet_b200.ops.csa_fuse).  The 3-D-conv aggregators that share t
 """
 import torch.nn as nn
 
+import torch
+
 from .. import ops
-from .deform import SimpleBottleneck, DeformSimpleBottleneck
+from .deform import SimpleBottleneck, DeformSimpleBottleneck, _inference_mode
 
 
 def _conv_bn(cin, cout, k, stride=1, pad=0, act=False):
@@ -103,8 +105,15 @@ class AdaptiveAggregation(nn.Module):
             if not intermediate_supervision:
                 break
 
+    use_fused_inference = True     # eval + no_grad: channels-last tcgen05 executor (aanet_b200/fused.py)
+
     def forward(self, cost_volume):
         assert isinstance(cost_volume, list)
+        if self.use_fused_inference and _inference_mode(self) and cost_volume[0].is_cuda \
+                and cost_volume[0].dtype == torch.float32:
+            from .. import fused
+            if fused.supported(self):
+                return fused.run(self, cost_volume)
         for i in range(self.num_fusions):
             cost_volume = self.fusions[i](cost_volume)
         return [conv(cost_volume[s]) for s, conv in enumerate(self.final_conv)]

@@ -141,7 +141,7 @@ def _mdcn_forward(x, offset, mask, weight, bias, stride, pad, dil, groups, dg,
             _ptr(x), _ptr(offset), _ptr(mask), _ptr(weight), _ptr(bias), _ptr(out),
             B, Cin, H, W, Cout, kh, kw, stride, pad, dil, groups, dg,
             _ptr(post_scale), _ptr(post_shift), int(relu), _ptr(ws), nbytes, _stream(x)), "aanet_mdcn_fwd")
-    _count(2 if nbytes else 1)
+    _count(3 if nbytes else 1)
     return out
 
 
@@ -255,13 +255,102 @@ def conv2d_fused(x, weight, bias=None, scale=None, shift=None, residual=None, ac
         raise ValueError("conv2d_fused: residual must have the output's shape")
     lib = _lib.load()
     nbytes = lib.aanet_conv2d_workspace_bytes(B, Cin, H, W, Cout, kh, kw, stride, padding, dilation, groups)
-    ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=x.device)
+    if nbytes == 0:
+        raise _lib.AanetError("conv2d_fused needs Cin %% 4 == 0 and Cin/groups %% 4 == 0 (got Cin=%d, groups=%d)"
+                              % (Cin, groups))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
         _lib.check(lib.aanet_conv2d_fwd(_ptr(x), _ptr(weight), _ptr(bias), _ptr(scale), _ptr(shift),
                                         _ptr(residual), int(act), float(slope), _ptr(out), B, Cin, H, W, Cout,
                                         kh, kw, stride, padding, dilation, groups, _ptr(ws), nbytes,
                                         _stream(x)), "aanet_conv2d_fwd")
-    _count(2)
+    _count(3)
+    return out
+
+
+# ------------------------------------------------------------------------------------ channels-last engine
+ACT_OFFSET_MASK = 3
+
+
+def nchw_to_nhwc(x):
+    """[B,C,H,W] -> [B,H,W,C] (contiguous) with the library's tiled transpose."""
+    x = _prep(x, "nchw_to_nhwc")
+    B, C, H, W = x.shape
+    out = x.new_empty(B, H, W, C)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().aanet_nchw_to_nhwc(_ptr(x), _ptr(out), B, C, H * W, _stream(x)), "aanet_nchw_to_nhwc")
+    _count()
+    return out
+
+
+def nhwc_to_nchw(x):
+    x = _prep(x, "nhwc_to_nchw")
+    B, H, W, C = x.shape
+    out = x.new_empty(B, C, H, W)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().aanet_nhwc_to_nchw(_ptr(x), _ptr(out), B, C, H * W, _stream(x)), "aanet_nhwc_to_nchw")
+    _count()
+    return out
+
+
+def pack_conv_weight(weight, groups=1):
+    """tf32 hi/lo split + 128-byte swizzle of a [Cout, Cin/groups, kh, kw] weight for the tcgen05 engine."""
+    weight = _prep(weight.detach(), "pack_conv_weight")
+    Cout, cg, kh, kw = weight.shape
+    lib = _lib.load()
+    n = lib.aanet_conv_wpack_bytes(Cout, cg * groups, kh, kw, groups)
+    if n == 0:
+        raise _lib.AanetError("conv engine needs Cin/groups %% 4 == 0 (got Cin=%d, groups=%d)" % (cg * groups, groups))
+    wpack = torch.empty(n, dtype=torch.uint8, device=weight.device)
+    with torch.cuda.device(weight.device):
+        _lib.check(lib.aanet_conv_pack_weights(_ptr(weight), _ptr(wpack), Cout, cg * groups, kh, kw, groups,
+                                               _stream(weight)), "aanet_conv_pack_weights")
+    _count()
+    return wpack
+
+
+def conv2d_nhwc(x, wpack, Cout, kh, kw, bias=None, scale=None, shift=None, residual=None, act=ACT_NONE,
+                slope=0.2, stride=1, padding=0, dilation=1, groups=1, out_nchw=False, n_offset_ch=0,
+                mask_scale=1.0):
+    """Dense convolution on channels-last activations x [B,H,W,Cin] with pre-packed weights."""
+    B, H, W, Cin = x.shape
+    Ho, Wo = _out_hw(H, W, kh, kw, stride, padding, dilation)
+    out = x.new_empty((B, Cout, Ho, Wo) if out_nchw else (B, Ho, Wo, Cout))
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().aanet_conv2d_nhwc(
+            _ptr(x), _ptr(wpack), _ptr(bias), _ptr(scale), _ptr(shift), _ptr(residual), int(act), float(slope),
+            int(n_offset_ch), float(mask_scale), _ptr(out), int(out_nchw), B, Cin, H, W, Cout, kh, kw, stride,
+            padding, dilation, groups, _stream(x)), "aanet_conv2d_nhwc")
+    _count()
+    return out
+
+
+def mdcn_nhwc(x, offmask, wpack, Cout, kh, kw, bias=None, scale=None, shift=None, relu=False, stride=1,
+              padding=0, dilation=1, groups=1, deformable_groups=1, out_nchw=False):
+    """DCNv2 on channels-last x [B,H,W,Cin] with offsets+mask in one channels-last tensor."""
+    B, H, W, Cin = x.shape
+    Ho, Wo = _out_hw(H, W, kh, kw, stride, padding, dilation)
+    out = x.new_empty((B, Cout, Ho, Wo) if out_nchw else (B, Ho, Wo, Cout))
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().aanet_mdcn_nhwc(
+            _ptr(x), _ptr(offmask), offmask.shape[-1], _ptr(wpack), _ptr(bias), _ptr(scale), _ptr(shift),
+            int(relu), _ptr(out), int(out_nchw), B, Cin, H, W, Cout, kh, kw, stride, padding, dilation, groups,
+            deformable_groups, _stream(x)), "aanet_mdcn_nhwc")
+    _count()
+    return out
+
+
+def csa_fuse_nhwc(terms, slope=0.2):
+    """Channels-last csa_fuse (inference): terms [B,h,w,C] -> [B,H,W,C] of terms[0]'s size."""
+    B, H, W, C = terms[0].shape
+    n = len(terms)
+    th = (ctypes.c_int * n)(*[t.shape[1] for t in terms])
+    tw = (ctypes.c_int * n)(*[t.shape[2] for t in terms])
+    out = terms[0].new_empty(B, H, W, C)
+    with torch.cuda.device(out.device):
+        _lib.check(_lib.load().aanet_csa_fuse_nhwc(_term_arrays(terms), th, tw, n, _ptr(out), B, C, H, W,
+                                                   float(slope), _stream(out)), "aanet_csa_fuse_nhwc")
+    _count()
     return out
 
 

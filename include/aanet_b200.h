@@ -96,7 +96,8 @@ AANET_API int aanet_softargmin_bwd(const float *cost, const float *gdisp, float 
  * NULL, NULL, 0 for the reference semantics.
  *
  * Workspace: query with aanet_mdcn_workspace_bytes().  Forward: the workspace receives the tf32
- * hi/lo-split, swizzled weights that the tcgen05 kernel streams; passing ws == NULL is legal and
+ * hi/lo-split, swizzled weights that the tcgen05 kernel streams and a channels-last copy of x
+ * (the engine gathers 128-byte channel rows); passing ws == NULL is legal and
  * selects the shape-generic FFMA kernel instead (same results within fp32 rounding).  Backward: the
  * workspace holds grad_weight partials and is required.
  * ------------------------------------------------------------------------------------------- */
@@ -139,6 +140,38 @@ AANET_API int aanet_conv2d_fwd(const float *x, const float *weight, const float 
                                int B, int Cin, int H, int W, int Cout, int kh, int kw,
                                int stride, int pad, int dil, int groups,
                                void *ws, size_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Channels-last engine calls (used by the drop-in's fused inference path; no counterpart in the
+ * reference, which keeps NCHW throughout).  Activations are [B][H*W][C]; weights are pre-packed once
+ * (tf32 hi/lo split + 128-byte swizzle) with aanet_conv_pack_weights into a buffer of
+ * aanet_conv_wpack_bytes() bytes and reused until the weights change.
+ *
+ * aanet_conv2d_nhwc:  out = act((conv(x, w) + bias) * scale + shift + residual), out/residual channels-last
+ *   (out_nchw == 0) or NCHW (out_nchw != 0).  act 0-2 as above; act == 3 is the DeformConv2d offset/mask
+ *   head (nets/deform.py:80-89): channels >= n_offset_ch get mask_scale * sigmoid(.), the rest pass through.
+ * aanet_mdcn_nhwc:  DCNv2 with x channels-last and offsets+mask in ONE channels-last tensor
+ *   offmask [B][Ho*Wo][om_channels], offsets in channels [0, dg*2*kh*kw) and the (already activated) mask
+ *   behind them, i.e. the positional split of nets/deform.py:82-85; om_channels == dg*2*kh*kw means no
+ *   mask (DCNv1).
+ * ------------------------------------------------------------------------------------------- */
+AANET_API size_t aanet_conv_wpack_bytes(int Cout, int Cin, int kh, int kw, int groups);
+AANET_API int aanet_conv_pack_weights(const float *weight, void *wpack, int Cout, int Cin, int kh, int kw,
+                                      int groups, void *stream);
+AANET_API int aanet_nchw_to_nhwc(const float *src, float *dst, int B, int C, int HW, void *stream);
+AANET_API int aanet_nhwc_to_nchw(const float *src, float *dst, int B, int C, int HW, void *stream);
+AANET_API int aanet_conv2d_nhwc(const float *x, const void *wpack, const float *bias, const float *scale,
+                                const float *shift, const float *residual, int act, float slope,
+                                int n_offset_ch, float mask_scale, float *out, int out_nchw,
+                                int B, int Cin, int H, int W, int Cout, int kh, int kw,
+                                int stride, int pad, int dil, int groups, void *stream);
+AANET_API int aanet_mdcn_nhwc(const float *x, const float *offmask, int om_channels, const void *wpack,
+                              const float *bias, const float *post_scale, const float *post_shift, int relu,
+                              float *out, int out_nchw, int B, int Cin, int H, int W, int Cout, int kh, int kw,
+                              int stride, int pad, int dil, int groups, int dg, void *stream);
+/* Channels-last twin of aanet_csa_fuse_fwd: terms and out are [B][h][w][C], C % 4 == 0. */
+AANET_API int aanet_csa_fuse_nhwc(const float *const *terms, const int *th, const int *tw, int n_terms,
+                                  float *out, int B, int C, int H, int W, float slope, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Cross-scale aggregation fuse.  Replaces the resize + sum + LeakyReLU tail of

@@ -102,6 +102,38 @@ def test_hot_path_vs_port_midsize():
     assert np.abs(npy(disp) - ref[-1].numpy()).max() < 1e-3
 
 
+@pytest.mark.parametrize("D0,H,W,B", [(32, 24, 40, 2), (64, 128, 416, 1)])
+def test_fused_executor_matches_module_path(D0, H, W, B):
+    """Channels-last tcgen05 executor (eval + no_grad) vs the module-by-module path on the same weights,
+    at a small size and at the full KITTI 1/3-scale pyramid of the bench workload."""
+    import aanet_b200.nets as n
+    from aanet_b200 import fused
+    torch.manual_seed(326)
+    agg = n.AdaptiveAggregation(D0, num_deform_blocks=3, intermediate_supervision=False).cuda().eval()
+    for name, m in agg.named_modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.8, 1.2)
+        if name.endswith("offset_conv"):
+            torch.nn.init.normal_(m.weight, std=0.05); torch.nn.init.normal_(m.bias, std=0.5)
+    assert fused.supported(agg)
+    costs = [torch.randn(B, D0 >> s, H >> s, W >> s, device="cuda") for s in range(3)]
+    with torch.no_grad():
+        fast = agg([c.clone() for c in costs])
+        agg.use_fused_inference = False
+        slow = agg([c.clone() for c in costs])
+        d_fast = n.DisparityEstimation(D0)(fast[0])
+        d_slow = n.DisparityEstimation(D0)(slow[0])
+    assert hasattr(agg, "_aanet_fused")
+    assert rel_err(npy(fast[0]), npy(slow[0])) < 1e-4
+    assert (d_fast - d_slow).abs().max().item() < 1e-3
+    # editing a weight invalidates the packed cache
+    with torch.no_grad():
+        agg.final_conv[0].bias.add_(1.0)
+        agg.use_fused_inference = True
+        again = agg([c.clone() for c in costs])
+    assert rel_err(npy(again[0]), npy(slow[0] + 1.0)) < 1e-4
+
+
 def test_training_step_runs():
     """fwd + bwd through the drop-in modules in train mode (BN batch statistics, autograd kernels)."""
     import aanet_b200.nets as n

@@ -253,6 +253,70 @@ def test_conv2d_fused(ops, cfg):
     assert rel_err(npy(relu), npy(ref3)) < 1e-5
 
 
+# ------------------------------------------------------------------------------------ channels-last engine calls
+def test_layout_transposes(ops):
+    x = torch.randn(2, 20, 7, 45, device="cuda")
+    t = ops.nchw_to_nhwc(x)
+    assert t.shape == (2, 7, 45, 20) and torch.equal(t, x.permute(0, 2, 3, 1).contiguous())
+    assert torch.equal(ops.nhwc_to_nchw(t), x)
+
+
+@pytest.mark.parametrize("cfg", [
+    (1, 64, 64, 128, 416, 1, 1, 0, 1, 1), (2, 64, 54, 24, 40, 3, 1, 2, 2, 2), (1, 64, 32, 33, 47, 3, 2, 1, 1, 1),
+    (3, 16, 16, 19, 23, 3, 1, 1, 1, 1), (1, 32, 64, 64, 208, 1, 1, 0, 1, 1), (1, 8, 4, 5, 300, 3, 1, 1, 1, 1),
+])
+def test_conv2d_nhwc(ops, cfg):
+    B, Ci, Co, H, W, k, st, pad, dil, grp = cfg
+    torch.manual_seed(17)
+    x = torch.randn(B, Ci, H, W, device="cuda")
+    w = torch.randn(Co, Ci // grp, k, k, device="cuda") / (Ci * k * k / grp) ** 0.5
+    bias, scale, shift = torch.randn(Co, device="cuda"), torch.rand(Co, device="cuda") + 0.5, torch.randn(Co, device="cuda")
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), bias.double(), st, pad, dil, grp)
+    res = torch.randn_like(ref).float()
+    wp = ops.pack_conv_weight(w, grp)
+    xt = ops.nchw_to_nhwc(x)
+    out = ops.conv2d_nhwc(xt, wp, Co, k, k, bias, scale, shift, ops.nchw_to_nhwc(res), ops.ACT_LEAKY, 0.2, st, pad, dil, grp)
+    ref2 = torch.nn.functional.leaky_relu(ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) + res, 0.2)
+    assert rel_err(npy(out.permute(0, 3, 1, 2)), npy(ref2)) < 1e-5
+    out_nchw = ops.conv2d_nhwc(xt, wp, Co, k, k, bias, None, None, res, ops.ACT_RELU, 0.0, st, pad, dil, grp, out_nchw=True)
+    assert rel_err(npy(out_nchw), npy(torch.relu(ref + res))) < 1e-5
+    # offset/mask head: channels >= n_off get 2*sigmoid
+    n_off = (Co * 2) // 3
+    om = ops.conv2d_nhwc(xt, wp, Co, k, k, bias, None, None, None, ops.ACT_OFFSET_MASK, 0.0, st, pad, dil, grp,
+                         n_offset_ch=n_off, mask_scale=2.0)
+    ref_om = ref.clone()
+    ref_om[:, n_off:] = 2 * torch.sigmoid(ref[:, n_off:])
+    assert rel_err(npy(om.permute(0, 3, 1, 2)), npy(ref_om)) < 1e-5
+
+
+@pytest.mark.parametrize("cfg", [(1, 64, 64, 24, 52, 1, 2, 2), (2, 32, 32, 16, 26, 1, 2, 2), (1, 16, 24, 9, 13, 2, 1, 2),
+                                 (1, 96, 96, 9, 11, 1, 2, 8), (1, 8, 8, 12, 10, 1, 2, 2)])
+def test_mdcn_nhwc(ops, cfg):
+    B, Ci, Co, H, W, st, dil, dg = cfg
+    rng = np.random.default_rng(23)
+    Ho, Wo = orc.mdcn_out_hw(H, W, 3, st, dil, dil)
+    x = rng.standard_normal((B, Ci, H, W)).astype(np.float32)
+    off = (2 * rng.standard_normal((B, dg * 18, Ho, Wo))).astype(np.float32)
+    msk = rng.uniform(0, 2, (B, dg * 9, Ho, Wo)).astype(np.float32)
+    w = (rng.standard_normal((Co, Ci, 3, 3)) / np.sqrt(Ci * 9)).astype(np.float32)
+    ref = orc.mdcn_fwd(x, off, msk, w, None, st, dil, dil, 1, dg)
+    om = ops.nchw_to_nhwc(cu(np.concatenate([off, msk], 1)))
+    out = ops.mdcn_nhwc(ops.nchw_to_nhwc(cu(x)), om, ops.pack_conv_weight(cu(w)), Co, 3, 3, None, None, None, False,
+                        st, dil, dil, 1, dg)
+    assert rel_err(npy(out.permute(0, 3, 1, 2)), ref) < VOL_TOL
+    v1 = ops.mdcn_nhwc(ops.nchw_to_nhwc(cu(x)), ops.nchw_to_nhwc(cu(off)), ops.pack_conv_weight(cu(w)), Co, 3, 3,
+                       None, None, None, False, st, dil, dil, 1, dg, out_nchw=True)          # DCNv1: no mask
+    assert rel_err(npy(v1), orc.mdcn_fwd(x, off, None, w, None, st, dil, dil, 1, dg)) < VOL_TOL
+
+
+def test_csa_fuse_nhwc(ops):
+    rng = np.random.default_rng(4)
+    (B, C, H, W), ths = (2, 8, 31, 45), [(31, 45), (16, 23), (8, 12)]
+    terms = [rng.standard_normal((B, C, h, w)).astype(np.float32) for h, w in ths]
+    out = ops.csa_fuse_nhwc([ops.nchw_to_nhwc(cu(t)) for t in terms], 0.2)
+    assert rel_err(npy(out.permute(0, 3, 1, 2)), orc.csa_fuse_fwd(terms, (H, W), 0.2)) < 1e-5
+
+
 # ------------------------------------------------------------------------------------ CSA fuse
 @pytest.mark.parametrize("tag", ["x2x4", "odd", "same", "two"])
 def test_csa_golden(ops, golden, tag):
