@@ -43,7 +43,8 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(build_dir, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("AANET_NVCC_DEFS", "").split() + \
+              (["-Xptxas", "-v"] if verbose else []) + \
               ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     failed = False

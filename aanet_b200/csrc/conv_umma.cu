@@ -20,14 +20,16 @@
 // Blackwell mapping.  A CTA is persistent (grid = #SMs) and walks 128-pixel tiles.  M = 128 pixels is
 // the UMMA M (one TMEM lane per pixel), N = BN output channels, K walks (tap, channel) in blocks of
 // 32 tf32 = one 128-byte swizzle row.  Warp roles:
-//   warps 0-7   A producers: lane = (pixel row, 16-byte chunk); LDG.128 (4 per item for DEFORM, 1 for
+//   warps 0-15  A producers: lane = (pixel row, 16-byte chunk); LDG.128 (4 per item for DEFORM, 1 for
 //               DENSE), bilinear combine, split into tf32 hi + lo (cvt.rna + exact remainder), two
-//               STS.128 into SWIZZLE_128B K-major tiles; fence.proxy.async + mbarrier arrive.
-//   warp 13     streams the pre-split, pre-swizzled weight block of the stage with one cp.async.bulk.
-//   warp 12     one thread issues tcgen05.mma.kind::tf32 three times per K step (lo*hi + hi*lo + hi*hi:
+//               STS.128 into SWIZZLE_128B K-major tiles; fence.proxy.async + mbarrier arrive.  DENSE keeps
+//               three K blocks of loads in flight per thread (register ring); DEFORM prefetches the next
+//               block's offsets/mask while the current block's gathers are outstanding.
+//   warp 21     streams the pre-split, pre-swizzled weight block of the stage with one cp.async.bulk.
+//   warp 20     one thread issues tcgen05.mma.kind::tf32 three times per K step (lo*hi + hi*lo + hi*hi:
 //               fp32-grade accuracy, the parity bar is 1e-4) into one of two TMEM accumulators and
 //               releases the stage with tcgen05.commit.
-//   warps 8-11  epilogue: tcgen05.ld (lane = pixel), bias / folded-BN affine / residual / activation,
+//   warps 16-19 epilogue: tcgen05.ld (lane = pixel), bias / folded-BN affine / residual / activation,
 //               128-bit channels-last stores (or coalesced NCHW stores); runs one tile behind the MMA.
 // All hand-offs are mbarriers; the ring (4 stages at BN = 64) runs across tile boundaries.
 #include "mdcn_common.cuh"
@@ -37,11 +39,17 @@ namespace aanet {
 
 constexpr int kUM = 128;                 // pixels per tile (UMMA M)
 constexpr int kUK = 32;                  // K per stage (one 128-byte swizzle row of tf32)
-constexpr int kProdWarps = 8;
-constexpr int kMmaWarp = 12, kLoadWarp = 13;   // warps 8..11 are the epilogue (warp % 4 = TMEM lane quarter)
-constexpr int kUThreads = 14 * 32;
+constexpr int kProdWarps = 16;           // 4 warp groups of A producers
+constexpr int kRows = 128 * 8 / (kProdWarps * 32);   // pixel rows per producer thread (2)
+constexpr int kRowStep = kProdWarps * 4;              // row distance between a thread's items (64)
+constexpr int kMmaWarp = 20, kLoadWarp = 21;
+constexpr int kUThreads = 22 * 32;
+// 704 threads -> 88 registers per thread.  (setmaxnreg rebalancing between the roles faulted on the B200
+// test box with "unspecified launch failure"; the producers fit in the uniform budget without spills.)
+constexpr int kDensePrefetch = 3;        // K blocks of loads in flight per dense producer thread
 constexpr int kATileBytes = kUM * kUK * 4;   // 16 KB (hi); same for lo
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kSmemBudget = 200 * 1024;   // dynamic; ~9 KB of static tables on top (227 KB per SM)
+constexpr int kMaxKB = 256;               // K <= 8192
 
 enum ConvAct { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_OFFSET_MASK = 3 };
 
@@ -63,6 +71,20 @@ struct ConvParams {
     int n_ptiles;                       // B * tiles_per_img
     int total_tiles;                    // groups * n_tiles_n * n_ptiles
 };
+
+#ifdef AANET_PROFILE
+// Profile build only (-DAANET_PROFILE): per-CTA cycle counters of where each role waits.
+__device__ long long g_prof[148 * 16];
+#define PROF_T0() long long prof_t0 = clock64()
+#define PROF_ADD(slot) do { const long long prof_t1 = clock64(); prof_acc[slot] += prof_t1 - prof_t0; prof_t0 = prof_t1; } while (0)
+#define PROF_DECL() long long prof_acc[16] = {0}
+#define PROF_FLUSH(slot) g_prof[blockIdx.x * 16 + (slot)] = prof_acc[slot]
+#else
+#define PROF_T0()
+#define PROF_ADD(slot)
+#define PROF_DECL()
+#define PROF_FLUSH(slot)
+#endif
 
 template <int BN> struct EngineCfg {
     static constexpr int kBTileBytes = BN * kUK * 4;
@@ -149,6 +171,10 @@ conv_umma_kernel(const ConvParams p) {
     __shared__ __align__(8) uint64_t bar_full_a[S], bar_full_b[S], bar_empty[S];
     __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2];
     __shared__ uint32_t s_tmem;
+    // (tap, first channel) of every 16-byte chunk of every K block: c | ki << 16 | kj << 20 | tap << 24 | ok << 31
+    __shared__ uint32_t s_chunk[kMaxKB * 8];
+    // epilogue affine of the current (group, n-tile): out = acc * s_aff[0][n] + s_aff[1][n]
+    __shared__ __align__(16) float s_aff[2][BN];
 
     const MdcnDims &d = p.d;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -167,6 +193,16 @@ conv_umma_kernel(const ConvParams p) {
         umma::fence_mbar_init();
     }
     if (warp == kMmaWarp) umma::tmem_alloc<Cfg::kTmemCols>(&s_tmem);
+    for (int i = tid; i < p.KB * 8; i += kUThreads) {
+        const int kk = (i >> 3) * kUK + (i & 7) * 4;
+        uint32_t e = 0;
+        if (kk < p.K) {
+            const int tap = kk / d.Cg, c = kk - tap * d.Cg;
+            const int ki = tap / d.kw, kj = tap - ki * d.kw;
+            e = (uint32_t)c | ((uint32_t)ki << 16) | ((uint32_t)kj << 20) | ((uint32_t)tap << 24) | 0x80000000u;
+        }
+        s_chunk[i] = e;
+    }
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
@@ -174,159 +210,275 @@ conv_umma_kernel(const ConvParams p) {
 
     if (warp < kProdWarps) {
         // ================================ A producers ===========================================
-        // item = (row, 16-byte chunk): chunk j = tid % 8 (fixed), rows r0 + 32*u, u = 0..3
+        // item = (row, 16-byte chunk): chunk j = tid % 8 (fixed), rows r0 + 64*u, u = 0..kRows-1.
+        // A cursor walks the (tile, K block) sequence of this CTA; the load cursor runs ahead of the
+        // store cursor so that global latency is covered by loads already in flight.
         const int j = tid & 7, r0 = tid >> 3;
         const int P32 = (int)d.P;
-        uint32_t it = 0;                                   // K-block counter across tiles
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-            const TileCoord tc = tile_coord(p, t);
-            const float *x_b = p.x + (long)tc.b * d.HW * d.Cin;
-            int oh[4], ow[4];
-            bool rok[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int px = tc.p0 + r0 + 32 * u;
-                rok[u] = px < P32;
-                const int pc = rok[u] ? px : P32 - 1;
-                oh[u] = pc / d.Wo;
-                ow[u] = pc - oh[u] * d.Wo;
-            }
-            const float *off_b = DEFORM ? p.offset + (long)tc.b * p.off_bs : nullptr;
-            const float *mask_b = (DEFORM && p.mask) ? p.mask + (long)tc.b * p.mask_bs : nullptr;
+        PROF_DECL();
+        PROF_T0();
 
-            for (int kb = 0; kb < p.KB; ++kb, ++it) {
-                const int s = it % S;
-                const uint32_t ph = (it / S) & 1;
-                const int kk = kb * kUK + j * 4;
-                const bool k_ok = kk < p.K;
-                const int tap = k_ok ? kk / d.Cg : 0;
-                const int c_abs = tc.grp * d.Cg + (k_ok ? kk - tap * d.Cg : 0);
-                const int ki = tap / d.kw, kj = tap - ki * d.kw;
-                float *a_hi = reinterpret_cast<float *>(smem + (size_t)s * Cfg::kStageBytes);
-                float *a_lo = a_hi + kATileBytes / 4;
-                float v[4][4];
-                if (DEFORM) {
-                    const int g = c_abs / d.Cd;
-                    const long ch = (long)(g * d.K + tap);
-                    float gh[4], gw[4], gm[4];
+        struct Cursor {
+            int t, kb;
+            TileCoord tc;
+            int oh[kRows], ow[kRows];
+            bool rok[kRows];
+        };
+        auto enter_tile = [&](Cursor &c) {
+            if (c.t >= p.total_tiles) return;
+            c.tc = tile_coord(p, c.t);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const long pc = oh[u] * d.Wo + ow[u];
-                        gh[u] = __ldg(off_b + pc * p.off_ps + (ch * 2) * p.off_cs);
-                        gw[u] = __ldg(off_b + pc * p.off_ps + (ch * 2 + 1) * p.off_cs);
-                        gm[u] = mask_b ? __ldg(mask_b + pc * p.mask_ps + ch * p.mask_cs) : 1.f;
-                    }
-                    float4 q[4][4];
-                    float wgt[4][4];
+            for (int u = 0; u < kRows; ++u) {
+                const int px = c.tc.p0 + r0 + kRowStep * u;
+                c.rok[u] = px < P32;
+                const int pc = c.rok[u] ? px : P32 - 1;
+                c.oh[u] = pc / d.Wo;
+                c.ow[u] = pc - c.oh[u] * d.Wo;
+            }
+        };
+        auto advance = [&](Cursor &c) {
+            if (++c.kb == p.KB) { c.kb = 0; c.t += gridDim.x; enter_tile(c); }
+        };
+        // (tap, first channel) of this thread's chunk in K block kb: table lookup, no divisions
+        auto chunk_of = [&](const Cursor &c, bool &k_ok, int &tap, int &ki, int &kj, int &c_abs) {
+            const uint32_t e = s_chunk[c.kb * 8 + j];
+            k_ok = (e >> 31) != 0;
+            c_abs = c.tc.grp * d.Cg + (int)(e & 0xffffu);
+            ki = (e >> 16) & 15; kj = (e >> 20) & 15; tap = (e >> 24) & 127;
+        };
+        auto store_block = [&](uint32_t it, const float (&v)[kRows][4]) {
+            const int s = it % S;
+            const uint32_t ph = (it / S) & 1;
+            float *a_hi = reinterpret_cast<float *>(smem + (size_t)s * Cfg::kStageBytes);
+            float *a_lo = a_hi + kATileBytes / 4;
+            PROF_ADD(1);                                   // slot 1: everything but the two waits below
+            umma::mbar_wait(&bar_empty[s], ph ^ 1);
+            PROF_ADD(2);                                   // slot 2: waiting for a free stage
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float h = (float)(oh[u] * d.stride - d.pad + ki * d.dil) + gh[u];
-                        const float w = (float)(ow[u] * d.stride - d.pad + kj * d.dil) + gw[u];
-                        const Sample sm = make_sample(h, w, d.H, d.W);
-                        const float m = (k_ok && rok[u]) ? gm[u] : 0.f;
+            for (int u = 0; u < kRows; ++u) {
+                const int row = r0 + kRowStep * u;
+                float4 h4, l4;
+                umma::split_tf32(v[u][0], h4.x, l4.x); umma::split_tf32(v[u][1], h4.y, l4.y);
+                umma::split_tf32(v[u][2], h4.z, l4.z); umma::split_tf32(v[u][3], h4.w, l4.w);
+                const int at = row * kUK + ((j ^ (row & 7)) << 2);
+                *reinterpret_cast<float4 *>(a_hi + at) = h4;
+                *reinterpret_cast<float4 *>(a_lo + at) = l4;
+            }
+            umma::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(&bar_full_a[s]);
+        };
+
+        Cursor cs;                        // store cursor
+        cs.t = blockIdx.x; cs.kb = 0;
+        enter_tile(cs);
+        uint32_t it = 0;                  // K-block counter across tiles (stage / phase)
+
+        if (!DEFORM) {
+            Cursor cl = cs;               // load cursor, kDensePrefetch blocks ahead
+            float4 ring[kDensePrefetch][kRows];
+            auto issue = [&](float4 (&dst)[kRows]) {
+                if (cl.t >= p.total_tiles) return;
+                bool k_ok; int tap, ki, kj, c_abs;
+                chunk_of(cl, k_ok, tap, ki, kj, c_abs);
+                const float *x_b = p.x + (long)cl.tc.b * d.HW * d.Cin + c_abs;
 #pragma unroll
-                        for (int c4 = 0; c4 < 4; ++c4) {
-                            wgt[u][c4] = sm.w[c4] * m;
-                            q[u][c4] = __ldg(reinterpret_cast<const float4 *>(x_b + (long)sm.i[c4] * d.Cin + c_abs));
+                for (int u = 0; u < kRows; ++u) {
+                    const int hi_ = cl.oh[u] * d.stride - d.pad + ki * d.dil;
+                    const int wi_ = cl.ow[u] * d.stride - d.pad + kj * d.dil;
+                    const bool ok = k_ok && cl.rok[u] && hi_ >= 0 && hi_ < d.H && wi_ >= 0 && wi_ < d.W;
+                    dst[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok) dst[u] = __ldg(reinterpret_cast<const float4 *>(x_b + ((long)hi_ * d.W + wi_) * d.Cin));
+                }
+                advance(cl);
+            };
+#pragma unroll
+            for (int f = 0; f < kDensePrefetch; ++f) issue(ring[f]);
+            while (cs.t < p.total_tiles) {
+#pragma unroll
+                for (int f = 0; f < kDensePrefetch; ++f) {
+                    if (cs.t < p.total_tiles) {
+                        float v[kRows][4];
+#pragma unroll
+                        for (int u = 0; u < kRows; ++u) {
+                            v[u][0] = ring[f][u].x; v[u][1] = ring[f][u].y; v[u][2] = ring[f][u].z; v[u][3] = ring[f][u].w;
                         }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        v[u][0] = wgt[u][0] * q[u][0].x + wgt[u][1] * q[u][1].x + wgt[u][2] * q[u][2].x + wgt[u][3] * q[u][3].x;
-                        v[u][1] = wgt[u][0] * q[u][0].y + wgt[u][1] * q[u][1].y + wgt[u][2] * q[u][2].y + wgt[u][3] * q[u][3].y;
-                        v[u][2] = wgt[u][0] * q[u][0].z + wgt[u][1] * q[u][1].z + wgt[u][2] * q[u][2].z + wgt[u][3] * q[u][3].z;
-                        v[u][3] = wgt[u][0] * q[u][0].w + wgt[u][1] * q[u][1].w + wgt[u][2] * q[u][2].w + wgt[u][3] * q[u][3].w;
-                    }
-                } else {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int hi_ = oh[u] * d.stride - d.pad + ki * d.dil;
-                        const int wi_ = ow[u] * d.stride - d.pad + kj * d.dil;
-                        const bool ok = k_ok && rok[u] && hi_ >= 0 && hi_ < d.H && wi_ >= 0 && wi_ < d.W;
-                        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (ok) q = __ldg(reinterpret_cast<const float4 *>(x_b + ((long)hi_ * d.W + wi_) * d.Cin + c_abs));
-                        v[u][0] = q.x; v[u][1] = q.y; v[u][2] = q.z; v[u][3] = q.w;
+                        store_block(it, v);
+                        issue(ring[f]);
+                        advance(cs);
+                        ++it;
                     }
                 }
-                umma::mbar_wait(&bar_empty[s], ph ^ 1);
+            }
+        } else {
+            // geometry inputs (offset h, w, mask) of the block after the current one are loaded while the
+            // current block's gathers are in flight
+            float gh[kRows], gw[kRows], gm[kRows];
+            auto load_geo = [&](const Cursor &c) {
+                if (c.t >= p.total_tiles) return;
+                bool k_ok; int tap, ki, kj, c_abs;
+                chunk_of(c, k_ok, tap, ki, kj, c_abs);
+                const long ch = (long)((c_abs / d.Cd) * d.K + tap);
+                const float *off_b = p.offset + (long)c.tc.b * p.off_bs;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int row = r0 + 32 * u;
-                    float4 h4, l4;
-                    umma::split_tf32(v[u][0], h4.x, l4.x); umma::split_tf32(v[u][1], h4.y, l4.y);
-                    umma::split_tf32(v[u][2], h4.z, l4.z); umma::split_tf32(v[u][3], h4.w, l4.w);
-                    const int at = row * kUK + ((j ^ (row & 7)) << 2);
-                    *reinterpret_cast<float4 *>(a_hi + at) = h4;
-                    *reinterpret_cast<float4 *>(a_lo + at) = l4;
+                for (int u = 0; u < kRows; ++u) {
+                    const long pc = c.oh[u] * d.Wo + c.ow[u];
+                    gh[u] = __ldg(off_b + pc * p.off_ps + (ch * 2) * p.off_cs);
+                    gw[u] = __ldg(off_b + pc * p.off_ps + (ch * 2 + 1) * p.off_cs);
+                    gm[u] = p.mask ? __ldg(p.mask + (long)c.tc.b * p.mask_bs + pc * p.mask_ps + ch * p.mask_cs) : 1.f;
                 }
-                umma::fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) umma::mbar_arrive(&bar_full_a[s]);
+            };
+            load_geo(cs);
+            Cursor cn = cs;               // cursor of the next block (geometry prefetch)
+            while (cs.t < p.total_tiles) {
+                bool k_ok; int tap, ki, kj, c_abs;
+                chunk_of(cs, k_ok, tap, ki, kj, c_abs);
+                const float *x_b = p.x + (long)cs.tc.b * d.HW * d.Cin + c_abs;
+                float4 q[kRows][4];
+                float wgt[kRows][4];
+#pragma unroll
+                for (int u = 0; u < kRows; ++u) {
+                    const float h = (float)(cs.oh[u] * d.stride - d.pad + ki * d.dil) + gh[u];
+                    const float w = (float)(cs.ow[u] * d.stride - d.pad + kj * d.dil) + gw[u];
+                    const Sample sm = make_sample(h, w, d.H, d.W);
+                    const float m = (k_ok && cs.rok[u]) ? gm[u] : 0.f;
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        wgt[u][c4] = sm.w[c4] * m;
+                        q[u][c4] = __ldg(reinterpret_cast<const float4 *>(x_b + (long)sm.i[c4] * d.Cin));
+                    }
+                }
+                advance(cn);
+                load_geo(cn);             // overwrites gh/gw/gm: their last use is above
+                float v[kRows][4];
+#pragma unroll
+                for (int u = 0; u < kRows; ++u) {
+                    v[u][0] = wgt[u][0] * q[u][0].x + wgt[u][1] * q[u][1].x + wgt[u][2] * q[u][2].x + wgt[u][3] * q[u][3].x;
+                    v[u][1] = wgt[u][0] * q[u][0].y + wgt[u][1] * q[u][1].y + wgt[u][2] * q[u][2].y + wgt[u][3] * q[u][3].y;
+                    v[u][2] = wgt[u][0] * q[u][0].z + wgt[u][1] * q[u][1].z + wgt[u][2] * q[u][2].z + wgt[u][3] * q[u][3].z;
+                    v[u][3] = wgt[u][0] * q[u][0].w + wgt[u][1] * q[u][1].w + wgt[u][2] * q[u][2].w + wgt[u][3] * q[u][3].w;
+                }
+                store_block(it, v);
+                cs = cn;
+                ++it;
             }
         }
+        PROF_ADD(1);
+        if (tid == 0) { PROF_FLUSH(1); PROF_FLUSH(2); }
     } else if (warp < kMmaWarp) {
         // ================================ epilogue: TMEM -> registers -> global ==================
         const int q = warp & 3;                                  // TMEM lane quarter
         const int row = q * 32 + lane;
+        const int et = tid - kProdWarps * 32;                    // 0..127 within the epilogue group
         uint32_t ti = 0;
+        int cur_gn = -1;
+        PROF_DECL();
+        PROF_T0();
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
             const TileCoord tc = tile_coord(p, t);
             const int a = ti & 1;
             const int pix = tc.p0 + row;
             const bool p_ok = pix < (int)d.P;
-            umma::mbar_wait_sleep(&bar_acc_full[a], (ti >> 1) & 1);
-            umma::tc_fence_after();
             const int o_base = tc.grp * d.Og + tc.nt * BN;          // first global out channel of the tile
             const int n_valid = min(BN, d.Og - tc.nt * BN);
+            if (tc.grp * p.n_tiles_n + tc.nt != cur_gn) {
+                // (re)build the per-channel affine of this (group, n-tile):
+                //   (acc + bias) * scale + shift  ==  acc * scale + (bias * scale + shift)
+                cur_gn = tc.grp * p.n_tiles_n + tc.nt;
+                asm volatile("bar.sync 1, 128;" ::: "memory");       // previous tile's readers are done
+                if (et < BN) {
+                    float sc = 1.f, sh = 0.f;
+                    if (et < n_valid) {
+                        const int o = o_base + et;
+                        if (p.scale) { sc = __ldg(p.scale + o); sh = __ldg(p.shift + o); }
+                        if (p.bias) sh = fmaf(__ldg(p.bias + o), sc, sh);
+                    }
+                    s_aff[0][et] = sc; s_aff[1][et] = sh;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
             const long pix_g = (long)tc.b * d.P + pix;
             const bool vec_ok = !p.out_nchw && ((d.Cout | o_base) & 3) == 0;
+            umma::mbar_wait_sleep(&bar_acc_full[a], (ti >> 1) & 1);
+            umma::tc_fence_after();
+            PROF_ADD(3);                                   // slot 3: epilogue waiting for an accumulator
 #pragma unroll 1
             for (int n0 = 0; n0 < BN; n0 += 16) {
-                float acc[16];
-                umma::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + a * Cfg::kAccStride + n0, acc);
-                if (!p_ok || n0 >= n_valid) continue;
+                const bool live = p_ok && n0 < n_valid;
+                const bool full = vec_ok && n0 + 16 <= n_valid;
+                float res[16];
+                if (p.residual && live) {                  // issue the residual loads before the TMEM read
+                    if (full) {
+                        const float4 *rp = reinterpret_cast<const float4 *>(p.residual + pix_g * d.Cout + o_base + n0);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int o = o_base + n0 + i;
-                    if (n0 + i < n_valid) {
-                        float tv = acc[i];
-                        if (p.bias) tv += __ldg(p.bias + o);
-                        if (p.scale) tv = fmaf(tv, __ldg(p.scale + o), __ldg(p.shift + o));
-                        if (p.residual)
-                            tv += p.out_nchw ? __ldg(p.residual + ((long)tc.b * d.Cout + o) * d.P + pix)
-                                             : __ldg(p.residual + pix_g * d.Cout + o);
-                        if (p.act == ACT_RELU) tv = fmaxf(tv, 0.f);
-                        else if (p.act == ACT_LEAKY) tv = tv > 0.f ? tv : tv * p.slope;
-                        else if (p.act == ACT_OFFSET_MASK && o >= p.n_offset_ch)
-                            tv = p.mask_scale / (1.f + __expf(-tv));
-                        acc[i] = tv;
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 r4 = __ldg(rp + i);
+                            res[4 * i] = r4.x; res[4 * i + 1] = r4.y; res[4 * i + 2] = r4.z; res[4 * i + 3] = r4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int o = o_base + n0 + i;
+                            res[i] = (n0 + i < n_valid)
+                                         ? (p.out_nchw ? __ldg(p.residual + ((long)tc.b * d.Cout + o) * d.P + pix)
+                                                       : __ldg(p.residual + pix_g * d.Cout + o))
+                                         : 0.f;
+                        }
                     }
                 }
-                if (p.out_nchw) {
+                float acc[16];
+                umma::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + a * Cfg::kAccStride + n0, acc);
+                if (!live) continue;
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 sc = *reinterpret_cast<const float4 *>(&s_aff[0][n0 + i]);
+                    const float4 sh = *reinterpret_cast<const float4 *>(&s_aff[1][n0 + i]);
+                    acc[i] = fmaf(acc[i], sc.x, sh.x); acc[i + 1] = fmaf(acc[i + 1], sc.y, sh.y);
+                    acc[i + 2] = fmaf(acc[i + 2], sc.z, sh.z); acc[i + 3] = fmaf(acc[i + 3], sc.w, sh.w);
+                }
+                if (p.residual) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[i] += res[i];
+                }
+                if (p.act == ACT_RELU) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[i] = fmaxf(acc[i], 0.f);
+                } else if (p.act == ACT_LEAKY) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[i] = acc[i] > 0.f ? acc[i] : acc[i] * p.slope;
+                } else if (p.act == ACT_OFFSET_MASK) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (o_base + n0 + i >= p.n_offset_ch) acc[i] = __fdividef(p.mask_scale, 1.f + __expf(-acc[i]));
+                }
+                if (full) {
+                    float4 *dst = reinterpret_cast<float4 *>(p.out + pix_g * d.Cout + o_base + n0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+                } else if (p.out_nchw) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
                         if (n0 + i < n_valid) p.out[((long)tc.b * d.Cout + o_base + n0 + i) * d.P + pix] = acc[i];
                 } else {
                     float *dst = p.out + pix_g * d.Cout + o_base + n0;
-                    if (vec_ok && n0 + 16 <= n_valid) {
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4)
-                            *reinterpret_cast<float4 *>(dst + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (n0 + i < n_valid) dst[i] = acc[i];
-                    }
+                    for (int i = 0; i < 16; ++i)
+                        if (n0 + i < n_valid) dst[i] = acc[i];
                 }
             }
             umma::tc_fence_before();
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(&bar_acc_empty[a]);
+            PROF_ADD(4);                                   // slot 4: epilogue work
         }
-    } else if (warp == kLoadWarp) {
+        if (warp == kProdWarps && lane == 0) { PROF_FLUSH(3); PROF_FLUSH(4); }
+    } else {
+        if (warp == kLoadWarp && lane == 0) {
         // ================================ weight loader (bulk async copy) ========================
-        if (lane == 0) {
             uint32_t it = 0;
+            PROF_DECL();
+            PROF_T0();
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const TileCoord tc = tile_coord(p, t);
                 const uint8_t *src = reinterpret_cast<const uint8_t *>(p.wpack) +
@@ -335,27 +487,34 @@ conv_umma_kernel(const ConvParams p) {
                     const int s = it % S;
                     const uint32_t ph = (it / S) & 1;
                     umma::mbar_wait_sleep(&bar_empty[s], ph ^ 1);
+                    PROF_ADD(5);                           // slot 5: loader waiting for a free stage
                     umma::mbar_expect_tx(&bar_full_b[s], 2 * Cfg::kBTileBytes);
                     umma::bulk_g2s(smem + (size_t)s * Cfg::kStageBytes + 2 * kATileBytes,
                                    src + (size_t)kb * 2 * Cfg::kBTileBytes, 2 * Cfg::kBTileBytes, &bar_full_b[s]);
+                    PROF_ADD(6);
                 }
             }
-        }
-    } else {
+            PROF_FLUSH(5); PROF_FLUSH(6);
+        } else if (warp == kMmaWarp && lane == 0) {
         // ================================ MMA issuer (one thread) ================================
-        if (lane == 0) {
             constexpr uint32_t idesc = umma::make_idesc_tf32(kUM, BN);
             uint32_t it = 0, ti = 0;
+            PROF_DECL();
+            PROF_T0();
+            const long long prof_start = clock64();
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
                 const int a = ti & 1;
                 umma::mbar_wait_sleep(&bar_acc_empty[a], ((ti >> 1) & 1) ^ 1);   // epilogue drained this accumulator
                 umma::tc_fence_after();
+                PROF_ADD(7);                               // slot 7: MMA waiting for a drained accumulator
                 const uint32_t d_tmem = tmem_base + a * Cfg::kAccStride;
                 for (int kb = 0; kb < p.KB; ++kb, ++it) {
                     const int s = it % S;
                     const uint32_t ph = (it / S) & 1;
                     umma::mbar_wait_sleep(&bar_full_a[s], ph);
+                    PROF_ADD(8);                           // slot 8: MMA waiting for A
                     umma::mbar_wait_sleep(&bar_full_b[s], ph);
+                    PROF_ADD(9);                           // slot 9: MMA waiting for B
                     umma::tc_fence_after();
                     const uint32_t a0 = umma::smem_u32(smem + (size_t)s * Cfg::kStageBytes);
                     const uint64_t a_hi = umma::make_desc_sw128(a0), a_lo = umma::make_desc_sw128(a0 + kATileBytes);
@@ -370,9 +529,14 @@ conv_umma_kernel(const ConvParams p) {
                         umma::mma_tf32(d_tmem, umma::desc_advance(a_hi, adv), umma::desc_advance(b_hi, adv), idesc, 1);
                     }
                     umma::tc_commit(&bar_empty[s]);      // frees this stage when the MMAs above retire
+                    PROF_ADD(10);                          // slot 10: issuing MMAs
                 }
                 umma::tc_commit(&bar_acc_full[a]);       // accumulator of this tile complete
             }
+#ifdef AANET_PROFILE
+            prof_acc[0] = clock64() - prof_start; prof_acc[11] = ti;
+#endif
+            PROF_FLUSH(0); PROF_FLUSH(7); PROF_FLUSH(8); PROF_FLUSH(9); PROF_FLUSH(10); PROF_FLUSH(11);
         }
     }
     umma::tc_fence_before();
@@ -399,6 +563,7 @@ bool conv_umma_supported(const MdcnDims &d, bool deform) {
     if (deform && (d.Cd % 4)) return false;
     if (d.P > 0x3fffffffLL || d.HW > 0x3fffffffLL) return false;
     if ((long)d.B * ceil_div_ll(d.P, kUM) > 0x3fffffffLL) return false;
+    if (ceil_div(d.K * d.Cg, kUK) > kMaxKB || d.Cg > 0xffff || d.kh > 15 || d.kw > 15) return false;
     return true;
 }
 
@@ -435,6 +600,12 @@ static int launch_one(const ConvParams &p, cudaStream_t stream) {
     conv_umma_kernel<BN, DEFORM><<<grid, kUThreads, smem, stream>>>(p);
     return check_launch();
 }
+
+#ifdef AANET_PROFILE
+extern "C" __attribute__((visibility("default"))) int aanet_profile_read(long long *host_dst) {
+    return (int)cudaMemcpyFromSymbol(host_dst, g_prof, sizeof(long long) * 148 * 16);
+}
+#endif
 
 int conv_umma_launch(ConvParams p, bool deform, cudaStream_t stream) {
     const MdcnDims &d = p.d;

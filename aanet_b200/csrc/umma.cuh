@@ -68,6 +68,18 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) 
     }
 }
 
+// Register rebalancing between warp roles; executed by every warp of an aligned 4-warp group.
+template <int REGS> __device__ __forceinline__ void setmaxnreg_inc() {
+#ifndef AANET_NO_SETMAXNREG
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS));
+#endif
+}
+template <int REGS> __device__ __forceinline__ void setmaxnreg_dec() {
+#ifndef AANET_NO_SETMAXNREG
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS));
+#endif
+}
+
 // generic-proxy smem writes -> visible to the async proxy (tensor core / bulk copy engine)
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
