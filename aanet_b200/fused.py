@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .streams import fork_join
 from .nets.deform import DeformSimpleBottleneck, SimpleBottleneck, bn_affine
 
 
@@ -114,24 +115,42 @@ class FusedAggregation:
         self.final = [_Conv(c) for c in agg.final_conv]
 
     def __call__(self, cost_volume):
-        xs = [ops.nchw_to_nhwc(c) for c in cost_volume]
-        for branches, fuse, slope in self.stages:
-            for s, blocks in enumerate(branches):
+        dev = cost_volume[0].device
+        keep = []                       # every intermediate stays alive until the final join (streams.py)
+
+        def track(t):
+            keep.append(t)
+            return t
+
+        def branch(s, blocks, x):
+            def go():
+                y = x
                 for blk in blocks:
-                    xs[s] = blk(xs[s])
+                    y = track(blk(y))
+                return y
+            return go
+
+        xs = fork_join(dev, [(lambda c=c: track(ops.nchw_to_nhwc(c))) for c in cost_volume])
+        for branches, fuse, slope in self.stages:
+            # ISA: the scales are independent -> one stream each
+            xs = fork_join(dev, [branch(s, blocks, xs[s]) for s, blocks in enumerate(branches)])
             if fuse is None:
                 continue
-            outs = []
-            for row in fuse:
-                terms = []
-                for j, chain in enumerate(row):
-                    t = xs[j]
-                    for conv in chain:
-                        t = conv(t)
-                    terms.append(t)
-                outs.append(ops.csa_fuse_nhwc(terms, slope))
-            xs = outs
-        return [conv(xs[s], out_nchw=True) for s, conv in enumerate(self.final)]
+            # CSA: output scale i needs every input scale; the output scales are independent
+            def fuse_row(row):
+                def go():
+                    terms = []
+                    for j, chain in enumerate(row):
+                        t = xs[j]
+                        for conv in chain:
+                            t = track(conv(t))
+                        terms.append(t)
+                    return track(ops.csa_fuse_nhwc(terms, slope))
+                return go
+            xs = fork_join(dev, [fuse_row(row) for row in fuse])
+        outs = fork_join(dev, [(lambda s=s, conv=conv: conv(xs[s], out_nchw=True)) for s, conv in enumerate(self.final)])
+        del keep
+        return outs
 
 
 def run(agg, cost_volume):

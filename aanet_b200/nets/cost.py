@@ -5,9 +5,11 @@ reference constructors and call conventions (nets/cost.py:5-76).  Only the corre
 (cost.py:40-48) is on the hot path and implemented; 'difference' / 'concat' (cost.py:22-38) build
 5-D volumes for the StereoNet/PSMNet/GC-Net ablations and are out of scope.
 """
+import torch
 import torch.nn as nn
 
 from .. import ops
+from ..streams import fork_join
 
 
 class CostVolume(nn.Module):
@@ -34,5 +36,10 @@ class CostVolumePyramid(nn.Module):
     def forward(self, left_feature_pyramid, right_feature_pyramid):
         if self.feature_similarity != 'correlation':
             raise NotImplementedError("aanet_b200 implements feature_similarity='correlation' only")
-        return [ops.correlation(l, r, self.max_disp // (2 ** s))
-                for s, (l, r) in enumerate(zip(left_feature_pyramid, right_feature_pyramid))]
+        pairs = list(zip(left_feature_pyramid, right_feature_pyramid))
+        if pairs and pairs[0][0].is_cuda and not torch.is_grad_enabled():
+            # inference: the scales are independent, run them on parallel streams
+            return fork_join(pairs[0][0].device,
+                             [(lambda s=s, l=l, r=r: ops.correlation(l, r, self.max_disp // (2 ** s)))
+                              for s, (l, r) in enumerate(pairs)])
+        return [ops.correlation(l, r, self.max_disp // (2 ** s)) for s, (l, r) in enumerate(pairs)]

@@ -1,0 +1,45 @@
+"""Fork/join of independent per-scale work onto side streams.
+
+The three pyramid scales of the hot path are independent inside the cost-volume stage and inside the ISA
+half of every aggregation module.  The 1/6 and 1/12 scale kernels are launch/latency bound (26-104 tiles
+on 148 SMs), so running them next to the 1/3 scale work hides them almost completely.  The pattern is
+plain event fork/join, which CUDA-graph capture records as parallel branches.
+
+Allocator note: a tensor produced on a side stream and consumed on the main stream (or vice versa) must not
+be freed while the other stream may still touch it.  Callers keep every intermediate alive until the join
+that ends their forward (see FusedAggregation.__call__), so blocks only return to their pools after all
+consumers were enqueued and the next fork orders any reuse behind them.
+"""
+import torch
+
+_side = {}
+
+
+def side_streams(device, n):
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    pool = _side.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device))
+    return pool[:n]
+
+
+def fork_join(device, fns):
+    """Run fns[0] on the current stream and fns[1:] on side streams; returns their results in order."""
+    if len(fns) == 1:
+        return [fns[0]()]
+    main = torch.cuda.current_stream(device)
+    start = torch.cuda.Event()
+    start.record(main)
+    results = [None] * len(fns)
+    done = []
+    for i, (fn, s) in enumerate(zip(fns[1:], side_streams(device, len(fns) - 1)), 1):
+        s.wait_event(start)
+        with torch.cuda.stream(s):
+            results[i] = fn()
+            e = torch.cuda.Event()
+            e.record(s)
+        done.append(e)
+    results[0] = fns[0]()
+    for e in done:
+        main.wait_event(e)
+    return results
