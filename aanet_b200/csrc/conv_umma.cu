@@ -18,17 +18,20 @@
 // shaped boundary are done by transpose_kernel.
 //
 // Blackwell mapping.  A CTA is persistent (grid = #SMs) and walks 128-pixel tiles.  M = 128 pixels is
-// the UMMA M (one TMEM lane per pixel), N = BN output channels, K walks (tap, channel) in blocks of
+// the UMMA M (one TMEM lane per pixel), N = BN <= 64 output channels (wider layers = several N tiles), K walks (tap, channel) in blocks of
 // 32 tf32 = one 128-byte swizzle row.  Warp roles:
-//   warps 0-15  A producers: lane = (pixel row, 16-byte chunk); LDG.128 (4 per item for DEFORM, 1 for
-//               DENSE), bilinear combine, split into tf32 hi + lo (cvt.rna + exact remainder), two
-//               STS.128 into SWIZZLE_128B K-major tiles; fence.proxy.async + mbarrier arrive.  DENSE keeps
-//               three K blocks of loads in flight per thread (register ring); DEFORM prefetches the next
-//               block's offsets/mask while the current block's gathers are outstanding.
+//   warps 0-15  A producers, 4 groups of 4 warps; a group fills a whole stage, so four K blocks are in
+//               production at once.  lane = (pixel row, 16-byte chunk): LDG.128 (4 per item for DEFORM, 1
+//               for DENSE), bilinear combine, split into tf32 hi + lo (cvt.rna + exact remainder), two
+//               STS.128 into SWIZZLE_128B K-major tiles; fence.proxy.async + mbarrier arrive.  Each lane
+//               owns the geometry (output coordinates, bilinear sample) of ONE of the 8 rows its row group
+//               covers and broadcasts it with __shfl_sync, so the sampling math is done once per
+//               (pixel, tap, deformable group) instead of once per 16-byte chunk.
 //   warp 21     streams the pre-split, pre-swizzled weight block of the stage with one cp.async.bulk.
-//   warp 20     one thread issues tcgen05.mma.kind::tf32 three times per K step (lo*hi + hi*lo + hi*hi:
-//               fp32-grade accuracy, the parity bar is 1e-4) into one of two TMEM accumulators and
-//               releases the stage with tcgen05.commit.
+//   warp 20     one thread issues the 3xTF32 products per K step (hi*hi + hi*lo + lo*hi: fp32-grade accuracy,
+//               the parity bar is 1e-4) as tcgen05.mma.kind::tf32 into one of two TMEM accumulators -- two
+//               MMAs with the stacked [B_hi|B_lo] operand at BN <= 64, three otherwise -- and releases the
+//               stage with tcgen05.commit.
 //   warps 16-19 epilogue: tcgen05.ld (lane = pixel), bias / folded-BN affine / residual / activation,
 //               128-bit channels-last stores (or coalesced NCHW stores); runs one tile behind the MMA.
 // All hand-offs are mbarriers; the ring (4 stages at BN = 64) runs across tile boundaries.
@@ -39,14 +42,12 @@ namespace aanet {
 
 constexpr int kUM = 128;                 // pixels per tile (UMMA M)
 constexpr int kUK = 32;                  // K per stage (one 128-byte swizzle row of tf32)
-constexpr int kProdWarps = 16;           // 4 warp groups of A producers
-constexpr int kRows = 128 * 8 / (kProdWarps * 32);   // pixel rows per producer thread (2)
-constexpr int kRowStep = kProdWarps * 4;              // row distance between a thread's items (64)
+constexpr int kProdWarps = 16;           // A producers: kGroups groups of 4 warps
+constexpr int kGroups = 4;               // each group fills one whole stage; 4 K blocks are in production at once
 constexpr int kMmaWarp = 20, kLoadWarp = 21;
 constexpr int kUThreads = 22 * 32;
 // 704 threads -> 88 registers per thread.  (setmaxnreg rebalancing between the roles faulted on the B200
 // test box with "unspecified launch failure"; the producers fit in the uniform budget without spills.)
-constexpr int kDensePrefetch = 3;        // K blocks of loads in flight per dense producer thread
 constexpr int kATileBytes = kUM * kUK * 4;   // 16 KB (hi); same for lo
 constexpr int kSmemBudget = 200 * 1024;   // dynamic; ~9 KB of static tables on top (227 KB per SM)
 constexpr int kMaxKB = 256;               // K <= 8192
@@ -89,8 +90,15 @@ __device__ long long g_prof[148 * 16];
 template <int BN> struct EngineCfg {
     static constexpr int kBTileBytes = BN * kUK * 4;
     static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;
-    static constexpr int kStages = (kSmemBudget / kStageBytes) > 6 ? 6 : (kSmemBudget / kStageBytes);
-    static constexpr int kAccStride = BN <= 32 ? 32 : BN <= 64 ? 64 : 128;   // TMEM columns per accumulator
+    // One stage per producer group: group g always refills stage g, so a group can never run two mbarrier
+    // phases ahead of the stage it waits on (with stages != groups the parity wait aliases).
+    static constexpr int kStages = kGroups;
+    static_assert(BN <= 64 && kStages * kStageBytes <= kSmemBudget, "N tile is capped at 64 (4 stages must fit)");
+    // The hi and lo weight tiles (adjacent in smem) are fed as ONE N = 2*BN operand, so a K step is
+    // A_hi x [B_hi | B_lo] (columns [0,BN) and [BN,2BN)) + A_lo x B_hi (columns [0,BN)): 2 MMAs and 14 KB of
+    // smem operand reads instead of 3 MMAs and 18 KB; the epilogue adds the two column halves.
+    static constexpr int kAccCols = 2 * BN;
+    static constexpr int kAccStride = kAccCols <= 32 ? 32 : kAccCols <= 64 ? 64 : 128;   // TMEM columns per accumulator
     static constexpr uint32_t kTmemCols = 2 * kAccStride;                     // two accumulators
     static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024;
 };
@@ -173,6 +181,9 @@ conv_umma_kernel(const ConvParams p) {
     __shared__ uint32_t s_tmem;
     // (tap, first channel) of every 16-byte chunk of every K block: c | ki << 16 | kj << 20 | tap << 24 | ok << 31
     __shared__ uint32_t s_chunk[kMaxKB * 8];
+    // DEFORM: per K block, index of the first chunk whose (tap, deformable group) differs from chunk 0
+    // (8 = none) | 16 if the block has at most two such runs (the shuffle-shared geometry path applies)
+    __shared__ uint8_t s_kbinfo[kMaxKB];
     // epilogue affine of the current (group, n-tile): out = acc * s_aff[0][n] + s_aff[1][n]
     __shared__ __align__(16) float s_aff[2][BN];
 
@@ -182,7 +193,7 @@ conv_umma_kernel(const ConvParams p) {
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            umma::mbar_init(&bar_full_a[s], kProdWarps);   // one arrival per producer warp
+            umma::mbar_init(&bar_full_a[s], kProdWarps / kGroups);   // one arrival per warp of the filling group
             umma::mbar_init(&bar_full_b[s], 1);            // expect_tx arrival + bulk-copy bytes
             umma::mbar_init(&bar_empty[s], 1);             // tcgen05.commit
         }
@@ -203,6 +214,29 @@ conv_umma_kernel(const ConvParams p) {
         }
         s_chunk[i] = e;
     }
+    if (DEFORM) {
+        for (int kb = tid; kb < p.KB; kb += kUThreads) {
+            int key[8];
+            for (int c8 = 0; c8 < 8; ++c8) {
+                const int kk = kb * kUK + c8 * 4;
+                if (kk < p.K) {
+                    const int tap = kk / d.Cg, c = kk - tap * d.Cg;
+                    key[c8] = tap * 4096 + c / d.Cd;          // (tap, deformable group within the conv group)
+                } else {
+                    key[c8] = -1 - c8;                        // padding chunks: weight 0, geometry irrelevant
+                }
+            }
+            int split = 8;
+            for (int c8 = 1; c8 < 8; ++c8)
+                if (key[c8] >= 0 && key[c8] != key[0]) { split = c8; break; }
+            bool two = true;
+            for (int c8 = split; c8 < 8; ++c8)
+                if (key[c8] >= 0 && key[c8] != key[split]) two = false;
+            for (int c8 = 1; c8 < split && c8 < 8; ++c8)
+                if (key[c8] >= 0 && key[c8] != key[0]) two = false;
+            s_kbinfo[kb] = (uint8_t)(split | (two ? 16 : 0));
+        }
+    }
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
@@ -210,158 +244,170 @@ conv_umma_kernel(const ConvParams p) {
 
     if (warp < kProdWarps) {
         // ================================ A producers ===========================================
-        // item = (row, 16-byte chunk): chunk j = tid % 8 (fixed), rows r0 + 64*u, u = 0..kRows-1.
-        // A cursor walks the (tile, K block) sequence of this CTA; the load cursor runs ahead of the
-        // store cursor so that global latency is covered by loads already in flight.
-        const int j = tid & 7, r0 = tid >> 3;
+        // Group g (4 warps) fills every kGroups-th K block of the CTA's (tile, K block) sequence on its own,
+        // so four stages are in production concurrently and the wait / fence / arrive chain is paid once per
+        // 8 rows per thread.  Inside a group, the 8 lanes t..t+7 of a "row group" cover the eight 16-byte
+        // chunks of rows row0..row0+7: lane j handles chunk j of every row and OWNS the geometry of row
+        // row0 + j (output coordinates; for DEFORM the bilinear sample), broadcast with __shfl_sync.
+        const int grpi = warp >> 2;
+        const int tg = tid & 127, j = tg & 7;
+        const int row0 = (tg >> 3) * 8;
+        const int lane_base = lane & ~7;
         const int P32 = (int)d.P;
         PROF_DECL();
         PROF_T0();
 
-        struct Cursor {
-            int t, kb;
-            TileCoord tc;
-            int oh[kRows], ow[kRows];
-            bool rok[kRows];
-        };
-        auto enter_tile = [&](Cursor &c) {
-            if (c.t >= p.total_tiles) return;
-            c.tc = tile_coord(p, c.t);
-#pragma unroll
-            for (int u = 0; u < kRows; ++u) {
-                const int px = c.tc.p0 + r0 + kRowStep * u;
-                c.rok[u] = px < P32;
-                const int pc = c.rok[u] ? px : P32 - 1;
-                c.oh[u] = pc / d.Wo;
-                c.ow[u] = pc - c.oh[u] * d.Wo;
+        int t = blockIdx.x, kb = grpi;
+        uint32_t it = grpi;
+        while (kb >= p.KB && t < p.total_tiles) { kb -= p.KB; t += gridDim.x; }
+        int cur_t = -1;
+        TileCoord tc = {0, 0, 0, 0};
+        int my_oh = 0, my_ow = 0;
+        bool my_ok = false;
+
+        while (t < p.total_tiles) {
+            if (t != cur_t) {                       // entered a new tile: coordinates of the row this lane owns
+                cur_t = t;
+                tc = tile_coord(p, t);
+                const int px = tc.p0 + row0 + j;
+                my_ok = px < P32;
+                const int pc = my_ok ? px : P32 - 1;
+                my_oh = pc / d.Wo;
+                my_ow = pc - my_oh * d.Wo;
             }
-        };
-        auto advance = [&](Cursor &c) {
-            if (++c.kb == p.KB) { c.kb = 0; c.t += gridDim.x; enter_tile(c); }
-        };
-        // (tap, first channel) of this thread's chunk in K block kb: table lookup, no divisions
-        auto chunk_of = [&](const Cursor &c, bool &k_ok, int &tap, int &ki, int &kj, int &c_abs) {
-            const uint32_t e = s_chunk[c.kb * 8 + j];
-            k_ok = (e >> 31) != 0;
-            c_abs = c.tc.grp * d.Cg + (int)(e & 0xffffu);
-            ki = (e >> 16) & 15; kj = (e >> 20) & 15; tap = (e >> 24) & 127;
-        };
-        auto store_block = [&](uint32_t it, const float (&v)[kRows][4]) {
             const int s = it % S;
             const uint32_t ph = (it / S) & 1;
             float *a_hi = reinterpret_cast<float *>(smem + (size_t)s * Cfg::kStageBytes);
             float *a_lo = a_hi + kATileBytes / 4;
-            PROF_ADD(1);                                   // slot 1: everything but the two waits below
-            umma::mbar_wait(&bar_empty[s], ph ^ 1);
-            PROF_ADD(2);                                   // slot 2: waiting for a free stage
-#pragma unroll
-            for (int u = 0; u < kRows; ++u) {
-                const int row = r0 + kRowStep * u;
+            const uint32_t e = s_chunk[kb * 8 + j];           // this lane's chunk of the K block
+            const bool k_ok = (e >> 31) != 0;
+            const int c_abs = tc.grp * d.Cg + (int)(e & 0xffffu);
+            const float *x_b = p.x + (long)tc.b * d.HW * d.Cin + c_abs;
+
+            auto store_row = [&](int u, const float (&v)[4]) {
+                const int row = row0 + u;
                 float4 h4, l4;
-                umma::split_tf32(v[u][0], h4.x, l4.x); umma::split_tf32(v[u][1], h4.y, l4.y);
-                umma::split_tf32(v[u][2], h4.z, l4.z); umma::split_tf32(v[u][3], h4.w, l4.w);
+                umma::split_tf32(v[0], h4.x, l4.x); umma::split_tf32(v[1], h4.y, l4.y);
+                umma::split_tf32(v[2], h4.z, l4.z); umma::split_tf32(v[3], h4.w, l4.w);
                 const int at = row * kUK + ((j ^ (row & 7)) << 2);
                 *reinterpret_cast<float4 *>(a_hi + at) = h4;
                 *reinterpret_cast<float4 *>(a_lo + at) = l4;
+            };
+
+            if (!DEFORM) {
+                const int ki = (e >> 16) & 15, kj = (e >> 20) & 15;
+                // owner lanes publish (oh, ow, valid) of their row; every lane gathers its chunk of all 8 rows
+                const int my_pack = (my_oh << 16) | my_ow | (my_ok ? (int)0x80000000 : 0);
+                float4 q[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int pk = __shfl_sync(0xffffffffu, my_pack, lane_base + u);
+                    const int hi_ = ((pk >> 16) & 0x7fff) * d.stride - d.pad + ki * d.dil;
+                    const int wi_ = (pk & 0xffff) * d.stride - d.pad + kj * d.dil;
+                    const bool ok = k_ok && pk < 0 && hi_ >= 0 && hi_ < d.H && wi_ >= 0 && wi_ < d.W;
+                    q[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok) q[u] = __ldg(reinterpret_cast<const float4 *>(x_b + ((long)hi_ * d.W + wi_) * d.Cin));
+                }
+                PROF_ADD(1);
+                umma::mbar_wait(&bar_empty[s], ph ^ 1);
+                PROF_ADD(2);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float v[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+                    store_row(u, v);
+                }
+            } else {
+                const uint8_t info = s_kbinfo[kb];
+                const int split = info & 15;
+                const float *off_b = p.offset + (long)tc.b * p.off_bs;
+                const float *mask_b = p.mask ? p.mask + (long)tc.b * p.mask_bs : nullptr;
+                // bilinear sample of (pixel of `pk`, chunk entry `ce`): 4 clamped indices + 4 weights (mask folded in)
+                auto geometry = [&](int oh, int ow, bool ok, uint32_t ce, int (&gi)[4], float (&gwt)[4]) {
+                    const bool ce_ok = (ce >> 31) != 0;
+                    const int tap = (ce >> 24) & 127, ki = (ce >> 16) & 15, kj = (ce >> 20) & 15;
+                    const long ch = (long)(((tc.grp * d.Cg + (int)(ce & 0xffffu)) / d.Cd) * d.K + tap);
+                    const long pc = (long)oh * d.Wo + ow;
+                    const float gh = __ldg(off_b + pc * p.off_ps + (ch * 2) * p.off_cs);
+                    const float gw = __ldg(off_b + pc * p.off_ps + (ch * 2 + 1) * p.off_cs);
+                    const float gm = mask_b ? __ldg(mask_b + pc * p.mask_ps + ch * p.mask_cs) : 1.f;
+                    const Sample sm = make_sample((float)(oh * d.stride - d.pad + ki * d.dil) + gh,
+                                                  (float)(ow * d.stride - d.pad + kj * d.dil) + gw, d.H, d.W);
+                    const float m = (ok && ce_ok) ? gm : 0.f;
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) { gi[c4] = sm.i[c4]; gwt[c4] = sm.w[c4] * m; }
+                };
+                auto gather = [&](const int (&gi)[4], float4 (&q)[4]) {
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4)
+                        q[c4] = __ldg(reinterpret_cast<const float4 *>(x_b + (long)gi[c4] * d.Cin));
+                };
+                auto combine = [&](const float (&w4)[4], const float4 (&q)[4], float (&v)[4]) {
+                    v[0] = w4[0] * q[0].x + w4[1] * q[1].x + w4[2] * q[2].x + w4[3] * q[3].x;
+                    v[1] = w4[0] * q[0].y + w4[1] * q[1].y + w4[2] * q[2].y + w4[3] * q[3].y;
+                    v[2] = w4[0] * q[0].z + w4[1] * q[1].z + w4[2] * q[2].z + w4[3] * q[3].z;
+                    v[3] = w4[0] * q[0].w + w4[1] * q[1].w + w4[2] * q[2].w + w4[3] * q[3].w;
+                };
+                int ri[2][4];
+                float rw[2][4];
+                float4 q[2][4];
+                bool waited = false;
+                if (info & 16) {
+                    // shared path: this lane samples ITS row once per run (at most 2 runs per K block) ...
+                    int ia[4], ib[4];
+                    float wa[4], wb[4];
+                    geometry(my_oh, my_ow, my_ok, s_chunk[kb * 8], ia, wa);
+                    if (split < 8) geometry(my_oh, my_ow, my_ok, s_chunk[kb * 8 + split], ib, wb);
+                    const bool second = j >= split;
+                    // ... and every lane receives the sample of row u from its owner (lane_base + u)
+                    auto fetch = [&](int u, int (&gi)[4], float (&gwt)[4]) {
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            gi[c4] = __shfl_sync(0xffffffffu, ia[c4], lane_base + u);
+                            gwt[c4] = __shfl_sync(0xffffffffu, wa[c4], lane_base + u);
+                        }
+                        if (split < 8) {           // block-uniform
+#pragma unroll
+                            for (int c4 = 0; c4 < 4; ++c4) {
+                                const int i2 = __shfl_sync(0xffffffffu, ib[c4], lane_base + u);
+                                const float w2 = __shfl_sync(0xffffffffu, wb[c4], lane_base + u);
+                                if (second) { gi[c4] = i2; gwt[c4] = w2; }
+                            }
+                        }
+                    };
+                    fetch(0, ri[0], rw[0]);
+                    gather(ri[0], q[0]);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int cur = u & 1, nxt = cur ^ 1;
+                        if (u + 1 < 8) { fetch(u + 1, ri[nxt], rw[nxt]); gather(ri[nxt], q[nxt]); }
+                        float v[4];
+                        combine(rw[cur], q[cur], v);
+                        if (!k_ok) { v[0] = 0.f; v[1] = 0.f; v[2] = 0.f; v[3] = 0.f; }     // K padding
+                        if (!waited) { PROF_ADD(1); umma::mbar_wait(&bar_empty[s], ph ^ 1); PROF_ADD(2); waited = true; }
+                        store_row(u, v);
+                    }
+                } else {
+                    // general path (more than two (tap, group) runs in the block: tiny channel counts): every
+                    // lane samples every row for its own chunk
+                    const int my_pack = (my_oh << 16) | my_ow | (my_ok ? (int)0x80000000 : 0);
+#pragma unroll 1
+                    for (int u = 0; u < 8; ++u) {
+                        const int pk = __shfl_sync(0xffffffffu, my_pack, lane_base + u);
+                        geometry((pk >> 16) & 0x7fff, pk & 0xffff, pk < 0, e, ri[0], rw[0]);
+                        gather(ri[0], q[0]);
+                        float v[4];
+                        combine(rw[0], q[0], v);
+                        if (!waited) { PROF_ADD(1); umma::mbar_wait(&bar_empty[s], ph ^ 1); PROF_ADD(2); waited = true; }
+                        store_row(u, v);
+                    }
+                }
             }
             umma::fence_proxy_async();
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(&bar_full_a[s]);
-        };
 
-        Cursor cs;                        // store cursor
-        cs.t = blockIdx.x; cs.kb = 0;
-        enter_tile(cs);
-        uint32_t it = 0;                  // K-block counter across tiles (stage / phase)
-
-        if (!DEFORM) {
-            Cursor cl = cs;               // load cursor, kDensePrefetch blocks ahead
-            float4 ring[kDensePrefetch][kRows];
-            auto issue = [&](float4 (&dst)[kRows]) {
-                if (cl.t >= p.total_tiles) return;
-                bool k_ok; int tap, ki, kj, c_abs;
-                chunk_of(cl, k_ok, tap, ki, kj, c_abs);
-                const float *x_b = p.x + (long)cl.tc.b * d.HW * d.Cin + c_abs;
-#pragma unroll
-                for (int u = 0; u < kRows; ++u) {
-                    const int hi_ = cl.oh[u] * d.stride - d.pad + ki * d.dil;
-                    const int wi_ = cl.ow[u] * d.stride - d.pad + kj * d.dil;
-                    const bool ok = k_ok && cl.rok[u] && hi_ >= 0 && hi_ < d.H && wi_ >= 0 && wi_ < d.W;
-                    dst[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok) dst[u] = __ldg(reinterpret_cast<const float4 *>(x_b + ((long)hi_ * d.W + wi_) * d.Cin));
-                }
-                advance(cl);
-            };
-#pragma unroll
-            for (int f = 0; f < kDensePrefetch; ++f) issue(ring[f]);
-            while (cs.t < p.total_tiles) {
-#pragma unroll
-                for (int f = 0; f < kDensePrefetch; ++f) {
-                    if (cs.t < p.total_tiles) {
-                        float v[kRows][4];
-#pragma unroll
-                        for (int u = 0; u < kRows; ++u) {
-                            v[u][0] = ring[f][u].x; v[u][1] = ring[f][u].y; v[u][2] = ring[f][u].z; v[u][3] = ring[f][u].w;
-                        }
-                        store_block(it, v);
-                        issue(ring[f]);
-                        advance(cs);
-                        ++it;
-                    }
-                }
-            }
-        } else {
-            // geometry inputs (offset h, w, mask) of the block after the current one are loaded while the
-            // current block's gathers are in flight
-            float gh[kRows], gw[kRows], gm[kRows];
-            auto load_geo = [&](const Cursor &c) {
-                if (c.t >= p.total_tiles) return;
-                bool k_ok; int tap, ki, kj, c_abs;
-                chunk_of(c, k_ok, tap, ki, kj, c_abs);
-                const long ch = (long)((c_abs / d.Cd) * d.K + tap);
-                const float *off_b = p.offset + (long)c.tc.b * p.off_bs;
-#pragma unroll
-                for (int u = 0; u < kRows; ++u) {
-                    const long pc = c.oh[u] * d.Wo + c.ow[u];
-                    gh[u] = __ldg(off_b + pc * p.off_ps + (ch * 2) * p.off_cs);
-                    gw[u] = __ldg(off_b + pc * p.off_ps + (ch * 2 + 1) * p.off_cs);
-                    gm[u] = p.mask ? __ldg(p.mask + (long)c.tc.b * p.mask_bs + pc * p.mask_ps + ch * p.mask_cs) : 1.f;
-                }
-            };
-            load_geo(cs);
-            Cursor cn = cs;               // cursor of the next block (geometry prefetch)
-            while (cs.t < p.total_tiles) {
-                bool k_ok; int tap, ki, kj, c_abs;
-                chunk_of(cs, k_ok, tap, ki, kj, c_abs);
-                const float *x_b = p.x + (long)cs.tc.b * d.HW * d.Cin + c_abs;
-                float4 q[kRows][4];
-                float wgt[kRows][4];
-#pragma unroll
-                for (int u = 0; u < kRows; ++u) {
-                    const float h = (float)(cs.oh[u] * d.stride - d.pad + ki * d.dil) + gh[u];
-                    const float w = (float)(cs.ow[u] * d.stride - d.pad + kj * d.dil) + gw[u];
-                    const Sample sm = make_sample(h, w, d.H, d.W);
-                    const float m = (k_ok && cs.rok[u]) ? gm[u] : 0.f;
-#pragma unroll
-                    for (int c4 = 0; c4 < 4; ++c4) {
-                        wgt[u][c4] = sm.w[c4] * m;
-                        q[u][c4] = __ldg(reinterpret_cast<const float4 *>(x_b + (long)sm.i[c4] * d.Cin));
-                    }
-                }
-                advance(cn);
-                load_geo(cn);             // overwrites gh/gw/gm: their last use is above
-                float v[kRows][4];
-#pragma unroll
-                for (int u = 0; u < kRows; ++u) {
-                    v[u][0] = wgt[u][0] * q[u][0].x + wgt[u][1] * q[u][1].x + wgt[u][2] * q[u][2].x + wgt[u][3] * q[u][3].x;
-                    v[u][1] = wgt[u][0] * q[u][0].y + wgt[u][1] * q[u][1].y + wgt[u][2] * q[u][2].y + wgt[u][3] * q[u][3].y;
-                    v[u][2] = wgt[u][0] * q[u][0].z + wgt[u][1] * q[u][1].z + wgt[u][2] * q[u][2].z + wgt[u][3] * q[u][3].z;
-                    v[u][3] = wgt[u][0] * q[u][0].w + wgt[u][1] * q[u][1].w + wgt[u][2] * q[u][2].w + wgt[u][3] * q[u][3].w;
-                }
-                store_block(it, v);
-                cs = cn;
-                ++it;
-            }
+            kb += kGroups; it += kGroups;
+            while (kb >= p.KB && t < p.total_tiles) { kb -= p.KB; t += gridDim.x; }
         }
         PROF_ADD(1);
         if (tid == 0) { PROF_FLUSH(1); PROF_FLUSH(2); }
@@ -428,6 +474,12 @@ conv_umma_kernel(const ConvParams p) {
                 }
                 float acc[16];
                 umma::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + a * Cfg::kAccStride + n0, acc);
+                {                                          // + A_hi x B_lo half
+                    float acc2[16];
+                    umma::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + a * Cfg::kAccStride + BN + n0, acc2);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[i] += acc2[i];
+                }
                 if (!live) continue;
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) {
@@ -498,6 +550,7 @@ conv_umma_kernel(const ConvParams p) {
         } else if (warp == kMmaWarp && lane == 0) {
         // ================================ MMA issuer (one thread) ================================
             constexpr uint32_t idesc = umma::make_idesc_tf32(kUM, BN);
+            constexpr uint32_t idesc2 = umma::make_idesc_tf32(kUM, 2 * BN);   // stacked [B_hi | B_lo]
             uint32_t it = 0, ti = 0;
             PROF_DECL();
             PROF_T0();
@@ -518,15 +571,13 @@ conv_umma_kernel(const ConvParams p) {
                     umma::tc_fence_after();
                     const uint32_t a0 = umma::smem_u32(smem + (size_t)s * Cfg::kStageBytes);
                     const uint64_t a_hi = umma::make_desc_sw128(a0), a_lo = umma::make_desc_sw128(a0 + kATileBytes);
-                    const uint64_t b_hi = umma::make_desc_sw128(a0 + 2 * kATileBytes);
-                    const uint64_t b_lo = umma::make_desc_sw128(a0 + 2 * kATileBytes + Cfg::kBTileBytes);
+                    const uint64_t b_hi = umma::make_desc_sw128(a0 + 2 * kATileBytes);   // B_lo follows it in smem
 #pragma unroll
                     for (int k = 0; k < kUK / 8; ++k) {
                         const uint32_t adv = k * 32;     // 8 tf32 = 32 bytes along K inside the swizzle row
-                        umma::mma_tf32(d_tmem, umma::desc_advance(a_lo, adv), umma::desc_advance(b_hi, adv), idesc,
+                        umma::mma_tf32(d_tmem, umma::desc_advance(a_hi, adv), umma::desc_advance(b_hi, adv), idesc2,
                                        (kb | k) != 0);
-                        umma::mma_tf32(d_tmem, umma::desc_advance(a_hi, adv), umma::desc_advance(b_lo, adv), idesc, 1);
-                        umma::mma_tf32(d_tmem, umma::desc_advance(a_hi, adv), umma::desc_advance(b_hi, adv), idesc, 1);
+                        umma::mma_tf32(d_tmem, umma::desc_advance(a_lo, adv), umma::desc_advance(b_hi, adv), idesc, 1);
                     }
                     umma::tc_commit(&bar_empty[s]);      // frees this stage when the MMAs above retire
                     PROF_ADD(10);                          // slot 10: issuing MMAs
@@ -548,14 +599,11 @@ conv_umma_kernel(const ConvParams p) {
 }
 
 // ------------------------------------------------------------------------------------------ host side
+// N tile: a multiple of 16, at most 64; wider outputs are split evenly (96 -> 2 x 48, 128 -> 2 x 64).
 int conv_umma_pick_bn(int Og) {
-    const int r = (Og + 15) / 16 * 16;
-    if (r <= 16) return 16;
-    if (r <= 32) return 32;
-    if (r <= 48) return 48;
-    if (r <= 64) return 64;
-    if (r <= 96) return 96;
-    return 128;
+    const int n_tiles = (Og + 63) / 64;
+    const int per = (Og + n_tiles - 1) / n_tiles;
+    return (per + 15) / 16 * 16;
 }
 
 bool conv_umma_supported(const MdcnDims &d, bool deform) {
@@ -564,6 +612,7 @@ bool conv_umma_supported(const MdcnDims &d, bool deform) {
     if (d.P > 0x3fffffffLL || d.HW > 0x3fffffffLL) return false;
     if ((long)d.B * ceil_div_ll(d.P, kUM) > 0x3fffffffLL) return false;
     if (ceil_div(d.K * d.Cg, kUK) > kMaxKB || d.Cg > 0xffff || d.kh > 15 || d.kw > 15) return false;
+    if (d.Ho > 0x7fff || d.Wo > 0xffff) return false;      // producers pack (oh, ow) into one register
     return true;
 }
 
@@ -626,8 +675,6 @@ int conv_umma_launch(ConvParams p, bool deform, cudaStream_t stream) {
         AANET_CONV_CASE(32)
         AANET_CONV_CASE(48)
         AANET_CONV_CASE(64)
-        AANET_CONV_CASE(96)
-        AANET_CONV_CASE(128)
     }
 #undef AANET_CONV_CASE
     return AANET_ERR_UNSUPPORTED;

@@ -33,6 +33,9 @@ H_IMG, W_IMG, MAX_DISP, FEAT_C = 384, 1248, 192, 128
 METRIC = "384x1248 stereo pairs/s (cost+ISA/CSA+soft-argmin)"
 UNIT = "pairs/s"
 N_SETS = 4      # rotating input sets: 4 x 71.6 MB > 126 MB L2
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+# (profiles/), MB; None until a capture of the current kernel exists.
+NCU_TRAFFIC_MB = {"mdconv": None}
 
 
 def pyramid_shapes(batch):
@@ -132,31 +135,50 @@ def run_cpu_baseline(steps, warmup, batch=1):
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
-def time_mdconv_kernel(device, iters=20):
-    """Dominant kernel: ISA mdconv forward at the 1/3 scale ([1,64,128,416], dg=2, dil=2).  CUDA events on
-    the launching stream, inputs rotated over sets larger than L2."""
-    from aanet_b200 import ops
-    torch.manual_seed(326)
-    C, H, W = MAX_DISP // 3, H_IMG // 3, W_IMG // 3
-    n_sets = 6      # (13.6 + 11.5 + 13.6) MB per set -> 232 MB > L2
-    xs = [torch.randn(1, C, H, W, device=device) for _ in range(n_sets)]
-    offs = [2 * torch.randn(1, 36, H, W, device=device) for _ in range(n_sets)]
-    masks = [2 * torch.sigmoid(torch.randn(1, 18, H, W, device=device)) for _ in range(n_sets)]
-    w = torch.randn(C, C, 3, 3, device=device) / 24
+def _timed(fn, n_sets, iters, device):
     stream = torch.cuda.current_stream(device)
     for i in range(3):
-        ops.modulated_deform_conv(xs[i], offs[i], masks[i], w, None, 1, 2, 2, 1, 2)
+        fn(i % n_sets)
     torch.cuda.synchronize(device)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(iters):
-        ops.modulated_deform_conv(xs[i % n_sets], offs[i % n_sets], masks[i % n_sets], w, None, 1, 2, 2, 1, 2)
+        fn(i % n_sets)
     e1.record(stream)
     torch.cuda.synchronize(device)
-    ms = e0.elapsed_time(e1) / iters
+    return e0.elapsed_time(e1) / iters
+
+
+def time_kernels(device, iters=20):
+    """Live CUDA-event timing (launching stream, inputs rotated over sets larger than L2) of the dominant
+    kernel -- the ISA modulated deformable conv at the 1/3 scale as the fused path runs it (tcgen05 engine,
+    channels-last, packed weights) -- and of the other engine / memory-bound kernels for context."""
+    from aanet_b200 import ops
+    torch.manual_seed(326)
+    C, H, W = MAX_DISP // 3, H_IMG // 3, W_IMG // 3
+    n = 6      # (13.6 + 11.5 + 13.6) MB per set -> 232 MB > L2
+    xs = [torch.randn(1, H, W, C, device=device) for _ in range(n)]
+    oms = [torch.cat([2 * torch.randn(1, H, W, 36, device=device),
+                      2 * torch.sigmoid(torch.randn(1, H, W, 18, device=device))], -1).contiguous() for _ in range(n)]
+    wp3 = ops.pack_conv_weight(torch.randn(C, C, 3, 3, device=device) / 24)
+    wp1 = ops.pack_conv_weight(torch.randn(C, C, 1, 1, device=device) / 8)
+    sc, sh = torch.rand(C, device=device) + 0.5, torch.randn(C, device=device)
+    out = {}
+    ms = _timed(lambda i: ops.mdcn_nhwc(xs[i], oms[i], wp3, C, 3, 3, None, sc, sh, True, 1, 2, 2, 1, 2), n, iters, device)
     flops = 2.0 * C * C * 9 * H * W
     bytes_alg = 4.0 * (C * H * W + 27 * 2 * H * W + C * H * W) + 36.0 * C * C
-    return ms, flops, bytes_alg
+    out["mdconv"] = (ms, flops, bytes_alg)
+    ms = _timed(lambda i: ops.conv2d_nhwc(xs[i], wp3, C, 3, 3, None, sc, sh, None, ops.ACT_RELU, 0.0, 1, 1, 1, 1), n, iters, device)
+    out["conv3x3"] = (ms, flops, 4.0 * 2 * C * H * W)
+    ms = _timed(lambda i: ops.conv2d_nhwc(xs[i], wp1, C, 1, 1, None, sc, sh, None, ops.ACT_RELU, 0.0, 1, 0, 1, 1), n, iters, device)
+    out["conv1x1"] = (ms, flops / 9, 4.0 * 2 * C * H * W)
+    cs = [torch.randn(1, C, H, W, device=device) for _ in range(n)]
+    ms = _timed(lambda i: ops.soft_argmin(cs[i], True), n, iters, device)
+    out["softargmin"] = (ms, 0.0, 4.0 * H * W * (C + 1))
+    Ls = [torch.relu(torch.randn(1, FEAT_C, H, W, device=device)) for _ in range(4)]
+    ms = _timed(lambda i: ops.correlation(Ls[i], Ls[(i + 1) % 4], C), 4, iters, device)
+    out["correlation_s0"] = (ms, 2.0 * FEAT_C * H * (W * C - C * (C - 1) / 2), 4.0 * H * W * (2 * FEAT_C + C))
+    return out
 
 
 def load_peaks():
@@ -237,14 +259,21 @@ def run_gpu(args):
     out = None
     if rank == 0:
         hbm, bf16, peak_src = load_peaks()
-        k_ms, k_flops, k_bytes = time_mdconv_kernel(device)
+        kt = time_kernels(device)
+        k_ms, k_flops, k_bytes = kt["mdconv"]
         tf32_peak = bf16 / 2.0
         achieved = k_flops / (k_ms * 1e-3) / 1e12
-        roofline = {"kernel": "mdcn_fwd (ISA, 1/3 scale, C=64, dg=2)", "bound": "tensor",
-                    "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
-                    "traffic": None, "us_per_launch": k_ms * 1e3, "algorithmic_mb": k_bytes / 1e6,
+        roofline = {"kernel": "conv_umma_kernel<64,DEFORM> = ISA modulated deformable conv, 1/3 scale "
+                              "[1,64,128,416], dg=2, dil=2, 3xTF32 tcgen05",
+                    "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                    "frac": achieved / tf32_peak, "traffic": NCU_TRAFFIC_MB.get("mdconv"),
+                    "us_per_launch": k_ms * 1e3, "algorithmic_mb": k_bytes / 1e6,
                     "hbm_frac_if_memory_bound": k_bytes / (k_ms * 1e-3) / 1e9 / hbm,
-                    "peak_source": peak_src + "; TF32 dense taken as bf16_tflops/2, logical FLOPs counted once"}
+                    "peak_source": peak_src + "; TF32 dense taken as bf16_tflops/2 (burst, kernel timed alone); "
+                                   "logical FLOPs counted once although 3 MMAs are issued per product",
+                    "other_kernels": {k: {"us": v[0] * 1e3, "tflops": v[1] / (v[0] * 1e-3) / 1e12,
+                                          "gbs": v[2] / (v[0] * 1e-3) / 1e9, "hbm_frac": v[2] / (v[0] * 1e-3) / 1e9 / hbm}
+                                      for k, v in kt.items() if k != "mdconv"}}
         cpu = None if args.no_cpu_baseline else run_cpu_baseline(3, 1)
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
