@@ -35,7 +35,7 @@ UNIT = "pairs/s"
 N_SETS = 4      # rotating input sets: 4 x 71.6 MB > 126 MB L2
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
 # (profiles/), MB; None until a capture of the current kernel exists.
-NCU_TRAFFIC_MB = {"mdconv": None}
+NCU_TRAFFIC_MB = {"mdconv": 25.5}   # profiles/r01_launches_and_engine.md: 25.48 MB read + 0.003 MB written
 
 
 def pyramid_shapes(batch):
@@ -136,14 +136,26 @@ def run_cpu_baseline(steps, warmup, batch=1):
 
 # ------------------------------------------------------------------------------------------- GPU arm
 def _timed(fn, n_sets, iters, device):
-    stream = torch.cuda.current_stream(device)
-    for i in range(3):
-        fn(i % n_sets)
+    """ms per call, device time: `iters` calls cycling through n_sets input sets are captured into one CUDA
+    graph (no host launch gaps between the kernels) and the replay is bracketed by CUDA events on the
+    launching stream."""
+    side = torch.cuda.Stream(device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    with torch.cuda.stream(side), torch.no_grad():
+        for i in range(max(3, n_sets)):
+            fn(i % n_sets)
+    torch.cuda.current_stream(device).wait_stream(side)
     torch.cuda.synchronize(device)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g), torch.no_grad():
+        for i in range(iters):
+            fn(i % n_sets)
+    g.replay()
+    torch.cuda.synchronize(device)
+    stream = torch.cuda.current_stream(device)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for i in range(iters):
-        fn(i % n_sets)
+    g.replay()
     e1.record(stream)
     torch.cuda.synchronize(device)
     return e0.elapsed_time(e1) / iters
