@@ -309,7 +309,7 @@ conv_umma_kernel(const ConvParams p) {
                     if (ok) q[u] = __ldg(reinterpret_cast<const float4 *>(x_b + ((long)hi_ * d.W + wi_) * d.Cin));
                 }
                 PROF_ADD(1);
-                umma::mbar_wait(&bar_empty[s], ph ^ 1);
+                umma::mbar_wait_sleep(&bar_empty[s], ph ^ 1);
                 PROF_ADD(2);
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
@@ -383,7 +383,7 @@ conv_umma_kernel(const ConvParams p) {
                         float v[4];
                         combine(rw[cur], q[cur], v);
                         if (!k_ok) { v[0] = 0.f; v[1] = 0.f; v[2] = 0.f; v[3] = 0.f; }     // K padding
-                        if (!waited) { PROF_ADD(1); umma::mbar_wait(&bar_empty[s], ph ^ 1); PROF_ADD(2); waited = true; }
+                        if (!waited) { PROF_ADD(1); umma::mbar_wait_sleep(&bar_empty[s], ph ^ 1); PROF_ADD(2); waited = true; }
                         store_row(u, v);
                     }
                 } else {
@@ -397,7 +397,7 @@ conv_umma_kernel(const ConvParams p) {
                         gather(ri[0], q[0]);
                         float v[4];
                         combine(rw[0], q[0], v);
-                        if (!waited) { PROF_ADD(1); umma::mbar_wait(&bar_empty[s], ph ^ 1); PROF_ADD(2); waited = true; }
+                        if (!waited) { PROF_ADD(1); umma::mbar_wait_sleep(&bar_empty[s], ph ^ 1); PROF_ADD(2); waited = true; }
                         store_row(u, v);
                     }
                 }
