@@ -27,16 +27,26 @@ SIGNATURES = {
     "aanet_mdcn_bwd": (_i, [_vp] * 10 + [_i] * 12 + [_vp, _sz, _vp]),
     "aanet_conv2d_workspace_bytes": (_sz, [_i] * 11),
     "aanet_conv2d_fwd": (_i, [_vp] * 6 + [_i, _f, _vp] + [_i] * 11 + [_vp, _sz, _vp]),
-    "aanet_conv_wpack_bytes": (_sz, [_i] * 5),
-    "aanet_conv_pack_weights": (_i, [_vp, _vp] + [_i] * 5 + [_vp]),
+    "aanet_conv_wpack_bytes": (_sz, [_i] * 6),
+    "aanet_conv_pack_weights": (_i, [_vp, _vp] + [_i] * 6 + [_vp]),
     "aanet_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "aanet_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _vp]),
-    "aanet_conv2d_nhwc": (_i, [_vp] * 6 + [_i, _f, _i, _f, _vp, _i] + [_i] * 11 + [_vp]),
-    "aanet_mdcn_nhwc": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _i] + [_i] * 12 + [_vp]),
+    "aanet_conv_batch_nhwc": (_i, [_vp, _i, _i, _i, _vp]),
     "aanet_csa_fuse_nhwc": (_i, [_vp, _vp, _vp, _i, _vp] + [_i] * 4 + [_f, _vp]),
     "aanet_csa_fuse_fwd": (_i, [_vp, _vp, _vp, _i, _vp] + [_i] * 4 + [_f, _vp]),
     "aanet_csa_fuse_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i] + [_i] * 4 + [_f, _vp]),
 }
+
+
+
+class ConvDesc(ctypes.Structure):
+    """Mirror of `aanet_conv_desc` (include/aanet_b200.h)."""
+    _fields_ = [("x", _vp), ("wpack", _vp), ("bias", _vp), ("scale", _vp), ("shift", _vp), ("residual", _vp),
+                ("out", _vp), ("offmask", _vp), ("om_channels", _i),
+                ("B", _i), ("Cin", _i), ("H", _i), ("W", _i), ("Cout", _i), ("kh", _i), ("kw", _i),
+                ("stride", _i), ("pad", _i), ("dil", _i), ("groups", _i), ("dg", _i),
+                ("act", _i), ("slope", _f), ("n_offset_ch", _i), ("mask_scale", _f), ("out_nchw", _i)]
+
 
 _lib = None
 

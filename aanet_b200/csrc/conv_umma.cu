@@ -54,6 +54,10 @@ constexpr int kMaxKB = 256;               // K <= 8192
 
 enum ConvAct { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_OFFSET_MASK = 3 };
 
+constexpr int kMaxProblems = 3;
+
+// One convolution problem.  A launch (ConvBatch) walks the tiles of up to kMaxProblems problems of the same
+// kind (all DENSE or all DEFORM, same N-tile width): the three pyramid scales of one aggregation stage.
 struct ConvParams {
     const float *x;                     // channels-last input [B][H*W][Cin]
     const float *offset, *mask;         // DEFORM only; mask may be NULL (DCNv1)
@@ -71,6 +75,14 @@ struct ConvParams {
     int tiles_per_img;                  // ceil(P / 128)
     int n_ptiles;                       // B * tiles_per_img
     int total_tiles;                    // groups * n_tiles_n * n_ptiles
+    int tile_start;                     // first tile index of this problem in the batch's tile list
+    int tbl_off;                        // first K-block row of this problem in the chunk tables
+};
+
+struct ConvBatch {
+    ConvParams pr[kMaxProblems];
+    int n;
+    int total_tiles;
 };
 
 #ifdef AANET_PROFILE
@@ -159,20 +171,34 @@ transpose_kernel(const float *__restrict__ src, float *__restrict__ dst, int R, 
     }
 }
 
-struct TileCoord { int grp, nt, b; int p0; };
+struct TileCoord { int pi, grp, nt, b, p0; };
 
-__device__ __forceinline__ TileCoord tile_coord(const ConvParams &p, int t) {
+// Problem descriptors are staged in shared memory (dynamic indexing of kernel parameters would force a
+// local-memory copy; three-way code specialisation blew the register budget).
+__device__ __forceinline__ int tile_problem(const ConvParams *pr, int n, int t) {
+    int pi = 0;
+    if (n > 1 && t >= pr[1].tile_start) pi = 1;
+    if (n > 2 && t >= pr[2].tile_start) pi = 2;
+    return pi;
+}
+
+__device__ __forceinline__ TileCoord tile_coord(const ConvParams *pr, int n, int t) {
     TileCoord c;
-    const int pt = t % p.n_ptiles, gn = t / p.n_ptiles;
+    c.pi = tile_problem(pr, n, t);
+    const ConvParams &p = pr[c.pi];
+    const int lt = t - p.tile_start;
+    const int pt = lt % p.n_ptiles, gn = lt / p.n_ptiles;
     c.grp = gn / p.n_tiles_n; c.nt = gn % p.n_tiles_n;
     c.b = pt / p.tiles_per_img;
     c.p0 = (pt % p.tiles_per_img) * kUM;
     return c;
 }
 
-template <int BN, bool DEFORM>
+// MULTI = false: one problem, its descriptor stays in the constant bank (operands come straight from c[][]);
+// MULTI = true: up to kMaxProblems descriptors staged in shared memory and selected per tile.
+template <int BN, bool DEFORM, bool MULTI>
 __global__ void __launch_bounds__(kUThreads, 1)
-conv_umma_kernel(const ConvParams p) {
+conv_umma_kernel(const __grid_constant__ ConvBatch B) {
     using Cfg = EngineCfg<BN>;
     constexpr int S = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -186,8 +212,8 @@ conv_umma_kernel(const ConvParams p) {
     __shared__ uint8_t s_kbinfo[kMaxKB];
     // epilogue affine of the current (group, n-tile): out = acc * s_aff[0][n] + s_aff[1][n]
     __shared__ __align__(16) float s_aff[2][BN];
+    __shared__ __align__(16) ConvParams s_pr[kMaxProblems];
 
-    const MdcnDims &d = p.d;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t *smem = smem_raw + ((1024 - (umma::smem_u32(smem_raw) & 1023)) & 1023);   // 1024-byte aligned
 
@@ -204,39 +230,54 @@ conv_umma_kernel(const ConvParams p) {
         umma::fence_mbar_init();
     }
     if (warp == kMmaWarp) umma::tmem_alloc<Cfg::kTmemCols>(&s_tmem);
-    for (int i = tid; i < p.KB * 8; i += kUThreads) {
-        const int kk = (i >> 3) * kUK + (i & 7) * 4;
-        uint32_t e = 0;
-        if (kk < p.K) {
-            const int tap = kk / d.Cg, c = kk - tap * d.Cg;
-            const int ki = tap / d.kw, kj = tap - ki * d.kw;
-            e = (uint32_t)c | ((uint32_t)ki << 16) | ((uint32_t)kj << 20) | ((uint32_t)tap << 24) | 0x80000000u;
-        }
-        s_chunk[i] = e;
+    if (MULTI) {
+        static_assert(sizeof(ConvParams) % 4 == 0, "descriptor is copied word-wise");
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(&B.pr[0]);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&s_pr[0]);
+        for (int i = tid; i < (int)(sizeof(ConvParams) / 4) * B.n; i += kUThreads) dst[i] = src[i];
     }
-    if (DEFORM) {
-        for (int kb = tid; kb < p.KB; kb += kUThreads) {
-            int key[8];
-            for (int c8 = 0; c8 < 8; ++c8) {
-                const int kk = kb * kUK + c8 * 4;
-                if (kk < p.K) {
-                    const int tap = kk / d.Cg, c = kk - tap * d.Cg;
-                    key[c8] = tap * 4096 + c / d.Cd;          // (tap, deformable group within the conv group)
-                } else {
-                    key[c8] = -1 - c8;                        // padding chunks: weight 0, geometry irrelevant
-                }
+    const int n_prob = MULTI ? B.n : 1, total_tiles = B.total_tiles;
+    // descriptor table the roles index: shared copy (MULTI) or the kernel parameter itself
+    const ConvParams *const prob = MULTI ? s_pr : B.pr;
+    auto build_tables = [&](const ConvParams &p) {
+        const MdcnDims &d = p.d;
+        for (int i = tid; i < p.KB * 8; i += kUThreads) {
+            const int kk = (i >> 3) * kUK + (i & 7) * 4;
+            uint32_t e = 0;
+            if (kk < p.K) {
+                const int tap = kk / d.Cg, c = kk - tap * d.Cg;
+                const int ki = tap / d.kw, kj = tap - ki * d.kw;
+                e = (uint32_t)c | ((uint32_t)ki << 16) | ((uint32_t)kj << 20) | ((uint32_t)tap << 24) | 0x80000000u;
             }
-            int split = 8;
-            for (int c8 = 1; c8 < 8; ++c8)
-                if (key[c8] >= 0 && key[c8] != key[0]) { split = c8; break; }
-            bool two = true;
-            for (int c8 = split; c8 < 8; ++c8)
-                if (key[c8] >= 0 && key[c8] != key[split]) two = false;
-            for (int c8 = 1; c8 < split && c8 < 8; ++c8)
-                if (key[c8] >= 0 && key[c8] != key[0]) two = false;
-            s_kbinfo[kb] = (uint8_t)(split | (two ? 16 : 0));
+            s_chunk[p.tbl_off * 8 + i] = e;
         }
-    }
+        if (DEFORM) {
+            for (int kb = tid; kb < p.KB; kb += kUThreads) {
+                int key[8];
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    const int kk = kb * kUK + c8 * 4;
+                    if (kk < p.K) {
+                        const int tap = kk / d.Cg, c = kk - tap * d.Cg;
+                        key[c8] = tap * 4096 + c / d.Cd;          // (tap, deformable group within the conv group)
+                    } else {
+                        key[c8] = -1 - c8;                        // padding chunks: weight 0, geometry irrelevant
+                    }
+                }
+                int split = 8;
+                for (int c8 = 1; c8 < 8; ++c8)
+                    if (key[c8] >= 0 && key[c8] != key[0]) { split = c8; break; }
+                bool two = true;
+                for (int c8 = split; c8 < 8; ++c8)
+                    if (key[c8] >= 0 && key[c8] != key[split]) two = false;
+                for (int c8 = 1; c8 < split && c8 < 8; ++c8)
+                    if (key[c8] >= 0 && key[c8] != key[0]) two = false;
+                s_kbinfo[p.tbl_off + kb] = (uint8_t)(split | (two ? 16 : 0));
+            }
+        }
+    };
+    build_tables(B.pr[0]);
+    if (B.n > 1) build_tables(B.pr[1]);
+    if (B.n > 2) build_tables(B.pr[2]);
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
@@ -253,33 +294,40 @@ conv_umma_kernel(const ConvParams p) {
         const int tg = tid & 127, j = tg & 7;
         const int row0 = (tg >> 3) * 8;
         const int lane_base = lane & ~7;
-        const int P32 = (int)d.P;
         PROF_DECL();
         PROF_T0();
 
         int t = blockIdx.x, kb = grpi;
         uint32_t it = grpi;
-        while (kb >= p.KB && t < p.total_tiles) { kb -= p.KB; t += gridDim.x; }
+        // (tile, K block) cursor: skip whole tiles while kb runs past the K blocks of the tile's problem
+        auto normalize = [&]() {
+            while (t < total_tiles) {
+                const int nkb = (MULTI ? prob[tile_problem(prob, n_prob, t)].KB : B.pr[0].KB);
+                if (kb < nkb) break;
+                kb -= nkb; t += gridDim.x;
+            }
+        };
+        normalize();
         int cur_t = -1;
-        TileCoord tc = {0, 0, 0, 0};
+        TileCoord tc = {0, 0, 0, 0, 0};
         int my_oh = 0, my_ow = 0;
         bool my_ok = false;
 
-        while (t < p.total_tiles) {
-            if (t != cur_t) {                       // entered a new tile: coordinates of the row this lane owns
-                cur_t = t;
-                tc = tile_coord(p, t);
-                const int px = tc.p0 + row0 + j;
-                my_ok = px < P32;
-                const int pc = my_ok ? px : P32 - 1;
-                my_oh = pc / d.Wo;
-                my_ow = pc - my_oh * d.Wo;
-            }
+        auto enter_tile = [&](const ConvParams &p) {   // coordinates of the row this lane owns
+            const int P32 = (int)p.d.P;
+            const int px = tc.p0 + row0 + j;
+            my_ok = px < P32;
+            const int pc = my_ok ? px : P32 - 1;
+            my_oh = pc / p.d.Wo;
+            my_ow = pc - my_oh * p.d.Wo;
+        };
+        auto produce = [&](const ConvParams &p) {
+            const MdcnDims &d = p.d;
             const int s = it % S;
             const uint32_t ph = (it / S) & 1;
             float *a_hi = reinterpret_cast<float *>(smem + (size_t)s * Cfg::kStageBytes);
             float *a_lo = a_hi + kATileBytes / 4;
-            const uint32_t e = s_chunk[kb * 8 + j];           // this lane's chunk of the K block
+            const uint32_t e = s_chunk[(p.tbl_off + kb) * 8 + j];   // this lane's chunk of the K block
             const bool k_ok = (e >> 31) != 0;
             const int c_abs = tc.grp * d.Cg + (int)(e & 0xffffu);
             const float *x_b = p.x + (long)tc.b * d.HW * d.Cin + c_abs;
@@ -317,7 +365,7 @@ conv_umma_kernel(const ConvParams p) {
                     store_row(u, v);
                 }
             } else {
-                const uint8_t info = s_kbinfo[kb];
+                const uint8_t info = s_kbinfo[p.tbl_off + kb];
                 const int split = info & 15;
                 const float *off_b = p.offset + (long)tc.b * p.off_bs;
                 const float *mask_b = p.mask ? p.mask + (long)tc.b * p.mask_bs : nullptr;
@@ -355,8 +403,8 @@ conv_umma_kernel(const ConvParams p) {
                     // shared path: this lane samples ITS row once per run (at most 2 runs per K block) ...
                     int ia[4], ib[4];
                     float wa[4], wb[4];
-                    geometry(my_oh, my_ow, my_ok, s_chunk[kb * 8], ia, wa);
-                    if (split < 8) geometry(my_oh, my_ow, my_ok, s_chunk[kb * 8 + split], ib, wb);
+                    geometry(my_oh, my_ow, my_ok, s_chunk[(p.tbl_off + kb) * 8], ia, wa);
+                    if (split < 8) geometry(my_oh, my_ow, my_ok, s_chunk[(p.tbl_off + kb) * 8 + split], ib, wb);
                     const bool second = j >= split;
                     // ... and every lane receives the sample of row u from its owner (lane_base + u)
                     auto fetch = [&](int u, int (&gi)[4], float (&gwt)[4]) {
@@ -405,9 +453,17 @@ conv_umma_kernel(const ConvParams p) {
             umma::fence_proxy_async();
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(&bar_full_a[s]);
+        };
 
+        while (t < total_tiles) {
+            if (t != cur_t) {
+                cur_t = t;
+                tc = tile_coord(prob, n_prob, t);
+                enter_tile(MULTI ? prob[tc.pi] : B.pr[0]);
+            }
+            produce(MULTI ? prob[tc.pi] : B.pr[0]);
             kb += kGroups; it += kGroups;
-            while (kb >= p.KB && t < p.total_tiles) { kb -= p.KB; t += gridDim.x; }
+            normalize();
         }
         PROF_ADD(1);
         if (tid == 0) { PROF_FLUSH(1); PROF_FLUSH(2); }
@@ -420,17 +476,18 @@ conv_umma_kernel(const ConvParams p) {
         int cur_gn = -1;
         PROF_DECL();
         PROF_T0();
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
-            const TileCoord tc = tile_coord(p, t);
+        TileCoord tc = {0, 0, 0, 0, 0};
+        auto epilogue = [&](const ConvParams &p) {
+            const MdcnDims &d = p.d;
             const int a = ti & 1;
             const int pix = tc.p0 + row;
             const bool p_ok = pix < (int)d.P;
             const int o_base = tc.grp * d.Og + tc.nt * BN;          // first global out channel of the tile
             const int n_valid = min(BN, d.Og - tc.nt * BN);
-            if (tc.grp * p.n_tiles_n + tc.nt != cur_gn) {
-                // (re)build the per-channel affine of this (group, n-tile):
+            if ((tc.pi << 20) + tc.grp * p.n_tiles_n + tc.nt != cur_gn) {
+                // (re)build the per-channel affine of this (problem, group, n-tile):
                 //   (acc + bias) * scale + shift  ==  acc * scale + (bias * scale + shift)
-                cur_gn = tc.grp * p.n_tiles_n + tc.nt;
+                cur_gn = (tc.pi << 20) + tc.grp * p.n_tiles_n + tc.nt;
                 asm volatile("bar.sync 1, 128;" ::: "memory");       // previous tile's readers are done
                 if (et < BN) {
                     float sc = 1.f, sh = 0.f;
@@ -523,6 +580,10 @@ conv_umma_kernel(const ConvParams p) {
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(&bar_acc_empty[a]);
             PROF_ADD(4);                                   // slot 4: epilogue work
+        };
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+            tc = tile_coord(prob, n_prob, t);
+            epilogue(MULTI ? prob[tc.pi] : B.pr[0]);
         }
         if (warp == kProdWarps && lane == 0) { PROF_FLUSH(3); PROF_FLUSH(4); }
     } else {
@@ -531,11 +592,17 @@ conv_umma_kernel(const ConvParams p) {
             uint32_t it = 0;
             PROF_DECL();
             PROF_T0();
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                const TileCoord tc = tile_coord(p, t);
-                const uint8_t *src = reinterpret_cast<const uint8_t *>(p.wpack) +
-                                     (size_t)(tc.grp * p.n_tiles_n + tc.nt) * p.KB * (2 * Cfg::kBTileBytes);
-                for (int kb = 0; kb < p.KB; ++kb, ++it) {
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const TileCoord tc = tile_coord(prob, n_prob, t);
+                const uint8_t *src = nullptr;
+                int nkb = 0;
+                auto weights_of = [&](const ConvParams &p) {
+                    nkb = p.KB;
+                    src = reinterpret_cast<const uint8_t *>(p.wpack) +
+                          (size_t)(tc.grp * p.n_tiles_n + tc.nt) * p.KB * (2 * Cfg::kBTileBytes);
+                };
+                weights_of(MULTI ? prob[tc.pi] : B.pr[0]);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % S;
                     const uint32_t ph = (it / S) & 1;
                     umma::mbar_wait_sleep(&bar_empty[s], ph ^ 1);
@@ -555,13 +622,14 @@ conv_umma_kernel(const ConvParams p) {
             PROF_DECL();
             PROF_T0();
             const long long prof_start = clock64();
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
                 const int a = ti & 1;
+                const int nkb = (MULTI ? prob[tile_problem(prob, n_prob, t)].KB : B.pr[0].KB);
                 umma::mbar_wait_sleep(&bar_acc_empty[a], ((ti >> 1) & 1) ^ 1);   // epilogue drained this accumulator
                 umma::tc_fence_after();
                 PROF_ADD(7);                               // slot 7: MMA waiting for a drained accumulator
                 const uint32_t d_tmem = tmem_base + a * Cfg::kAccStride;
-                for (int kb = 0; kb < p.KB; ++kb, ++it) {
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % S;
                     const uint32_t ph = (it / S) & 1;
                     umma::mbar_wait_sleep(&bar_full_a[s], ph);
@@ -606,6 +674,8 @@ int conv_umma_pick_bn(int Og) {
     return (per + 15) / 16 * 16;
 }
 
+static bool bn_valid(int bn) { return bn == 16 || bn == 32 || bn == 48 || bn == 64; }
+
 bool conv_umma_supported(const MdcnDims &d, bool deform) {
     if (d.Cg % 4 || d.Cin % 4) return false;
     if (deform && (d.Cd % 4)) return false;
@@ -616,15 +686,17 @@ bool conv_umma_supported(const MdcnDims &d, bool deform) {
     return true;
 }
 
-size_t conv_umma_wpack_bytes(const MdcnDims &d) {
-    const int BN = conv_umma_pick_bn(d.Og);
+// bn == 0: the natural N tile of this layer; otherwise the (wider) N tile of the batch it will run in.
+size_t conv_umma_wpack_bytes(const MdcnDims &d, int bn) {
+    const int BN = bn ? bn : conv_umma_pick_bn(d.Og);
     const int n_tiles_n = ceil_div(d.Og, BN);
     const int KB = ceil_div(d.K * d.Cg, kUK);
     return (size_t)d.groups * n_tiles_n * KB * 2 * BN * kUK * sizeof(float);
 }
 
-int conv_umma_pack(const float *weight, void *wpack, const MdcnDims &d, cudaStream_t stream) {
-    const int BN = conv_umma_pick_bn(d.Og);
+int conv_umma_pack(const float *weight, void *wpack, const MdcnDims &d, int bn, cudaStream_t stream) {
+    const int BN = bn ? bn : conv_umma_pick_bn(d.Og);
+    if (!bn_valid(BN)) return AANET_ERR_UNSUPPORTED;
     const int n_tiles_n = ceil_div(d.Og, BN);
     const int K = d.K * d.Cg, KB = ceil_div(K, kUK);
     const long total = (long)d.groups * n_tiles_n * KB * BN * kUK;
@@ -641,13 +713,18 @@ int conv_umma_transpose(const float *src, float *dst, int B, int R, long Cc, cud
     return check_launch();
 }
 
-template <int BN, bool DEFORM>
-static int launch_one(const ConvParams &p, cudaStream_t stream) {
+template <int BN, bool DEFORM, bool MULTI>
+static int launch_inst(const ConvBatch &batch, cudaStream_t stream) {
     constexpr size_t smem = EngineCfg<BN>::kSmemBytes;
-    cudaFuncSetAttribute(conv_umma_kernel<BN, DEFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-    conv_umma_kernel<BN, DEFORM><<<grid, kUThreads, smem, stream>>>(p);
+    cudaFuncSetAttribute(conv_umma_kernel<BN, DEFORM, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int grid = batch.total_tiles < kNumSMs ? batch.total_tiles : kNumSMs;
+    conv_umma_kernel<BN, DEFORM, MULTI><<<grid, kUThreads, smem, stream>>>(batch);
     return check_launch();
+}
+
+template <int BN, bool DEFORM>
+static int launch_one(const ConvBatch &batch, cudaStream_t stream) {
+    return batch.n > 1 ? launch_inst<BN, DEFORM, true>(batch, stream) : launch_inst<BN, DEFORM, false>(batch, stream);
 }
 
 #ifdef AANET_PROFILE
@@ -656,20 +733,40 @@ extern "C" __attribute__((visibility("default"))) int aanet_profile_read(long lo
 }
 #endif
 
-int conv_umma_launch(ConvParams p, bool deform, cudaStream_t stream) {
-    const MdcnDims &d = p.d;
-    const int BN = conv_umma_pick_bn(d.Og);
-    p.n_tiles_n = ceil_div(d.Og, BN);
-    p.K = d.K * d.Cg;
-    p.KB = ceil_div(p.K, kUK);
-    p.tiles_per_img = (int)ceil_div_ll(d.P, kUM);
-    p.n_ptiles = d.B * p.tiles_per_img;
-    const long total = (long)d.groups * p.n_tiles_n * p.n_ptiles;
-    if (total > 0x7fffffffLL) return AANET_ERR_UNSUPPORTED;
-    p.total_tiles = (int)total;
-#define AANET_CONV_CASE(bn)                                                              \
-    case bn:                                                                             \
-        return deform ? launch_one<bn, true>(p, stream) : launch_one<bn, false>(p, stream);
+// Launch up to kMaxProblems problems of the same kind as one persistent kernel.  bn == 0: widest natural N
+// tile among the problems (their weights must have been packed with that same width).
+int conv_umma_launch_batch(const ConvParams *probs, int n, bool deform, int bn, cudaStream_t stream) {
+    if (n < 1 || n > kMaxProblems) return AANET_ERR_SHAPE;
+    int BN = bn;
+    if (!BN)
+        for (int i = 0; i < n; ++i) BN = BN > conv_umma_pick_bn(probs[i].d.Og) ? BN : conv_umma_pick_bn(probs[i].d.Og);
+    if (!bn_valid(BN)) return AANET_ERR_UNSUPPORTED;
+    ConvBatch batch{};
+    batch.n = n;
+    long tiles = 0;
+    int tbl = 0;
+    for (int i = 0; i < n; ++i) {
+        ConvParams p = probs[i];
+        const MdcnDims &d = p.d;
+        p.n_tiles_n = ceil_div(d.Og, BN);
+        p.K = d.K * d.Cg;
+        p.KB = ceil_div(p.K, kUK);
+        p.tiles_per_img = (int)ceil_div_ll(d.P, kUM);
+        p.n_ptiles = d.B * p.tiles_per_img;
+        const long total = (long)d.groups * p.n_tiles_n * p.n_ptiles;
+        if (tiles + total > 0x3fffffffLL) return AANET_ERR_UNSUPPORTED;
+        p.total_tiles = (int)total;
+        p.tile_start = (int)tiles;
+        p.tbl_off = tbl;
+        tiles += total;
+        tbl += p.KB;
+        batch.pr[i] = p;
+    }
+    if (tbl > kMaxKB) return AANET_ERR_UNSUPPORTED;
+    batch.total_tiles = (int)tiles;
+#define AANET_CONV_CASE(b)                                                              \
+    case b:                                                                              \
+        return deform ? launch_one<b, true>(batch, stream) : launch_one<b, false>(batch, stream);
     switch (BN) {
         AANET_CONV_CASE(16)
         AANET_CONV_CASE(32)
@@ -678,6 +775,10 @@ int conv_umma_launch(ConvParams p, bool deform, cudaStream_t stream) {
     }
 #undef AANET_CONV_CASE
     return AANET_ERR_UNSUPPORTED;
+}
+
+int conv_umma_launch(ConvParams p, bool deform, cudaStream_t stream) {
+    return conv_umma_launch_batch(&p, 1, deform, 0, stream);
 }
 
 }  // namespace aanet

@@ -27,13 +27,14 @@ struct ConvParams {
     const float *residual;
     int act; float slope; int n_offset_ch; float mask_scale;
     MdcnDims d;
-    int K, KB, n_tiles_n, tiles_per_img, n_ptiles, total_tiles;
+    int K, KB, n_tiles_n, tiles_per_img, n_ptiles, total_tiles, tile_start, tbl_off;
 };
 bool conv_umma_supported(const MdcnDims &d, bool deform);
-size_t conv_umma_wpack_bytes(const MdcnDims &d);
-int conv_umma_pack(const float *weight, void *wpack, const MdcnDims &d, cudaStream_t stream);
+size_t conv_umma_wpack_bytes(const MdcnDims &d, int bn);
+int conv_umma_pack(const float *weight, void *wpack, const MdcnDims &d, int bn, cudaStream_t stream);
 int conv_umma_transpose(const float *src, float *dst, int B, int R, long Cc, cudaStream_t stream);
 int conv_umma_launch(ConvParams p, bool deform, cudaStream_t stream);
+int conv_umma_launch_batch(const ConvParams *probs, int n, bool deform, int bn, cudaStream_t stream);
 
 static inline size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 static inline size_t nhwc_bytes(const MdcnDims &d) { return (size_t)d.B * d.Cin * d.HW * sizeof(float); }
@@ -47,7 +48,7 @@ extern "C" size_t aanet_mdcn_workspace_bytes(int backward, int B, int Cin, int H
     MdcnDims d;
     if (mdcn_make_dims(d, B, Cin, H, W, Cout, kh, kw, stride, pad, dil, groups, dg) != AANET_OK) return 0;
     if (backward) return mdcn_bwd_workspace_bytes(d);
-    return conv_umma_supported(d, true) ? align256(conv_umma_wpack_bytes(d)) + nhwc_bytes(d) : 0;
+    return conv_umma_supported(d, true) ? align256(conv_umma_wpack_bytes(d, 0)) + nhwc_bytes(d) : 0;
 }
 
 extern "C" int aanet_mdcn_fwd(const float *x, const float *offset, const float *mask, const float *weight,
@@ -63,10 +64,10 @@ extern "C" int aanet_mdcn_fwd(const float *x, const float *offset, const float *
     // tcgen05 path: needs the workspace (packed weights + channels-last copy of x).  ws == NULL selects the
     // shape-generic FFMA kernel.
     if (ws && conv_umma_supported(d, true) && aligned16(ws)) {
-        const size_t wbytes = align256(conv_umma_wpack_bytes(d));
+        const size_t wbytes = align256(conv_umma_wpack_bytes(d, 0));
         if (ws_bytes < wbytes + nhwc_bytes(d)) return AANET_ERR_WORKSPACE;
         float *xt = reinterpret_cast<float *>(static_cast<char *>(ws) + wbytes);
-        int prc = conv_umma_pack(weight, ws, d, as_stream(stream));
+        int prc = conv_umma_pack(weight, ws, d, 0, as_stream(stream));
         if (prc) return prc;
         prc = conv_umma_transpose(x, xt, d.B, d.Cin, d.HW, as_stream(stream));      // NCHW -> NHWC
         if (prc) return prc;
@@ -102,7 +103,7 @@ extern "C" size_t aanet_conv2d_workspace_bytes(int B, int Cin, int H, int W, int
                                                int stride, int pad, int dil, int groups) {
     MdcnDims d;
     if (mdcn_make_dims(d, B, Cin, H, W, Cout, kh, kw, stride, pad, dil, groups, 1) != AANET_OK) return 0;
-    return conv_umma_supported(d, false) ? align256(conv_umma_wpack_bytes(d)) + nhwc_bytes(d) : 0;
+    return conv_umma_supported(d, false) ? align256(conv_umma_wpack_bytes(d, 0)) + nhwc_bytes(d) : 0;
 }
 
 extern "C" int aanet_conv2d_fwd(const float *x, const float *weight, const float *bias, const float *scale,
@@ -116,10 +117,10 @@ extern "C" int aanet_conv2d_fwd(const float *x, const float *weight, const float
     const int rc = mdcn_make_dims(d, B, Cin, H, W, Cout, kh, kw, stride, pad, dil, groups, 1);
     if (rc) return rc;
     if (!conv_umma_supported(d, false)) return AANET_ERR_UNSUPPORTED;
-    const size_t wbytes = align256(conv_umma_wpack_bytes(d));
+    const size_t wbytes = align256(conv_umma_wpack_bytes(d, 0));
     if (!ws || !aligned16(ws) || ws_bytes < wbytes + nhwc_bytes(d)) return AANET_ERR_WORKSPACE;
     float *xt = reinterpret_cast<float *>(static_cast<char *>(ws) + wbytes);
-    int prc = conv_umma_pack(weight, ws, d, as_stream(stream));
+    int prc = conv_umma_pack(weight, ws, d, 0, as_stream(stream));
     if (prc) return prc;
     prc = conv_umma_transpose(x, xt, d.B, d.Cin, d.HW, as_stream(stream));
     if (prc) return prc;
@@ -132,20 +133,20 @@ extern "C" int aanet_conv2d_fwd(const float *x, const float *weight, const float
 }
 
 // ------------------------------------------------------------------------------ channels-last engine calls
-extern "C" size_t aanet_conv_wpack_bytes(int Cout, int Cin, int kh, int kw, int groups) {
+extern "C" size_t aanet_conv_wpack_bytes(int Cout, int Cin, int kh, int kw, int groups, int bn) {
     MdcnDims d;
     if (mdcn_make_dims(d, 1, Cin, kh, kw, Cout, kh, kw, 1, 0, 1, groups, 1) != AANET_OK) return 0;
-    return conv_umma_supported(d, false) ? conv_umma_wpack_bytes(d) : 0;
+    return conv_umma_supported(d, false) ? conv_umma_wpack_bytes(d, bn) : 0;
 }
 
 extern "C" int aanet_conv_pack_weights(const float *weight, void *wpack, int Cout, int Cin, int kh, int kw,
-                                       int groups, void *stream) {
+                                       int groups, int bn, void *stream) {
     if (!weight || !wpack) return AANET_ERR_NULL;
     MdcnDims d;
     const int rc = mdcn_make_dims(d, 1, Cin, kh, kw, Cout, kh, kw, 1, 0, 1, groups, 1);
     if (rc) return rc;
     if (!conv_umma_supported(d, false)) return AANET_ERR_UNSUPPORTED;
-    return conv_umma_pack(weight, wpack, d, as_stream(stream));
+    return conv_umma_pack(weight, wpack, d, bn, as_stream(stream));
 }
 
 extern "C" int aanet_nchw_to_nhwc(const float *src, float *dst, int B, int C, int HW, void *stream) {
@@ -160,46 +161,40 @@ extern "C" int aanet_nhwc_to_nchw(const float *src, float *dst, int B, int C, in
     return conv_umma_transpose(src, dst, B, HW, C, as_stream(stream));
 }
 
-extern "C" int aanet_conv2d_nhwc(const float *x, const void *wpack, const float *bias, const float *scale,
-                                 const float *shift, const float *residual, int act, float slope,
-                                 int n_offset_ch, float mask_scale, float *out, int out_nchw, int B, int Cin,
-                                 int H, int W, int Cout, int kh, int kw, int stride, int pad, int dil,
-                                 int groups, void *stream) {
-    if (!x || !wpack || !out) return AANET_ERR_NULL;
-    if ((scale == nullptr) != (shift == nullptr)) return AANET_ERR_NULL;
-    if (act < ACT_NONE || act > ACT_OFFSET_MASK) return AANET_ERR_UNSUPPORTED;
+// Fill a ConvParams from a descriptor; returns an aanet_status.
+static int problem_from_desc(const aanet_conv_desc &c, bool deform, ConvParams &p) {
+    if (!c.x || !c.wpack || !c.out) return AANET_ERR_NULL;
+    if ((c.scale == nullptr) != (c.shift == nullptr)) return AANET_ERR_NULL;
+    if (c.act < ACT_NONE || c.act > ACT_OFFSET_MASK) return AANET_ERR_UNSUPPORTED;
     MdcnDims d;
-    const int rc = mdcn_make_dims(d, B, Cin, H, W, Cout, kh, kw, stride, pad, dil, groups, 1);
+    const int rc = mdcn_make_dims(d, c.B, c.Cin, c.H, c.W, c.Cout, c.kh, c.kw, c.stride, c.pad, c.dil, c.groups,
+                                  deform ? c.dg : 1);
     if (rc) return rc;
-    if (!conv_umma_supported(d, false) || !aligned16(x) || !aligned16(wpack)) return AANET_ERR_UNSUPPORTED;
-    ConvParams p{};
-    p.x = x; p.wpack = static_cast<const float *>(wpack); p.out = out; p.out_nchw = out_nchw ? 1 : 0;
-    p.bias = bias; p.scale = scale; p.shift = shift; p.residual = residual;
-    p.act = act; p.slope = slope; p.n_offset_ch = n_offset_ch; p.mask_scale = mask_scale;
+    if (!conv_umma_supported(d, deform) || !aligned16(c.x) || !aligned16(c.wpack) || !aligned16(c.out))
+        return AANET_ERR_UNSUPPORTED;
+    p = ConvParams{};
+    p.x = c.x; p.wpack = static_cast<const float *>(c.wpack); p.out = c.out; p.out_nchw = c.out_nchw ? 1 : 0;
+    p.bias = c.bias; p.scale = c.scale; p.shift = c.shift; p.residual = c.residual;
+    p.act = c.act; p.slope = c.slope; p.n_offset_ch = c.n_offset_ch; p.mask_scale = c.mask_scale;
     p.d = d;
-    return conv_umma_launch(p, false, as_stream(stream));
+    if (deform) {
+        if (!c.offmask) return AANET_ERR_NULL;
+        const int n_off = c.dg * 2 * d.K, n_mask = c.dg * d.K;
+        if (c.om_channels != n_off && c.om_channels != n_off + n_mask) return AANET_ERR_SHAPE;
+        p.offset = c.offmask; p.off_bs = (long)d.P * c.om_channels; p.off_ps = c.om_channels; p.off_cs = 1;
+        p.mask = (c.om_channels == n_off) ? nullptr : c.offmask + n_off;
+        p.mask_bs = p.off_bs; p.mask_ps = c.om_channels; p.mask_cs = 1;
+    }
+    return AANET_OK;
 }
 
-extern "C" int aanet_mdcn_nhwc(const float *x, const float *offmask, int om_channels, const void *wpack,
-                               const float *bias, const float *post_scale, const float *post_shift, int relu,
-                               float *out, int out_nchw, int B, int Cin, int H, int W, int Cout, int kh, int kw,
-                               int stride, int pad, int dil, int groups, int dg, void *stream) {
-    if (!x || !offmask || !wpack || !out) return AANET_ERR_NULL;
-    if ((post_scale == nullptr) != (post_shift == nullptr)) return AANET_ERR_NULL;
-    MdcnDims d;
-    const int rc = mdcn_make_dims(d, B, Cin, H, W, Cout, kh, kw, stride, pad, dil, groups, dg);
-    if (rc) return rc;
-    const int n_off = dg * 2 * d.K, n_mask = dg * d.K;
-    if (om_channels != n_off && om_channels != n_off + n_mask) return AANET_ERR_SHAPE;
-    if (!conv_umma_supported(d, true) || !aligned16(x) || !aligned16(wpack)) return AANET_ERR_UNSUPPORTED;
-    ConvParams p{};
-    p.x = x;
-    p.offset = offmask; p.off_bs = (long)d.P * om_channels; p.off_ps = om_channels; p.off_cs = 1;
-    p.mask = (om_channels == n_off) ? nullptr : offmask + n_off;
-    p.mask_bs = p.off_bs; p.mask_ps = om_channels; p.mask_cs = 1;
-    p.wpack = static_cast<const float *>(wpack); p.out = out; p.out_nchw = out_nchw ? 1 : 0;
-    p.bias = bias; p.scale = post_scale; p.shift = post_shift;
-    p.act = relu ? ACT_RELU : ACT_NONE; p.mask_scale = 1.f;
-    p.d = d;
-    return conv_umma_launch(p, true, as_stream(stream));
+extern "C" int aanet_conv_batch_nhwc(const aanet_conv_desc *descs, int n, int deform, int bn, void *stream) {
+    if (!descs) return AANET_ERR_NULL;
+    if (n < 1 || n > AANET_CONV_MAX_BATCH) return AANET_ERR_SHAPE;
+    ConvParams probs[AANET_CONV_MAX_BATCH];
+    for (int i = 0; i < n; ++i) {
+        const int rc = problem_from_desc(descs[i], deform != 0, probs[i]);
+        if (rc) return rc;
+    }
+    return conv_umma_launch_batch(probs, n, deform != 0, bn, as_stream(stream));
 }

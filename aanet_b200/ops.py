@@ -293,51 +293,78 @@ def nhwc_to_nchw(x):
     return out
 
 
-def pack_conv_weight(weight, groups=1):
-    """tf32 hi/lo split + 128-byte swizzle of a [Cout, Cin/groups, kh, kw] weight for the tcgen05 engine."""
+def natural_bn(out_per_group):
+    """N-tile width the engine picks for a layer on its own: multiple of 16, <= 64, wider layers split evenly."""
+    n_tiles = (out_per_group + 63) // 64
+    per = (out_per_group + n_tiles - 1) // n_tiles
+    return (per + 15) // 16 * 16
+
+
+def pack_conv_weight(weight, groups=1, bn=0):
+    """tf32 hi/lo split + 128-byte swizzle of a [Cout, Cin/groups, kh, kw] weight for the tcgen05 engine.
+    bn = N-tile width of the launch the layer will run in (0: the layer's own natural width)."""
     weight = _prep(weight.detach(), "pack_conv_weight")
     Cout, cg, kh, kw = weight.shape
     lib = _lib.load()
-    n = lib.aanet_conv_wpack_bytes(Cout, cg * groups, kh, kw, groups)
+    n = lib.aanet_conv_wpack_bytes(Cout, cg * groups, kh, kw, groups, bn)
     if n == 0:
         raise _lib.AanetError("conv engine needs Cin/groups %% 4 == 0 (got Cin=%d, groups=%d)" % (cg * groups, groups))
     wpack = torch.empty(n, dtype=torch.uint8, device=weight.device)
     with torch.cuda.device(weight.device):
-        _lib.check(lib.aanet_conv_pack_weights(_ptr(weight), _ptr(wpack), Cout, cg * groups, kh, kw, groups,
+        _lib.check(lib.aanet_conv_pack_weights(_ptr(weight), _ptr(wpack), Cout, cg * groups, kh, kw, groups, bn,
                                                _stream(weight)), "aanet_conv_pack_weights")
     _count()
     return wpack
+
+
+def _dp(t):
+    return None if t is None else t.data_ptr()
+
+
+def conv_batch(problems, deform=False, bn=0):
+    """Run 1..3 problems (dicts, see conv_problem) as one persistent engine launch; returns their outputs."""
+    n = len(problems)
+    descs = (_lib.ConvDesc * n)()
+    outs = []
+    for d, q in zip(descs, problems):
+        x = q["x"]
+        B, H, W, Cin = x.shape
+        Ho, Wo = _out_hw(H, W, q["kh"], q["kw"], q["stride"], q["pad"], q["dil"])
+        out = x.new_empty((B, q["Cout"], Ho, Wo) if q.get("out_nchw") else (B, Ho, Wo, q["Cout"]))
+        outs.append(out)
+        om = q.get("offmask")
+        d.x, d.wpack, d.out = x.data_ptr(), q["wpack"].data_ptr(), out.data_ptr()
+        d.bias, d.scale, d.shift = _dp(q.get("bias")), _dp(q.get("scale")), _dp(q.get("shift"))
+        d.residual, d.offmask = _dp(q.get("residual")), _dp(om)
+        d.om_channels = 0 if om is None else om.shape[-1]
+        d.B, d.Cin, d.H, d.W, d.Cout, d.kh, d.kw = B, Cin, H, W, q["Cout"], q["kh"], q["kw"]
+        d.stride, d.pad, d.dil, d.groups, d.dg = q["stride"], q["pad"], q["dil"], q.get("groups", 1), q.get("dg", 1)
+        d.act, d.slope = int(q.get("act", ACT_NONE)), float(q.get("slope", 0.2))
+        d.n_offset_ch, d.mask_scale = int(q.get("n_offset_ch", 0)), float(q.get("mask_scale", 1.0))
+        d.out_nchw = int(bool(q.get("out_nchw")))
+    x0 = problems[0]["x"]
+    with torch.cuda.device(x0.device):
+        _lib.check(_lib.load().aanet_conv_batch_nhwc(ctypes.cast(descs, ctypes.c_void_p), n, int(deform), int(bn),
+                                                     _stream(x0)), "aanet_conv_batch_nhwc")
+    _count()
+    return outs
 
 
 def conv2d_nhwc(x, wpack, Cout, kh, kw, bias=None, scale=None, shift=None, residual=None, act=ACT_NONE,
                 slope=0.2, stride=1, padding=0, dilation=1, groups=1, out_nchw=False, n_offset_ch=0,
                 mask_scale=1.0):
     """Dense convolution on channels-last activations x [B,H,W,Cin] with pre-packed weights."""
-    B, H, W, Cin = x.shape
-    Ho, Wo = _out_hw(H, W, kh, kw, stride, padding, dilation)
-    out = x.new_empty((B, Cout, Ho, Wo) if out_nchw else (B, Ho, Wo, Cout))
-    with torch.cuda.device(x.device):
-        _lib.check(_lib.load().aanet_conv2d_nhwc(
-            _ptr(x), _ptr(wpack), _ptr(bias), _ptr(scale), _ptr(shift), _ptr(residual), int(act), float(slope),
-            int(n_offset_ch), float(mask_scale), _ptr(out), int(out_nchw), B, Cin, H, W, Cout, kh, kw, stride,
-            padding, dilation, groups, _stream(x)), "aanet_conv2d_nhwc")
-    _count()
-    return out
+    return conv_batch([dict(x=x, wpack=wpack, Cout=Cout, kh=kh, kw=kw, bias=bias, scale=scale, shift=shift,
+                            residual=residual, act=act, slope=slope, stride=stride, pad=padding, dil=dilation,
+                            groups=groups, out_nchw=out_nchw, n_offset_ch=n_offset_ch, mask_scale=mask_scale)])[0]
 
 
 def mdcn_nhwc(x, offmask, wpack, Cout, kh, kw, bias=None, scale=None, shift=None, relu=False, stride=1,
               padding=0, dilation=1, groups=1, deformable_groups=1, out_nchw=False):
     """DCNv2 on channels-last x [B,H,W,Cin] with offsets+mask in one channels-last tensor."""
-    B, H, W, Cin = x.shape
-    Ho, Wo = _out_hw(H, W, kh, kw, stride, padding, dilation)
-    out = x.new_empty((B, Cout, Ho, Wo) if out_nchw else (B, Ho, Wo, Cout))
-    with torch.cuda.device(x.device):
-        _lib.check(_lib.load().aanet_mdcn_nhwc(
-            _ptr(x), _ptr(offmask), offmask.shape[-1], _ptr(wpack), _ptr(bias), _ptr(scale), _ptr(shift),
-            int(relu), _ptr(out), int(out_nchw), B, Cin, H, W, Cout, kh, kw, stride, padding, dilation, groups,
-            deformable_groups, _stream(x)), "aanet_mdcn_nhwc")
-    _count()
-    return out
+    return conv_batch([dict(x=x, offmask=offmask, wpack=wpack, Cout=Cout, kh=kh, kw=kw, bias=bias, scale=scale,
+                            shift=shift, act=ACT_RELU if relu else ACT_NONE, stride=stride, pad=padding,
+                            dil=dilation, groups=groups, dg=deformable_groups, out_nchw=out_nchw)], deform=True)[0]
 
 
 def csa_fuse_nhwc(terms, slope=0.2):

@@ -147,28 +147,44 @@ AANET_API int aanet_conv2d_fwd(const float *x, const float *weight, const float 
  * (tf32 hi/lo split + 128-byte swizzle) with aanet_conv_pack_weights into a buffer of
  * aanet_conv_wpack_bytes() bytes and reused until the weights change.
  *
- * aanet_conv2d_nhwc:  out = act((conv(x, w) + bias) * scale + shift + residual), out/residual channels-last
+ * dense problem:  out = act((conv(x, w) + bias) * scale + shift + residual), out/residual channels-last
  *   (out_nchw == 0) or NCHW (out_nchw != 0).  act 0-2 as above; act == 3 is the DeformConv2d offset/mask
  *   head (nets/deform.py:80-89): channels >= n_offset_ch get mask_scale * sigmoid(.), the rest pass through.
- * aanet_mdcn_nhwc:  DCNv2 with x channels-last and offsets+mask in ONE channels-last tensor
+ * deform problem:  DCNv2 with x channels-last and offsets+mask in ONE channels-last tensor
  *   offmask [B][Ho*Wo][om_channels], offsets in channels [0, dg*2*kh*kw) and the (already activated) mask
  *   behind them, i.e. the positional split of nets/deform.py:82-85; om_channels == dg*2*kh*kw means no
  *   mask (DCNv1).
  * ------------------------------------------------------------------------------------------- */
-AANET_API size_t aanet_conv_wpack_bytes(int Cout, int Cin, int kh, int kw, int groups);
+/* bn: N-tile width the weights are packed for -- 0 = the layer's own (multiple of 16, <= 64), or the width
+ * of the batch the layer will run in (aanet_conv_batch_nhwc). */
+AANET_API size_t aanet_conv_wpack_bytes(int Cout, int Cin, int kh, int kw, int groups, int bn);
 AANET_API int aanet_conv_pack_weights(const float *weight, void *wpack, int Cout, int Cin, int kh, int kw,
-                                      int groups, void *stream);
+                                      int groups, int bn, void *stream);
 AANET_API int aanet_nchw_to_nhwc(const float *src, float *dst, int B, int C, int HW, void *stream);
 AANET_API int aanet_nhwc_to_nchw(const float *src, float *dst, int B, int C, int HW, void *stream);
-AANET_API int aanet_conv2d_nhwc(const float *x, const void *wpack, const float *bias, const float *scale,
-                                const float *shift, const float *residual, int act, float slope,
-                                int n_offset_ch, float mask_scale, float *out, int out_nchw,
-                                int B, int Cin, int H, int W, int Cout, int kh, int kw,
-                                int stride, int pad, int dil, int groups, void *stream);
-AANET_API int aanet_mdcn_nhwc(const float *x, const float *offmask, int om_channels, const void *wpack,
-                              const float *bias, const float *post_scale, const float *post_shift, int relu,
-                              float *out, int out_nchw, int B, int Cin, int H, int W, int Cout, int kh, int kw,
-                              int stride, int pad, int dil, int groups, int dg, void *stream);
+
+/* One convolution problem of a batch.  DENSE: offmask/om_channels/dg ignored.  DEFORM: act must be 0 or 1. */
+typedef struct aanet_conv_desc {
+    const float *x;          /* [B][H*W][Cin] */
+    const void *wpack;       /* aanet_conv_pack_weights(..., bn) */
+    const float *bias, *scale, *shift, *residual;   /* optional; residual has out's layout */
+    float *out;              /* [B][Ho*Wo][Cout], or NCHW when out_nchw != 0 */
+    const float *offmask;    /* DEFORM: [B][Ho*Wo][om_channels] */
+    int om_channels;
+    int B, Cin, H, W, Cout, kh, kw, stride, pad, dil, groups, dg;
+    int act;                 /* 0 none, 1 ReLU, 2 LeakyReLU(slope), 3 offset/mask head */
+    float slope;
+    int n_offset_ch;         /* act == 3 */
+    float mask_scale;        /* act == 3 */
+    int out_nchw;
+} aanet_conv_desc;
+
+#define AANET_CONV_MAX_BATCH 3
+
+/* Runs 1..3 problems of the same kind (deform != 0: all DCN, else all dense) as ONE persistent kernel whose
+ * tile list spans all of them -- the three pyramid scales of one aggregation stage.  All problems use the
+ * same N-tile width bn (0 = the widest natural width among them); their weights must be packed for it. */
+AANET_API int aanet_conv_batch_nhwc(const aanet_conv_desc *descs, int n, int deform, int bn, void *stream);
 /* Channels-last twin of aanet_csa_fuse_fwd: terms and out are [B][h][w][C], C % 4 == 0. */
 AANET_API int aanet_csa_fuse_nhwc(const float *const *terms, const int *th, const int *tw, int n_terms,
                                   float *out, int B, int C, int H, int W, float slope, void *stream);

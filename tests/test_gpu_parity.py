@@ -309,6 +309,36 @@ def test_mdcn_nhwc(ops, cfg):
     assert rel_err(npy(v1), orc.mdcn_fwd(x, off, None, w, None, st, dil, dil, 1, dg)) < VOL_TOL
 
 
+def test_conv_batch_three_problems(ops):
+    """One persistent launch walking the tiles of three different dense problems (1x1 / 3x3 stride 2 / 3x3,
+    different channel counts and sizes, shared N-tile width 64), and of three deformable problems."""
+    torch.manual_seed(29)
+    specs = [(64, 64, 40, 56, 1, 1, 0, 1), (64, 32, 33, 47, 3, 2, 1, 1), (16, 16, 20, 28, 3, 1, 1, 1)]
+    probs, refs = [], []
+    for Ci, Co, H, W, k, st, pad, dil in specs:
+        x = torch.randn(2, Ci, H, W, device="cuda")
+        w = torch.randn(Co, Ci, k, k, device="cuda") / (Ci * k * k) ** 0.5
+        b = torch.randn(Co, device="cuda")
+        refs.append(torch.relu(torch.nn.functional.conv2d(x.double(), w.double(), b.double(), st, pad, dil)))
+        probs.append(dict(x=ops.nchw_to_nhwc(x), wpack=ops.pack_conv_weight(w, 1, 64), Cout=Co, kh=k, kw=k, bias=b,
+                          act=ops.ACT_RELU, stride=st, pad=pad, dil=dil))
+    outs = ops.conv_batch(probs, deform=False, bn=64)
+    for o, r in zip(outs, refs):
+        assert rel_err(npy(o.permute(0, 3, 1, 2)), npy(r)) < 1e-5
+    rng = np.random.default_rng(31)
+    dprobs, drefs = [], []
+    for C, H, W in [(64, 24, 40), (32, 12, 20), (16, 6, 10)]:
+        x = rng.standard_normal((1, C, H, W)).astype(np.float32)
+        off = (2 * rng.standard_normal((1, 36, H, W))).astype(np.float32)
+        msk = rng.uniform(0, 2, (1, 18, H, W)).astype(np.float32)
+        w = (rng.standard_normal((C, C, 3, 3)) / np.sqrt(C * 9)).astype(np.float32)
+        drefs.append(orc.mdcn_fwd(x, off, msk, w, None, 1, 2, 2, 1, 2))
+        dprobs.append(dict(x=ops.nchw_to_nhwc(cu(x)), offmask=ops.nchw_to_nhwc(cu(np.concatenate([off, msk], 1))),
+                           wpack=ops.pack_conv_weight(cu(w), 1, 64), Cout=C, kh=3, kw=3, stride=1, pad=2, dil=2, dg=2))
+    for o, r in zip(ops.conv_batch(dprobs, deform=True, bn=64), drefs):
+        assert rel_err(npy(o.permute(0, 3, 1, 2)), r) < VOL_TOL
+
+
 def test_csa_fuse_nhwc(ops):
     rng = np.random.default_rng(4)
     (B, C, H, W), ths = (2, 8, 31, 45), [(31, 45), (16, 23), (8, 12)]

@@ -56,9 +56,13 @@ def test_argument_errors_without_gpu(lib_path):
     assert lib.aanet_mdcn_workspace_bytes(0, 1, 6, 8, 8, 6, 3, 3, 1, 1, 1, 1, 1) == 0   # Cin % 4 != 0: FFMA path
     assert lib.aanet_conv2d_workspace_bytes(1, 64, 128, 416, 64, 1, 1, 1, 0, 1, 1) == \
         2 * 2 * 64 * 32 * 4 + 64 * 128 * 416 * 4
-    assert lib.aanet_conv_wpack_bytes(64, 64, 3, 3, 1) == 18 * 2 * 64 * 32 * 4
-    assert lib.aanet_conv_wpack_bytes(54, 64, 3, 3, 2) == 2 * 9 * 2 * 32 * 32 * 4     # grouped: N = 27 -> 32
-    assert lib.aanet_conv_wpack_bytes(8, 6, 3, 3, 1) == 0
+    assert lib.aanet_conv_wpack_bytes(64, 64, 3, 3, 1, 0) == 18 * 2 * 64 * 32 * 4
+    assert lib.aanet_conv_wpack_bytes(54, 64, 3, 3, 2, 0) == 2 * 9 * 2 * 32 * 32 * 4     # grouped: N = 27 -> 32
+    assert lib.aanet_conv_wpack_bytes(16, 16, 3, 3, 1, 64) == 5 * 2 * 64 * 32 * 4       # packed for a BN=64 batch
+    assert lib.aanet_conv_wpack_bytes(128, 64, 1, 1, 1, 0) == 2 * 2 * 2 * 64 * 32 * 4   # 128 outputs = 2 N tiles
+    assert lib.aanet_conv_wpack_bytes(8, 6, 3, 3, 1, 0) == 0
+    assert lib.aanet_conv_batch_nhwc(None, 1, 0, 0, None) == 1
+    assert lib.aanet_conv_batch_nhwc(p, 4, 0, 0, None) == 2                              # at most 3 problems
     assert lib.aanet_conv2d_fwd(p, p, None, None, None, None, 0, 0.0, p, 1, 6, 8, 8, 4, 3, 3, 1, 1, 1, 1,
                                 p, 1 << 20, None) == 3                                 # unsupported Cin
     with pytest.raises(_lib.AanetError):
