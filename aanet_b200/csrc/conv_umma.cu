@@ -717,7 +717,11 @@ template <int BN, bool DEFORM, bool MULTI>
 static int launch_inst(const ConvBatch &batch, cudaStream_t stream) {
     constexpr size_t smem = EngineCfg<BN>::kSmemBytes;
     cudaFuncSetAttribute(conv_umma_kernel<BN, DEFORM, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int grid = batch.total_tiles < kNumSMs ? batch.total_tiles : kNumSMs;
+    // Persistent grid: the fewest CTAs that still finish in ceil(tiles / #SMs) rounds (416 tiles -> 139 CTAs x 3
+    // tiles instead of 148 CTAs of which 28 would idle in the last round): the SMs left free run the coarse-scale
+    // kernels that the fused executor issues on parallel streams.
+    const int rounds = ceil_div(batch.total_tiles, kNumSMs);
+    const int grid = ceil_div(batch.total_tiles, rounds);
     conv_umma_kernel<BN, DEFORM, MULTI><<<grid, kUThreads, smem, stream>>>(batch);
     return check_launch();
 }

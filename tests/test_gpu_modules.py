@@ -134,6 +134,38 @@ def test_fused_executor_matches_module_path(D0, H, W, B):
     assert rel_err(npy(again[0]), npy(slow[0] + 1.0)) < 1e-4
 
 
+@pytest.mark.parametrize("name,D0,C,H,W,B", [
+    ("config3 AANet+ Scene Flow 576x960 (2 of the 64 pairs)", 64, 32, 192, 320, 2),
+    ("config5 1080p -> 1104x1920, max_disp 288", 96, 16, 368, 640, 1),
+])
+def test_hot_path_large_configs(name, D0, C, H, W, B):
+    """BASELINE configs 3 and 5 as parity cases: the fused tcgen05 executor against the module-by-module path
+    (cuDNN fp32 glue + the same operators) at full resolution, plus size-independent properties of the cost
+    volume (zero band, d = 0 plane) and of the disparity (range).  D0 = 96 exercises two N tiles per layer."""
+    import aanet_b200.nets as n
+    torch.manual_seed(326)
+    agg = n.AdaptiveAggregation(D0, num_deform_blocks=3, intermediate_supervision=False).cuda().eval()
+    for nm, m in agg.named_modules():
+        if nm.endswith("offset_conv"):
+            torch.nn.init.normal_(m.weight, std=0.05); torch.nn.init.normal_(m.bias, std=0.05)
+    Ls = [torch.relu(torch.randn(B, C << s if D0 == 64 else 128, H >> s, W >> s, device="cuda")) for s in range(3)]
+    Rs = [torch.relu(torch.randn_like(l)) for l in Ls]
+    with torch.no_grad():
+        costs = n.CostVolumePyramid(D0)(Ls, Rs)
+        for s, c in enumerate(costs):
+            Ds = D0 >> s
+            assert c.shape == (B, Ds, H >> s, W >> s)
+            assert torch.all(c[:, Ds - 1, :, :Ds - 1] == 0)
+            assert rel_err(npy(c[:, 0]), npy((Ls[s] * Rs[s]).mean(1))) < 1e-5
+        fast = agg([c.clone() for c in costs])
+        agg.use_fused_inference = False
+        slow = agg([c.clone() for c in costs])
+        d_fast, d_slow = n.DisparityEstimation(D0)(fast[0]), n.DisparityEstimation(D0)(slow[0])
+    assert rel_err(npy(fast[0]), npy(slow[0])) < 1e-4
+    assert (d_fast - d_slow).abs().max().item() < 1e-3
+    assert float(d_fast.min()) >= 0 and float(d_fast.max()) <= D0 - 1
+
+
 def test_training_step_runs():
     """fwd + bwd through the drop-in modules in train mode (BN batch statistics, autograd kernels)."""
     import aanet_b200.nets as n
