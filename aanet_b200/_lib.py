@@ -19,6 +19,7 @@ SIGNATURES = {
     "aanet_status_string": (ctypes.c_char_p, [_i]),
     "aanet_last_cuda_error": (ctypes.c_char_p, []),
     "aanet_corr_fwd": (_i, [_vp, _vp, _vp] + [_i] * 5 + [_vp]),
+    "aanet_corr_fwd_bf16": (_i, [_vp, _vp, _vp] + [_i] * 5 + [_vp]),
     "aanet_corr_bwd": (_i, [_vp] * 5 + [_i] * 5 + [_vp]),
     "aanet_softargmin_fwd": (_i, [_vp, _vp] + [_i] * 5 + [_vp]),
     "aanet_softargmin_bwd": (_i, [_vp, _vp, _vp] + [_i] * 5 + [_vp]),
@@ -45,7 +46,8 @@ class ConvDesc(ctypes.Structure):
                 ("out", _vp), ("offmask", _vp), ("om_channels", _i),
                 ("B", _i), ("Cin", _i), ("H", _i), ("W", _i), ("Cout", _i), ("kh", _i), ("kw", _i),
                 ("stride", _i), ("pad", _i), ("dil", _i), ("groups", _i), ("dg", _i),
-                ("act", _i), ("slope", _f), ("n_offset_ch", _i), ("mask_scale", _f), ("out_nchw", _i)]
+                ("act", _i), ("slope", _f), ("n_offset_ch", _i), ("mask_scale", _f), ("out_nchw", _i),
+                ("om_nchw", _i)]
 
 
 _lib = None

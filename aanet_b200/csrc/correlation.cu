@@ -12,6 +12,7 @@
 // tile finds R[w-d] in shared memory.  A thread accumulates an 8(w) x 8(d) register tile: per
 // channel it needs 8 L values and the 15-wide R diagonal band, fetched as 2+4 LDS.128 for 64 FMAs.
 // The w<d triangle is written as exact zeros (the reference's new_zeros, cost.py:41).
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace aanet {
@@ -211,6 +212,105 @@ corr_fwd_pipelined_kernel(const float *__restrict__ L, const float *__restrict__
     }
 }
 
+// bf16-feature variant (BASELINE config 5: "bf16 cost-volume variant with stated EPE tolerance"): L and R are
+// bf16, products and the channel sum are fp32, the volume is fp32.  Same tiling and cp.async ring; a 16-byte
+// copy now carries 8 features, halving both the HBM reads and the shared-memory operand traffic.  Requires
+// W % 8 == 0.
+__device__ __forceinline__ void unpack_bf16x8(const uint4 &q, float *f) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+
+__global__ void __launch_bounds__(kCorrThreads)
+corr_fwd_bf16_kernel(const __nv_bfloat16 *__restrict__ L, const __nv_bfloat16 *__restrict__ R,
+                     float *__restrict__ cost, int C, int H, int W, int D, int n_wtiles) {
+    __shared__ __align__(16) __nv_bfloat16 sL[kCorrStages][kCK][kTW];
+    __shared__ __align__(16) __nv_bfloat16 sR[kCorrStages][kCK][kRW];
+
+    const int wt = blockIdx.x % n_wtiles, dt = blockIdx.x / n_wtiles;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int w0 = wt * kTW, d0 = dt * kTD;
+    const int tid = threadIdx.x;
+    const int tw = (tid & 15) * 8, td = (tid >> 4) * 8;
+    const long HW = (long)H * W;
+    const __nv_bfloat16 *Lrow = L + (long)b * C * HW + (long)h * W;
+    const __nv_bfloat16 *Rrow = R + (long)b * C * HW + (long)h * W;
+    const int rbase = w0 - d0 - kTD;
+    const bool all_zero = (w0 + kTW - 1) < d0;
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    const int nchunk = all_zero ? 0 : ceil_div(C, kCK);
+    auto issue = [&](int ck) {
+        if (ck < nchunk) {
+            const int buf = ck % kCorrStages, c0 = ck * kCK;
+            for (int i = tid; i < kCK * (kTW / 8); i += kCorrThreads) {
+                const int c = i / (kTW / 8), x = (i % (kTW / 8)) * 8, w = w0 + x;
+                const bool ok = (c0 + c < C) && (w < W);
+                cp_async16(&sL[buf][c][x], ok ? Lrow + (long)(c0 + c) * HW + w : Lrow, ok);
+            }
+            for (int i = tid; i < kCK * (kRW / 8); i += kCorrThreads) {
+                const int c = i / (kRW / 8), x = (i % (kRW / 8)) * 8, w = rbase + x;
+                const bool ok = (c0 + c < C) && (w >= 0) && (w < W);
+                cp_async16(&sR[buf][c][x], ok ? Rrow + (long)(c0 + c) * HW + w : Rrow, ok);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(0);
+    issue(1);
+    for (int ck = 0; ck < nchunk; ++ck) {
+        issue(ck + 2);
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        __syncthreads();
+        const int buf = ck % kCorrStages;
+#pragma unroll
+        for (int c = 0; c < kCK; ++c) {
+            float l[8], r[16];
+            unpack_bf16x8(*reinterpret_cast<const uint4 *>(&sL[buf][c][tw]), l);
+            const int rb = tw - td + kTD - 8;
+            unpack_bf16x8(*reinterpret_cast<const uint4 *>(&sR[buf][c][rb]), r);
+            unpack_bf16x8(*reinterpret_cast<const uint4 *>(&sR[buf][c][rb + 8]), r + 8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(l[i], r[8 + i - j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    const float inv = 1.f / (float)C;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int d = d0 + td + j;
+        if (d >= D) continue;
+        float *orow = cost + (((long)b * D + d) * H + h) * W;
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int w = w0 + tw + i;
+            o[i] = (w >= d) ? acc[i][j] * inv : 0.f;
+        }
+        const int w = w0 + tw;
+        if (w + 8 <= W) {
+            *reinterpret_cast<float4 *>(orow + w) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4 *>(orow + w + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (w + i < W) orow[w + i] = o[i];
+        }
+    }
+}
+
 // Backward (autograd of cost.py:45-48):
 //   gL[c,w]  = (1/C) sum_{d<=w}    g[d,w]    * R[c,w-d]
 //   gR[c,w'] = (1/C) sum_{w'+d<W}  g[d,w'+d] * L[c,w'+d]
@@ -263,6 +363,21 @@ extern "C" int aanet_corr_fwd(const float *L, const float *R, float *cost, int B
         corr_fwd_pipelined_kernel<<<grid, kCorrThreads, 0, as_stream(stream)>>>(L, R, cost, C, H, W, D, n_wtiles);
     else
         corr_fwd_kernel<<<grid, kCorrThreads, 0, as_stream(stream)>>>(L, R, cost, C, H, W, D, n_wtiles);
+    return check_launch();
+}
+
+extern "C" int aanet_corr_fwd_bf16(const void *L, const void *R, float *cost, int B, int C, int H, int W, int D,
+                                   void *stream) {
+    if (!L || !R || !cost) return AANET_ERR_NULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || D <= 0) return AANET_ERR_SHAPE;
+    if (H > 65535 || B > 65535) return AANET_ERR_UNSUPPORTED;
+    if (W % 8 || !aligned16(static_cast<const char *>(L)) || !aligned16(static_cast<const char *>(R)) ||
+        !aligned16(cost))
+        return AANET_ERR_UNSUPPORTED;
+    const int n_wtiles = ceil_div(W, kTW), n_dtiles = ceil_div(D, kTD);
+    const dim3 grid(n_wtiles * n_dtiles, H, B);
+    corr_fwd_bf16_kernel<<<grid, kCorrThreads, 0, as_stream(stream)>>>(
+        static_cast<const __nv_bfloat16 *>(L), static_cast<const __nv_bfloat16 *>(R), cost, C, H, W, D, n_wtiles);
     return check_launch();
 }
 

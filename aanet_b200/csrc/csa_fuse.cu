@@ -80,41 +80,71 @@ csa_fuse_fwd_kernel(CsaTerms t, float *__restrict__ out, int H, int W, long n_ve
 }
 
 // Channels-last variant for the fused inference path: terms and out are [B][h][w][C], C % 4 == 0.
+// A thread owns kCsaChunks 16-byte channel chunks of ONE pixel (chunk q, q + Cv/kCsaChunks, ...), so the
+// bilinear source indices / weights of the resized terms are computed once per thread instead of once per
+// chunk (ncu on the one-chunk-per-thread version: 68 % issue utilisation, i.e. bound by that index math),
+// while the lanes of a pixel still read consecutive 16-byte chunks.
+constexpr int kCsaChunks = 4;
+
 __global__ void __launch_bounds__(256)
-csa_fuse_nhwc_kernel(CsaTerms t, float *__restrict__ out, int H, int W, int C, long n_vec, float slope) {
-    const int Cv = C / 4;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long)gridDim.x * blockDim.x) {
-        const int cv = (int)(i % Cv);
-        long r = i / Cv;
+csa_fuse_nhwc_kernel(CsaTerms t, float *__restrict__ out, int H, int W, int C, long n_items, int tpp, float slope) {
+    const int Cv = C / 4;                 // 16-byte chunks per pixel; tpp = threads per pixel = ceil(Cv / kCsaChunks)
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += (long)gridDim.x * blockDim.x) {
+        const int q = (int)(i % tpp);
+        long r = i / tpp;
         const int w = (int)(r % W); r /= W;
         const int h = (int)(r % H);
         const long b = r / H;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        // per-term geometry: 4 source pixel offsets (in chunks) and 4 weights; same-size terms use slot 0 only
+        long o00[AANET_CSA_MAX_TERMS], o01[AANET_CSA_MAX_TERMS], o10[AANET_CSA_MAX_TERMS], o11[AANET_CSA_MAX_TERMS];
+        float w00[AANET_CSA_MAX_TERMS], w01[AANET_CSA_MAX_TERMS], w10[AANET_CSA_MAX_TERMS], w11[AANET_CSA_MAX_TERMS];
+        bool same[AANET_CSA_MAX_TERMS];
 #pragma unroll
         for (int k = 0; k < AANET_CSA_MAX_TERMS; ++k) {
             if (k >= t.n) break;
             const int th = t.th[k], tw = t.tw[k];
-            const float4 *src = reinterpret_cast<const float4 *>(t.ptr[k]) + b * th * tw * Cv + cv;
-            float4 v;
-            if (th == H && tw == W) {
-                v = __ldg(src + ((long)h * W + w) * Cv);
+            const long base = b * th * tw;
+            same[k] = (th == H && tw == W);
+            if (same[k]) {
+                o00[k] = (base + (long)h * W + w) * Cv;
             } else {
-                int h0, h1, w0, w1; float a0, a1, b0, b1;
+                int h0, h1, x0, x1; float a0, a1, b0, b1;
                 src_index(h, th, (float)th / (float)H, h0, h1, a0, a1);
-                src_index(w, tw, (float)tw / (float)W, w0, w1, b0, b1);
-                const float4 v00 = __ldg(src + ((long)h0 * tw + w0) * Cv), v01 = __ldg(src + ((long)h0 * tw + w1) * Cv);
-                const float4 v10 = __ldg(src + ((long)h1 * tw + w0) * Cv), v11 = __ldg(src + ((long)h1 * tw + w1) * Cv);
-                v.x = a0 * (b0 * v00.x + b1 * v01.x) + a1 * (b0 * v10.x + b1 * v11.x);
-                v.y = a0 * (b0 * v00.y + b1 * v01.y) + a1 * (b0 * v10.y + b1 * v11.y);
-                v.z = a0 * (b0 * v00.z + b1 * v01.z) + a1 * (b0 * v10.z + b1 * v11.z);
-                v.w = a0 * (b0 * v00.w + b1 * v01.w) + a1 * (b0 * v10.w + b1 * v11.w);
+                src_index(w, tw, (float)tw / (float)W, x0, x1, b0, b1);
+                o00[k] = (base + (long)h0 * tw + x0) * Cv; o01[k] = (base + (long)h0 * tw + x1) * Cv;
+                o10[k] = (base + (long)h1 * tw + x0) * Cv; o11[k] = (base + (long)h1 * tw + x1) * Cv;
+                w00[k] = a0 * b0; w01[k] = a0 * b1; w10[k] = a1 * b0; w11[k] = a1 * b1;
             }
-            if (k == 0) acc = v;
-            else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
         }
-        acc.x = acc.x > 0.f ? acc.x : acc.x * slope; acc.y = acc.y > 0.f ? acc.y : acc.y * slope;
-        acc.z = acc.z > 0.f ? acc.z : acc.z * slope; acc.w = acc.w > 0.f ? acc.w : acc.w * slope;
-        reinterpret_cast<float4 *>(out)[i] = acc;
+        float4 *orow = reinterpret_cast<float4 *>(out) + ((b * H + h) * W + w) * Cv;
+#pragma unroll
+        for (int u = 0; u < kCsaChunks; ++u) {
+            const int cv = q + u * tpp;
+            if (cv >= Cv) break;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < AANET_CSA_MAX_TERMS; ++k) {
+                if (k >= t.n) break;
+                const float4 *src = reinterpret_cast<const float4 *>(t.ptr[k]) + cv;
+                float4 v;
+                if (same[k]) {
+                    v = __ldg(src + o00[k]);
+                } else {
+                    // a0*(b0*v00 + b1*v01) + a1*(b0*v10 + b1*v11), evaluated with the products of the weights
+                    const float4 v00 = __ldg(src + o00[k]), v01 = __ldg(src + o01[k]);
+                    const float4 v10 = __ldg(src + o10[k]), v11 = __ldg(src + o11[k]);
+                    v.x = w00[k] * v00.x + w01[k] * v01.x + w10[k] * v10.x + w11[k] * v11.x;
+                    v.y = w00[k] * v00.y + w01[k] * v01.y + w10[k] * v10.y + w11[k] * v11.y;
+                    v.z = w00[k] * v00.z + w01[k] * v01.z + w10[k] * v10.z + w11[k] * v11.z;
+                    v.w = w00[k] * v00.w + w01[k] * v01.w + w10[k] * v10.w + w11[k] * v11.w;
+                }
+                if (k == 0) acc = v;
+                else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+            }
+            acc.x = acc.x > 0.f ? acc.x : acc.x * slope; acc.y = acc.y > 0.f ? acc.y : acc.y * slope;
+            acc.z = acc.z > 0.f ? acc.z : acc.z * slope; acc.w = acc.w > 0.f ? acc.w : acc.w * slope;
+            orow[cv] = acc;
+        }
     }
 }
 
@@ -214,8 +244,9 @@ extern "C" int aanet_csa_fuse_nhwc(const float *const *terms, const int *th, con
         if (!aligned16(terms[k])) return AANET_ERR_UNSUPPORTED;
         t.ptr[k] = terms[k]; t.th[k] = th[k]; t.tw[k] = tw[k];
     }
-    const long n = (long)B * H * W * (C / 4);
-    csa_fuse_nhwc_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(t, out, H, W, C, n, slope);
+    const int tpp = ceil_div(C / 4, kCsaChunks);
+    const long n = (long)B * H * W * tpp;
+    csa_fuse_nhwc_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(t, out, H, W, C, n, tpp, slope);
     return check_launch();
 }
 

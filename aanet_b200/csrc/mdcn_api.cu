@@ -181,9 +181,15 @@ static int problem_from_desc(const aanet_conv_desc &c, bool deform, ConvParams &
         if (!c.offmask) return AANET_ERR_NULL;
         const int n_off = c.dg * 2 * d.K, n_mask = c.dg * d.K;
         if (c.om_channels != n_off && c.om_channels != n_off + n_mask) return AANET_ERR_SHAPE;
-        p.offset = c.offmask; p.off_bs = (long)d.P * c.om_channels; p.off_ps = c.om_channels; p.off_cs = 1;
-        p.mask = (c.om_channels == n_off) ? nullptr : c.offmask + n_off;
-        p.mask_bs = p.off_bs; p.mask_ps = c.om_channels; p.mask_cs = 1;
+        p.offset = c.offmask; p.off_bs = (long)d.P * c.om_channels;
+        if (c.om_nchw) {        // channel planes: consecutive pixels are consecutive addresses
+            p.off_ps = 1; p.off_cs = d.P;
+            p.mask = (c.om_channels == n_off) ? nullptr : c.offmask + (long)n_off * d.P;
+        } else {
+            p.off_ps = c.om_channels; p.off_cs = 1;
+            p.mask = (c.om_channels == n_off) ? nullptr : c.offmask + n_off;
+        }
+        p.mask_bs = p.off_bs; p.mask_ps = p.off_ps; p.mask_cs = p.off_cs;
     }
     return AANET_OK;
 }

@@ -54,10 +54,12 @@ class _Deform:
         self.groups, self.dg = dc.groups, dc.deformable_groups
 
     def __call__(self, x):
-        # offsets pass through, mask channels get mask_scale * sigmoid (deform.py:82-89), one tensor
-        om = self.head(x, act=ops.ACT_OFFSET_MASK, n_offset_ch=self.n_off, mask_scale=self.mask_scale)
+        # offsets pass through, mask channels get mask_scale * sigmoid (deform.py:82-89), one tensor, written
+        # as channel planes: the DCN producers read it pixel-contiguously
+        om = self.head(x, act=ops.ACT_OFFSET_MASK, n_offset_ch=self.n_off, mask_scale=self.mask_scale,
+                       out_nchw=True)
         return ops.mdcn_nhwc(x, om, self.wpack, self.Cout, self.kh, self.kw, self.bias, self.scale, self.shift,
-                             True, self.stride, self.pad, self.dil, self.groups, self.dg)
+                             True, self.stride, self.pad, self.dil, self.groups, self.dg, om_nchw=True)
 
 
 class _Bottleneck:

@@ -70,8 +70,27 @@ class _Correlation(Function):
 
 
 def correlation(left, right, max_disp):
-    """cost[b,d,h,w] = mean_c left[b,c,h,w]*right[b,c,h,w-d], 0 where w<d (nets/cost.py:40-48)."""
+    """cost[b,d,h,w] = mean_c left[b,c,h,w]*right[b,c,h,w-d], 0 where w<d (nets/cost.py:40-48).
+    bfloat16 features select the bf16 cost-volume variant (inference only, fp32 volume)."""
+    if left.dtype == torch.bfloat16:
+        return correlation_bf16(left, right, max_disp)
     return _Correlation.apply(left, right, int(max_disp))
+
+
+def correlation_bf16(left, right, max_disp):
+    """BASELINE config 5 variant: bf16 features, fp32 accumulation and fp32 volume (no autograd)."""
+    if not left.is_cuda:
+        raise NotImplementedError("aanet_b200.correlation_bf16: CUDA tensors only (no CPU fallback)")
+    if left.dtype != torch.bfloat16 or right.dtype != torch.bfloat16 or left.shape != right.shape:
+        raise TypeError("correlation_bf16: left/right must be bfloat16 tensors of equal shape")
+    left, right = left.contiguous(), right.contiguous()
+    B, C, H, W = left.shape
+    out = torch.empty(B, int(max_disp), H, W, dtype=torch.float32, device=left.device)
+    with torch.cuda.device(left.device):
+        _lib.check(_lib.load().aanet_corr_fwd_bf16(_ptr(left), _ptr(right), _ptr(out), B, C, H, W, int(max_disp),
+                                                   _stream(left)), "aanet_corr_fwd_bf16")
+    _count()
+    return out
 
 
 # ------------------------------------------------------------------------------------ soft-argmin
@@ -336,7 +355,8 @@ def conv_batch(problems, deform=False, bn=0):
         d.x, d.wpack, d.out = x.data_ptr(), q["wpack"].data_ptr(), out.data_ptr()
         d.bias, d.scale, d.shift = _dp(q.get("bias")), _dp(q.get("scale")), _dp(q.get("shift"))
         d.residual, d.offmask = _dp(q.get("residual")), _dp(om)
-        d.om_channels = 0 if om is None else om.shape[-1]
+        d.om_nchw = int(bool(q.get("om_nchw")))
+        d.om_channels = 0 if om is None else (om.shape[1] if d.om_nchw else om.shape[-1])
         d.B, d.Cin, d.H, d.W, d.Cout, d.kh, d.kw = B, Cin, H, W, q["Cout"], q["kh"], q["kw"]
         d.stride, d.pad, d.dil, d.groups, d.dg = q["stride"], q["pad"], q["dil"], q.get("groups", 1), q.get("dg", 1)
         d.act, d.slope = int(q.get("act", ACT_NONE)), float(q.get("slope", 0.2))
@@ -360,11 +380,13 @@ def conv2d_nhwc(x, wpack, Cout, kh, kw, bias=None, scale=None, shift=None, resid
 
 
 def mdcn_nhwc(x, offmask, wpack, Cout, kh, kw, bias=None, scale=None, shift=None, relu=False, stride=1,
-              padding=0, dilation=1, groups=1, deformable_groups=1, out_nchw=False):
-    """DCNv2 on channels-last x [B,H,W,Cin] with offsets+mask in one channels-last tensor."""
+              padding=0, dilation=1, groups=1, deformable_groups=1, out_nchw=False, om_nchw=False):
+    """DCNv2 on channels-last x [B,H,W,Cin] with offsets+mask in one tensor: channels-last [B,Ho,Wo,om] or,
+    with om_nchw, channel planes [B,om,Ho,Wo] (one L1 wavefront per offset load instead of ~20)."""
     return conv_batch([dict(x=x, offmask=offmask, wpack=wpack, Cout=Cout, kh=kh, kw=kw, bias=bias, scale=scale,
                             shift=shift, act=ACT_RELU if relu else ACT_NONE, stride=stride, pad=padding,
-                            dil=dilation, groups=groups, dg=deformable_groups, out_nchw=out_nchw)], deform=True)[0]
+                            dil=dilation, groups=groups, dg=deformable_groups, out_nchw=out_nchw,
+                            om_nchw=om_nchw)], deform=True)[0]
 
 
 def csa_fuse_nhwc(terms, slope=0.2):

@@ -56,6 +56,13 @@ AANET_API const char *aanet_last_cuda_error(void);
 AANET_API int aanet_corr_fwd(const float *L, const float *R, float *cost,
                    int B, int C, int H, int W, int D, void *stream);
 
+/* bf16-feature variant (BASELINE config 5): L, R are bfloat16 [B,C,H,W]; products, channel sum and the
+ * volume stay fp32.  Not bit-comparable with the reference (features are rounded to 8 mantissa bits); the
+ * tests state the resulting end-point error.  Requires W % 8 == 0 (else AANET_ERR_UNSUPPORTED).  Inference
+ * only. */
+AANET_API int aanet_corr_fwd_bf16(const void *L, const void *R, float *cost,
+                                  int B, int C, int H, int W, int D, void *stream);
+
 /* Gradient of the above (the reference gets it from autograd of cost.py:45-48).
  * gcost: [B,D,H,W]   gL, gR: [B,C,H,W] (overwritten) */
 AANET_API int aanet_corr_bwd(const float *L, const float *R, const float *gcost, float *gL, float *gR,
@@ -177,6 +184,7 @@ typedef struct aanet_conv_desc {
     int n_offset_ch;         /* act == 3 */
     float mask_scale;        /* act == 3 */
     int out_nchw;
+    int om_nchw;             /* DEFORM: offmask is [B][om_channels][Ho*Wo] (channel planes) instead of channels-last */
 } aanet_conv_desc;
 
 #define AANET_CONV_MAX_BATCH 3

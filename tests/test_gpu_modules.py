@@ -166,6 +166,28 @@ def test_hot_path_large_configs(name, D0, C, H, W, B):
     assert float(d_fast.min()) >= 0 and float(d_fast.max()) <= D0 - 1
 
 
+def test_bf16_cost_volume_epe():
+    """BASELINE config 5: bf16 cost-volume variant.  End-point error (metric.py:7-14 = mean |d_a - d_b|) of the
+    1/3-scale disparity against the fp32 path, same random-init aggregation weights.  Stated tolerance:
+    EPE <= 0.005 px (disparity range 0..95); measured on the B200: 0.00015 px, max |diff| 0.0009 px."""
+    import aanet_b200.nets as n
+    torch.manual_seed(326)
+    D0, H, W = 96, 184, 320          # half of the 1104x1920 1/3-scale plane, keeps the test quick
+    agg = n.AdaptiveAggregation(D0, num_deform_blocks=3, intermediate_supervision=False).cuda().eval()
+    for nm, m in agg.named_modules():
+        if nm.endswith("offset_conv"):
+            torch.nn.init.normal_(m.weight, std=0.05); torch.nn.init.normal_(m.bias, std=0.05)
+    Ls = [torch.relu(torch.randn(1, 128, H >> s, W >> s, device="cuda")) for s in range(3)]
+    Rs = [torch.relu(torch.randn_like(l)) for l in Ls]
+    cv, est = n.CostVolumePyramid(D0), n.DisparityEstimation(D0)
+    with torch.no_grad():
+        d32 = est(agg(cv(Ls, Rs))[0])
+        d16 = est(agg(cv([l.bfloat16() for l in Ls], [r.bfloat16() for r in Rs]))[0])
+    epe = (d32 - d16).abs().mean().item()
+    print("bf16 cost volume: EPE vs fp32 = %.5f px, max |diff| = %.4f px" % (epe, (d32 - d16).abs().max().item()))
+    assert epe <= 0.005
+
+
 def test_training_step_runs():
     """fwd + bwd through the drop-in modules in train mode (BN batch statistics, autograd kernels)."""
     import aanet_b200.nets as n

@@ -81,6 +81,24 @@ def test_corr_full_size_properties(ops):
         assert rel_err(npy(a[:, d, :, d:]), npy((L[..., d:] * R[..., :-d]).mean(1))) < 1e-5
 
 
+def test_corr_bf16_variant(ops):
+    """Config-5 variant: bf16 features.  Exact w.r.t. the oracle fed the SAME bf16-rounded features (fp32
+    accumulation), and within a stated error of the fp32 volume: rel 1e-2 (8 mantissa bits per factor)."""
+    torch.manual_seed(326)
+    B, C, H, W, D = 1, 128, 16, 416, 64
+    L = torch.relu(torch.randn(B, C, H, W, device="cuda"))
+    R = torch.relu(torch.randn(B, C, H, W, device="cuda"))
+    Lb, Rb = L.bfloat16(), R.bfloat16()
+    vol = ops.correlation(Lb, Rb, D)
+    assert vol.dtype == torch.float32
+    ref_same = orc.corr_fwd(npy(Lb), npy(Rb), D)
+    assert rel_err(npy(vol), ref_same) < 1e-5
+    assert rel_err(npy(vol), npy(ops.correlation(L, R, D))) < 1e-2
+    assert torch.all(vol[:, 63, :, :63] == 0)
+    with pytest.raises(RuntimeError):
+        ops.correlation(Lb[..., :412].contiguous(), Rb[..., :412].contiguous(), D)     # W % 8 != 0
+
+
 # ------------------------------------------------------------------------------------ soft-argmin
 @pytest.mark.parametrize("tag", ["sim", "cost", "d1", "peaky"])
 def test_softargmin_golden(ops, golden, tag):
@@ -304,6 +322,9 @@ def test_mdcn_nhwc(ops, cfg):
     out = ops.mdcn_nhwc(ops.nchw_to_nhwc(cu(x)), om, ops.pack_conv_weight(cu(w)), Co, 3, 3, None, None, None, False,
                         st, dil, dil, 1, dg)
     assert rel_err(npy(out.permute(0, 3, 1, 2)), ref) < VOL_TOL
+    planes = ops.mdcn_nhwc(ops.nchw_to_nhwc(cu(x)), cu(np.concatenate([off, msk], 1)), ops.pack_conv_weight(cu(w)),
+                           Co, 3, 3, None, None, None, False, st, dil, dil, 1, dg, om_nchw=True)
+    assert rel_err(npy(planes.permute(0, 3, 1, 2)), ref) < VOL_TOL
     v1 = ops.mdcn_nhwc(ops.nchw_to_nhwc(cu(x)), ops.nchw_to_nhwc(cu(off)), ops.pack_conv_weight(cu(w)), Co, 3, 3,
                        None, None, None, False, st, dil, dil, 1, dg, out_nchw=True)          # DCNv1: no mask
     assert rel_err(npy(v1), orc.mdcn_fwd(x, off, None, w, None, st, dil, dil, 1, dg)) < VOL_TOL
