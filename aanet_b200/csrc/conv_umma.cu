@@ -20,21 +20,24 @@
 // Blackwell mapping.  A CTA is persistent (grid = #SMs) and walks 128-pixel tiles.  M = 128 pixels is
 // the UMMA M (one TMEM lane per pixel), N = BN <= 64 output channels (wider layers = several N tiles), K walks (tap, channel) in blocks of
 // 32 tf32 = one 128-byte swizzle row.  Warp roles:
-//   warps 0-15  A producers, 4 groups of 4 warps; a group fills a whole stage, so four K blocks are in
+//   warps 0-11  A producers, 3 groups of 4 warps; a group fills a whole stage, so three K blocks are in
 //               production at once.  lane = (pixel row, 16-byte chunk): LDG.128 (4 per item for DEFORM, 1
 //               for DENSE), bilinear combine, split into tf32 hi + lo (cvt.rna + exact remainder), two
 //               STS.128 into SWIZZLE_128B K-major tiles; fence.proxy.async + mbarrier arrive.  Each lane
 //               owns the geometry (output coordinates, bilinear sample) of ONE of the 8 rows its row group
 //               covers and broadcasts it with __shfl_sync, so the sampling math is done once per
 //               (pixel, tap, deformable group) instead of once per 16-byte chunk.
-//   warp 21     streams the pre-split, pre-swizzled weight block of the stage with one cp.async.bulk.
-//   warp 20     one thread issues the 3xTF32 products per K step (hi*hi + hi*lo + lo*hi: fp32-grade accuracy,
+//   warp 17     streams the pre-split, pre-swizzled weight block of the stage with one cp.async.bulk.
+//   warp 16     one thread issues the 3xTF32 products per K step (hi*hi + hi*lo + lo*hi: fp32-grade accuracy,
 //               the parity bar is 1e-4) as tcgen05.mma.kind::tf32 into one of two TMEM accumulators -- two
 //               MMAs with the stacked [B_hi|B_lo] operand at BN <= 64, three otherwise -- and releases the
 //               stage with tcgen05.commit.
-//   warps 16-19 epilogue: tcgen05.ld (lane = pixel), bias / folded-BN affine / residual / activation,
+//   warps 12-15 epilogue: tcgen05.ld (lane = pixel), bias / folded-BN affine / residual / activation,
 //               128-bit channels-last stores (or coalesced NCHW stores); runs one tile behind the MMA.
-// All hand-offs are mbarriers; the ring (4 stages at BN = 64) runs across tile boundaries.
+// All hand-offs are mbarriers; the 3-stage ring runs across tile boundaries.  3 stages x 48 KB keep the smem
+// carve-out at 164 KB, i.e. ~90 KB of L1 for the gathers; multi-tap convolutions use 16 x 8 pixel tiles so
+// that a tile's footprint over all taps fits it (1-D 128-pixel tiles + 206 KB of smem gave a 13 % L1 hit rate
+// and 579 MB of L2->L1 traffic per 1/3-scale deformable conv).
 #include "mdcn_common.cuh"
 #include "umma.cuh"
 
@@ -42,14 +45,16 @@ namespace aanet {
 
 constexpr int kUM = 128;                 // pixels per tile (UMMA M)
 constexpr int kUK = 32;                  // K per stage (one 128-byte swizzle row of tf32)
-constexpr int kProdWarps = 16;           // A producers: kGroups groups of 4 warps
-constexpr int kGroups = 4;               // each group fills one whole stage; 4 K blocks are in production at once
-constexpr int kMmaWarp = 20, kLoadWarp = 21;
-constexpr int kUThreads = 22 * 32;
-// 704 threads -> 88 registers per thread.  (setmaxnreg rebalancing between the roles faulted on the B200
-// test box with "unspecified launch failure"; the producers fit in the uniform budget without spills.)
+constexpr int kGroups = 3;               // producer groups; each fills one whole stage (3 K blocks in production at once)
+constexpr int kProdWarps = 4 * kGroups;  // A producers: kGroups groups of 4 warps
+constexpr int kTileW = 16, kTileH = 8;   // 2-D pixel tile (multi-tap convolutions): 128 = 16 x 8 output pixels
+constexpr int kMmaWarp = kProdWarps + 4, kLoadWarp = kProdWarps + 5;   // warps kProdWarps..+3: epilogue
+constexpr int kUThreads = (kProdWarps + 6) * 32;                        // 576 threads -> 112 registers each
+// (setmaxnreg rebalancing between the roles faulted on the B200 test box with "unspecified launch failure";
+// the producers fit in the uniform budget without spills.)
 constexpr int kATileBytes = kUM * kUK * 4;   // 16 KB (hi); same for lo
-constexpr int kSmemBudget = 200 * 1024;   // dynamic; ~9 KB of static tables on top (227 KB per SM)
+constexpr int kSmemBudget = 150 * 1024;   // dynamic (3 stages x <= 48 KB); ~9 KB of static tables on top.  Staying
+                                          // under the 164 KB carve-out leaves ~90 KB of L1 for the gathers.
 constexpr int kMaxKB = 256;               // K <= 8192
 
 enum ConvAct { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_OFFSET_MASK = 3 };
@@ -72,7 +77,8 @@ struct ConvParams {
     MdcnDims d;
     int K, KB;                          // K = kh*kw*Cg, KB = ceil(K / 32)
     int n_tiles_n;                      // ceil(Og / BN)
-    int tiles_per_img;                  // ceil(P / 128)
+    int tile2d, tiles_x;                // 2-D tiles (kTileW x kTileH pixels) and their count per image row
+    int tiles_per_img;                  // ceil(P / 128), or tiles_x * ceil(Ho / kTileH)
     int n_ptiles;                       // B * tiles_per_img
     int total_tiles;                    // groups * n_tiles_n * n_ptiles
     int tile_start;                     // first tile index of this problem in the batch's tile list
@@ -190,8 +196,27 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvParams *pr, int n, int
     const int pt = lt % p.n_ptiles, gn = lt / p.n_ptiles;
     c.grp = gn / p.n_tiles_n; c.nt = gn % p.n_tiles_n;
     c.b = pt / p.tiles_per_img;
-    c.p0 = (pt % p.tiles_per_img) * kUM;
+    c.p0 = pt % p.tiles_per_img;          // tile index inside the image
     return c;
+}
+
+// Output pixel of row r (0..127) of tile `ti` of an image: 1-D tiles are 128 consecutive pixels (contiguous
+// channels-last input/output: best for 1x1 convolutions), 2-D tiles are 16 x 8 patches whose gather footprint
+// over all taps fits L1.  Out-of-range rows are clamped to a valid pixel and flagged.
+__device__ __forceinline__ void tile_row(const ConvParams &p, int ti, int r, int &oh, int &ow, bool &ok) {
+    if (p.tile2d) {
+        const int ty = ti / p.tiles_x, tx = ti - ty * p.tiles_x;
+        oh = ty * kTileH + (r >> 4);
+        ow = tx * kTileW + (r & 15);
+        ok = oh < p.d.Ho && ow < p.d.Wo;
+        oh = min(oh, p.d.Ho - 1); ow = min(ow, p.d.Wo - 1);
+    } else {
+        const int px = ti * kUM + r, P32 = (int)p.d.P;
+        ok = px < P32;
+        const int pc = ok ? px : P32 - 1;
+        oh = pc / p.d.Wo;
+        ow = pc - oh * p.d.Wo;
+    }
 }
 
 // MULTI = false: one problem, its descriptor stays in the constant bank (operands come straight from c[][]);
@@ -314,12 +339,7 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
         bool my_ok = false;
 
         auto enter_tile = [&](const ConvParams &p) {   // coordinates of the row this lane owns
-            const int P32 = (int)p.d.P;
-            const int px = tc.p0 + row0 + j;
-            my_ok = px < P32;
-            const int pc = my_ok ? px : P32 - 1;
-            my_oh = pc / p.d.Wo;
-            my_ow = pc - my_oh * p.d.Wo;
+            tile_row(p, tc.p0, row0 + j, my_oh, my_ow, my_ok);
         };
         auto produce = [&](const ConvParams &p) {
             const MdcnDims &d = p.d;
@@ -395,10 +415,10 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
                     v[2] = w4[0] * q[0].z + w4[1] * q[1].z + w4[2] * q[2].z + w4[3] * q[3].z;
                     v[3] = w4[0] * q[0].w + w4[1] * q[1].w + w4[2] * q[2].w + w4[3] * q[3].w;
                 };
-                int ri[2][4];
-                float rw[2][4];
-                float4 q[2][4];
-                bool waited = false;
+                constexpr int kPf = 3;             // rows of gathers in flight per lane
+                int ri[kPf][4];
+                float rw[kPf][4];
+                float4 q[kPf][4];
                 if (info & 16) {
                     // shared path: this lane samples ITS row once per run (at most 2 runs per K block) ...
                     int ia[4], ib[4];
@@ -422,22 +442,26 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
                             }
                         }
                     };
-                    fetch(0, ri[0], rw[0]);
-                    gather(ri[0], q[0]);
+#pragma unroll
+                    for (int u = 0; u < kPf - 1; ++u) { fetch(u, ri[u], rw[u]); gather(ri[u], q[u]); }
+                    PROF_ADD(1);
+                    umma::mbar_wait_sleep(&bar_empty[s], ph ^ 1);      // the first gathers are already in flight
+                    PROF_ADD(2);
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const int cur = u & 1, nxt = cur ^ 1;
-                        if (u + 1 < 8) { fetch(u + 1, ri[nxt], rw[nxt]); gather(ri[nxt], q[nxt]); }
+                        const int cur = u % kPf, nxt = (u + kPf - 1) % kPf;
+                        if (u + kPf - 1 < 8) { fetch(u + kPf - 1, ri[nxt], rw[nxt]); gather(ri[nxt], q[nxt]); }
                         float v[4];
-                        combine(rw[cur], q[cur], v);
-                        if (!k_ok) { v[0] = 0.f; v[1] = 0.f; v[2] = 0.f; v[3] = 0.f; }     // K padding
-                        if (!waited) { PROF_ADD(1); umma::mbar_wait_sleep(&bar_empty[s], ph ^ 1); PROF_ADD(2); waited = true; }
+                        combine(rw[cur], q[cur], v);       // K-padding chunks need no zeroing: their weights are 0
                         store_row(u, v);
                     }
                 } else {
                     // general path (more than two (tap, group) runs in the block: tiny channel counts): every
                     // lane samples every row for its own chunk
                     const int my_pack = (my_oh << 16) | my_ow | (my_ok ? (int)0x80000000 : 0);
+                    PROF_ADD(1);
+                    umma::mbar_wait_sleep(&bar_empty[s], ph ^ 1);
+                    PROF_ADD(2);
 #pragma unroll 1
                     for (int u = 0; u < 8; ++u) {
                         const int pk = __shfl_sync(0xffffffffu, my_pack, lane_base + u);
@@ -445,7 +469,6 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
                         gather(ri[0], q[0]);
                         float v[4];
                         combine(rw[0], q[0], v);
-                        if (!waited) { PROF_ADD(1); umma::mbar_wait_sleep(&bar_empty[s], ph ^ 1); PROF_ADD(2); waited = true; }
                         store_row(u, v);
                     }
                 }
@@ -480,8 +503,10 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
         auto epilogue = [&](const ConvParams &p) {
             const MdcnDims &d = p.d;
             const int a = ti & 1;
-            const int pix = tc.p0 + row;
-            const bool p_ok = pix < (int)d.P;
+            int e_oh, e_ow;
+            bool p_ok;
+            tile_row(p, tc.p0, row, e_oh, e_ow, p_ok);
+            const int pix = e_oh * d.Wo + e_ow;
             const int o_base = tc.grp * d.Og + tc.nt * BN;          // first global out channel of the tile
             const int n_valid = min(BN, d.Og - tc.nt * BN);
             if ((tc.pi << 20) + tc.grp * p.n_tiles_n + tc.nt != cur_gn) {
@@ -755,7 +780,9 @@ int conv_umma_launch_batch(const ConvParams *probs, int n, bool deform, int bn, 
         p.n_tiles_n = ceil_div(d.Og, BN);
         p.K = d.K * d.Cg;
         p.KB = ceil_div(p.K, kUK);
-        p.tiles_per_img = (int)ceil_div_ll(d.P, kUM);
+        p.tile2d = d.K > 1 ? 1 : 0;
+        p.tiles_x = ceil_div(d.Wo, kTileW);
+        p.tiles_per_img = p.tile2d ? p.tiles_x * ceil_div(d.Ho, kTileH) : (int)ceil_div_ll(d.P, kUM);
         p.n_ptiles = d.B * p.tiles_per_img;
         const long total = (long)d.groups * p.n_tiles_n * p.n_ptiles;
         if (tiles + total > 0x3fffffffLL) return AANET_ERR_UNSUPPORTED;

@@ -27,7 +27,7 @@ struct ConvParams {
     const float *residual;
     int act; float slope; int n_offset_ch; float mask_scale;
     MdcnDims d;
-    int K, KB, n_tiles_n, tiles_per_img, n_ptiles, total_tiles, tile_start, tbl_off;
+    int K, KB, n_tiles_n, tile2d, tiles_x, tiles_per_img, n_ptiles, total_tiles, tile_start, tbl_off;
 };
 bool conv_umma_supported(const MdcnDims &d, bool deform);
 size_t conv_umma_wpack_bytes(const MdcnDims &d, int bn);
