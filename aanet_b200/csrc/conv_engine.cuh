@@ -1,0 +1,50 @@
+// Descriptor types and host entry points of the tcgen05 convolution engine (conv_umma.cu), shared with the
+// C-ABI layer (mdcn_api.cu).
+#pragma once
+#include "mdcn_common.cuh"
+
+namespace aanet {
+
+enum ConvAct { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_OFFSET_MASK = 3 };
+
+constexpr int kMaxProblems = 3;   // == AANET_CONV_MAX_BATCH
+
+// One convolution problem.  A launch (ConvBatch) walks the tiles of up to kMaxProblems problems of the same
+// kind (all DENSE or all DEFORM, same N-tile width): the three pyramid scales of one aggregation stage.
+struct ConvParams {
+    const float *x;                     // channels-last input [B][H*W][Cin]
+    const float *offset, *mask;         // DEFORM only; mask may be NULL (DCNv1)
+    long off_bs, off_ps, off_cs;        // offset strides in floats: batch, pixel, channel
+    long mask_bs, mask_ps, mask_cs;
+    const float *wpack;                 // packed weights, see conv_pack_weights_kernel
+    float *out;                         // [B][P][Cout] (out_nchw == 0) or [B][Cout][P]
+    int out_nchw;
+    const float *bias, *scale, *shift;  // per output channel, optional
+    const float *residual;              // same layout as out, optional
+    int act; float slope; int n_offset_ch; float mask_scale;
+    MdcnDims d;
+    int K, KB;                          // K = kh*kw*Cg, KB = ceil(K / 32)
+    int n_tiles_n;                      // ceil(Og / BN)
+    int tile2d, tiles_x;                // 2-D tiles (kTileW x kTileH pixels) and their count per image row
+    int tiles_per_img;                  // ceil(P / 128), or tiles_x * ceil(Ho / kTileH)
+    int n_ptiles;                       // B * tiles_per_img
+    int total_tiles;                    // groups * n_tiles_n * n_ptiles
+    int tile_start;                     // first tile index of this problem in the batch's tile list
+    int tbl_off;                        // first K-block row of this problem in the chunk tables
+};
+
+struct ConvBatch {
+    ConvParams pr[kMaxProblems];
+    int n;
+    int total_tiles;
+};
+
+bool conv_umma_supported(const MdcnDims &d, bool deform);
+int conv_umma_pick_bn(int Og);
+size_t conv_umma_wpack_bytes(const MdcnDims &d, int bn);
+int conv_umma_pack(const float *weight, void *wpack, const MdcnDims &d, int bn, cudaStream_t stream);
+int conv_umma_transpose(const float *src, float *dst, int B, int R, long Cc, cudaStream_t stream);
+int conv_umma_launch(ConvParams p, bool deform, cudaStream_t stream);
+int conv_umma_launch_batch(const ConvParams *probs, int n, bool deform, int bn, cudaStream_t stream);
+
+}  // namespace aanet

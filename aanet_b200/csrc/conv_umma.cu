@@ -38,7 +38,7 @@
 // carve-out at 164 KB, i.e. ~90 KB of L1 for the gathers; multi-tap convolutions use 16 x 8 pixel tiles so
 // that a tile's footprint over all taps fits it (1-D 128-pixel tiles + 206 KB of smem gave a 13 % L1 hit rate
 // and 579 MB of L2->L1 traffic per 1/3-scale deformable conv).
-#include "mdcn_common.cuh"
+#include "conv_engine.cuh"
 #include "umma.cuh"
 
 namespace aanet {
@@ -56,40 +56,6 @@ constexpr int kATileBytes = kUM * kUK * 4;   // 16 KB (hi); same for lo
 constexpr int kSmemBudget = 150 * 1024;   // dynamic (3 stages x <= 48 KB); ~9 KB of static tables on top.  Staying
                                           // under the 164 KB carve-out leaves ~90 KB of L1 for the gathers.
 constexpr int kMaxKB = 256;               // K <= 8192
-
-enum ConvAct { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_OFFSET_MASK = 3 };
-
-constexpr int kMaxProblems = 3;
-
-// One convolution problem.  A launch (ConvBatch) walks the tiles of up to kMaxProblems problems of the same
-// kind (all DENSE or all DEFORM, same N-tile width): the three pyramid scales of one aggregation stage.
-struct ConvParams {
-    const float *x;                     // channels-last input [B][H*W][Cin]
-    const float *offset, *mask;         // DEFORM only; mask may be NULL (DCNv1)
-    long off_bs, off_ps, off_cs;        // offset strides in floats: batch, pixel, channel
-    long mask_bs, mask_ps, mask_cs;
-    const float *wpack;                 // packed weights, see conv_pack_weights_kernel
-    float *out;                         // [B][P][Cout] (out_nchw == 0) or [B][Cout][P]
-    int out_nchw;
-    const float *bias, *scale, *shift;  // per output channel, optional
-    const float *residual;              // same layout as out, optional
-    int act; float slope; int n_offset_ch; float mask_scale;
-    MdcnDims d;
-    int K, KB;                          // K = kh*kw*Cg, KB = ceil(K / 32)
-    int n_tiles_n;                      // ceil(Og / BN)
-    int tile2d, tiles_x;                // 2-D tiles (kTileW x kTileH pixels) and their count per image row
-    int tiles_per_img;                  // ceil(P / 128), or tiles_x * ceil(Ho / kTileH)
-    int n_ptiles;                       // B * tiles_per_img
-    int total_tiles;                    // groups * n_tiles_n * n_ptiles
-    int tile_start;                     // first tile index of this problem in the batch's tile list
-    int tbl_off;                        // first K-block row of this problem in the chunk tables
-};
-
-struct ConvBatch {
-    ConvParams pr[kMaxProblems];
-    int n;
-    int total_tiles;
-};
 
 #ifdef AANET_PROFILE
 // Profile build only (-DAANET_PROFILE): per-CTA cycle counters of where each role waits.

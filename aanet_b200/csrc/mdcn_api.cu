@@ -1,7 +1,7 @@
 // C-ABI entry points of the convolution engine and the modulated deformable convolution
 // (include/aanet_b200.h): reference-shaped NCHW calls and the channels-last calls the fused inference
 // path uses.
-#include "mdcn_common.cuh"
+#include "conv_engine.cuh"
 
 namespace aanet {
 // mdcn_fwd.cu / mdcn_bwd.cu
@@ -12,29 +12,6 @@ size_t mdcn_bwd_workspace_bytes(const MdcnDims &d);
 int mdcn_bwd_launch(const float *x, const float *offset, const float *mask, const float *weight,
                     const float *gout, float *gx, float *goffset, float *gmask, float *gweight,
                     float *gbias, const MdcnDims &d, void *ws, size_t ws_bytes, cudaStream_t stream);
-
-// conv_umma.cu (keep in sync)
-enum ConvAct { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_OFFSET_MASK = 3 };
-struct ConvParams {
-    const float *x;
-    const float *offset, *mask;
-    long off_bs, off_ps, off_cs;
-    long mask_bs, mask_ps, mask_cs;
-    const float *wpack;
-    float *out;
-    int out_nchw;
-    const float *bias, *scale, *shift;
-    const float *residual;
-    int act; float slope; int n_offset_ch; float mask_scale;
-    MdcnDims d;
-    int K, KB, n_tiles_n, tile2d, tiles_x, tiles_per_img, n_ptiles, total_tiles, tile_start, tbl_off;
-};
-bool conv_umma_supported(const MdcnDims &d, bool deform);
-size_t conv_umma_wpack_bytes(const MdcnDims &d, int bn);
-int conv_umma_pack(const float *weight, void *wpack, const MdcnDims &d, int bn, cudaStream_t stream);
-int conv_umma_transpose(const float *src, float *dst, int B, int R, long Cc, cudaStream_t stream);
-int conv_umma_launch(ConvParams p, bool deform, cudaStream_t stream);
-int conv_umma_launch_batch(const ConvParams *probs, int n, bool deform, int bn, cudaStream_t stream);
 
 static inline size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 static inline size_t nhwc_bytes(const MdcnDims &d) { return (size_t)d.B * d.Cin * d.HW * sizeof(float); }
