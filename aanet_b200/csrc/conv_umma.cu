@@ -304,8 +304,17 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
         int my_oh = 0, my_ow = 0;
         bool my_ok = false;
 
-        auto enter_tile = [&](const ConvParams &p) {   // coordinates of the row this lane owns
-            tile_row(p, tc.p0, row0 + j, my_oh, my_ow, my_ok);
+        int g_oh = 0, g_ow0 = 0;                       // DENSE: first of the 8 consecutive pixels this thread copies
+        auto enter_tile = [&](const ConvParams &p) {
+            if (DEFORM) {                              // coordinates of the row this lane owns
+                tile_row(p, tc.p0, row0 + j, my_oh, my_ow, my_ok);
+            } else if (p.tile2d) {                     // rows row0..row0+7 = 8 consecutive pixels of one tile row
+                const int ty = tc.p0 / p.tiles_x, tx = tc.p0 - ty * p.tiles_x;
+                g_oh = ty * kTileH + (row0 >> 4);
+                g_ow0 = tx * kTileW + (row0 & 15);
+            } else {                                   // 1-D tile of a 1x1 / stride 1 / pad 0 conv: pixel index
+                g_ow0 = tc.p0 * kUM + row0;
+            }
         };
         auto produce = [&](const ConvParams &p) {
             const MdcnDims &d = p.d;
@@ -329,18 +338,30 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
             };
 
             if (!DEFORM) {
+                // The 8 rows of this thread are 8 consecutive output pixels of one image row (2-D tiles) or 8
+                // consecutive pixels of a 1x1 convolution (1-D tiles), so their input addresses are one base
+                // plus a constant step: one address computation per K block instead of eight, no shuffles.
                 const int ki = (e >> 16) & 15, kj = (e >> 20) & 15;
-                // owner lanes publish (oh, ow, valid) of their row; every lane gathers its chunk of all 8 rows
-                const int my_pack = (my_oh << 16) | my_ow | (my_ok ? (int)0x80000000 : 0);
+                const float *base;
+                int step, w0, wlim;
+                bool row_ok;
+                if (p.tile2d) {
+                    const int hi_ = g_oh * d.stride - d.pad + ki * d.dil;
+                    w0 = g_ow0 * d.stride - d.pad + kj * d.dil;
+                    row_ok = k_ok && (unsigned)hi_ < (unsigned)d.H;
+                    base = x_b + ((long)hi_ * d.W + w0) * d.Cin;
+                    step = d.stride; wlim = d.W;
+                } else {
+                    w0 = g_ow0; row_ok = k_ok; step = 1; wlim = (int)d.P;
+                    base = x_b + (long)g_ow0 * d.Cin;
+                }
+                const int estep = step * d.Cin;
                 float4 q[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int pk = __shfl_sync(0xffffffffu, my_pack, lane_base + u);
-                    const int hi_ = ((pk >> 16) & 0x7fff) * d.stride - d.pad + ki * d.dil;
-                    const int wi_ = (pk & 0xffff) * d.stride - d.pad + kj * d.dil;
-                    const bool ok = k_ok && pk < 0 && hi_ >= 0 && hi_ < d.H && wi_ >= 0 && wi_ < d.W;
+                    const bool ok = row_ok && (unsigned)(w0 + u * step) < (unsigned)wlim;
                     q[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok) q[u] = __ldg(reinterpret_cast<const float4 *>(x_b + ((long)hi_ * d.W + wi_) * d.Cin));
+                    if (ok) q[u] = __ldg(reinterpret_cast<const float4 *>(base + u * estep));
                 }
                 PROF_ADD(1);
                 umma::mbar_wait_sleep(&bar_empty[s], ph ^ 1);
@@ -746,7 +767,8 @@ int conv_umma_launch_batch(const ConvParams *probs, int n, bool deform, int bn, 
         p.n_tiles_n = ceil_div(d.Og, BN);
         p.K = d.K * d.Cg;
         p.KB = ceil_div(p.K, kUK);
-        p.tile2d = d.K > 1 ? 1 : 0;
+        // 1-D tiles (128 consecutive pixels) only where input pixel == output pixel
+        p.tile2d = (d.K > 1 || d.stride != 1 || d.pad != 0) ? 1 : 0;
         p.tiles_x = ceil_div(d.Wo, kTileW);
         p.tiles_per_img = p.tile2d ? p.tiles_x * ceil_div(d.Ho, kTileH) : (int)ceil_div_ll(d.P, kUM);
         p.n_ptiles = d.B * p.tiles_per_img;
