@@ -173,5 +173,10 @@ t1 = [rnd(1, 64, 64, 208) for _ in range(n)]
 t2 = [rnd(1, 64, 32, 104) for _ in range(n)]
 report("CSA fuse out0 (x0 + up2 + up4)", timeit(lambda i: ops.csa_fuse([t0[i], t1[i], t2[i]], 0.2), n),
        4.0 * 64 * (2 * 128 * 416 + 64 * 208 + 32 * 104) / 1e6)
+h0 = [rnd(1, 128, 416, 64) for _ in range(n)]
+h1 = [rnd(1, 64, 208, 64) for _ in range(n)]
+h2 = [rnd(1, 32, 104, 64) for _ in range(n)]
+report("CSA fuse out0, channels-last (tiled)", timeit(lambda i: ops.csa_fuse_nhwc([h0[i], h1[i], h2[i]], 0.2), n),
+       4.0 * 64 * (2 * 128 * 416 + 64 * 208 + 32 * 104) / 1e6)
 if "--json" in sys.argv:
     print(json.dumps(results))

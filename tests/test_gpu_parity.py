@@ -360,9 +360,19 @@ def test_conv_batch_three_problems(ops):
         assert rel_err(npy(o.permute(0, 3, 1, 2)), r) < VOL_TOL
 
 
-def test_csa_fuse_nhwc(ops):
+@pytest.mark.parametrize("cfg", [
+    ((2, 8, 31, 45), [(31, 45), (16, 23), (8, 12)]),          # odd ratios, partial tiles
+    ((1, 64, 128, 416), [(128, 416), (64, 208), (32, 104)]),  # out0 of config 2: exact 2x / 4x
+    ((1, 32, 64, 208), [(64, 208), (64, 208), (32, 104)]),    # out1
+    ((1, 16, 32, 104), [(32, 104), (32, 104), (32, 104)]),    # out2: same-size terms only
+    ((2, 12, 9, 70), [(9, 70), (3, 11)]),                     # C/4 not a power of two, two terms
+    ((1, 4, 5, 7), [(5, 7), (1, 1)]),                         # single-pixel source
+    ((1, 8, 6, 10), [(6, 10), (12, 20)]),                     # downsampling term -> per-pixel kernel
+    ((1, 640, 8, 40), [(8, 40), (4, 20), (2, 10)]),           # patches exceed the smem budget -> per-pixel kernel
+])
+def test_csa_fuse_nhwc(ops, cfg):
     rng = np.random.default_rng(4)
-    (B, C, H, W), ths = (2, 8, 31, 45), [(31, 45), (16, 23), (8, 12)]
+    (B, C, H, W), ths = cfg
     terms = [rng.standard_normal((B, C, h, w)).astype(np.float32) for h, w in ths]
     out = ops.csa_fuse_nhwc([ops.nchw_to_nhwc(cu(t)) for t in terms], 0.2)
     assert rel_err(npy(out.permute(0, 3, 1, 2)), orc.csa_fuse_fwd(terms, (H, W), 0.2)) < 1e-5
