@@ -46,7 +46,10 @@ def test_corr_golden(ops, golden, tag):
 
 
 @pytest.mark.parametrize("shape", [(1, 32, 6, 200, 64), (2, 16, 3, 131, 96), (1, 8, 4, 30, 48),
-                                   (1, 128, 2, 416, 64), (3, 5, 1, 257, 7)])
+                                   (1, 128, 2, 416, 64), (3, 5, 1, 257, 7),
+                                   (1, 128, 3, 208, 32), (1, 128, 2, 104, 16), (1, 64, 2, 300, 128),   # tcgen05 widths
+                                   (1, 33, 2, 140, 20), (2, 8, 2, 100, 100),
+                                   (1, 16, 2, 300, 144), (1, 6, 3, 203, 130)])                        # D > 128: FFMA kernels
 def test_corr_oracle(ops, shape):
     B, C, H, W, D = shape
     rng = np.random.default_rng(326)
