@@ -38,6 +38,7 @@
 // carve-out at 164 KB, i.e. ~90 KB of L1 for the gathers; multi-tap convolutions use 16 x 8 pixel tiles so
 // that a tile's footprint over all taps fits it (1-D 128-pixel tiles + 206 KB of smem gave a 13 % L1 hit rate
 // and 579 MB of L2->L1 traffic per 1/3-scale deformable conv).
+#include <cstdlib>
 #include "conv_engine.cuh"
 #include "umma.cuh"
 
@@ -273,6 +274,10 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
     __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem_base = s_tmem;
+    // Everything above (barriers, TMEM, chunk tables) only reads kernel parameters: with programmatic dependent
+    // launch it overlaps the tail of the previous kernel of the stream.  Global memory is touched from here on.
+    umma::pdl_wait();
+    bool triggered = false;
 
     if (warp < kProdWarps) {
         // ================================ A producers ===========================================
@@ -594,6 +599,10 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
             PROF_ADD(4);                                   // slot 4: epilogue work
         };
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+            if (t + (int)gridDim.x >= total_tiles) {     // last tile: the next kernel's launch + prologue overlap
+                umma::pdl_trigger();                     // this CTA's last epilogue
+                triggered = true;
+            }
             tc = tile_coord(prob, n_prob, t);
             epilogue(MULTI ? prob[tc.pi] : B.pr[0]);
         }
@@ -670,6 +679,7 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
             PROF_FLUSH(0); PROF_FLUSH(7); PROF_FLUSH(8); PROF_FLUSH(9); PROF_FLUSH(10); PROF_FLUSH(11);
         }
     }
+    if (!triggered) umma::pdl_trigger();
     umma::tc_fence_before();
     __syncthreads();
     if (warp == kMmaWarp) {
@@ -734,7 +744,16 @@ static int launch_inst(const ConvBatch &batch, cudaStream_t stream) {
     // kernels that the fused executor issues on parallel streams.
     const int rounds = ceil_div(batch.total_tiles, kNumSMs);
     const int grid = ceil_div(batch.total_tiles, rounds);
-    conv_umma_kernel<BN, DEFORM, MULTI><<<grid, kUThreads, smem, stream>>>(batch);
+    // Programmatic dependent launch: consecutive engine kernels of a stream overlap launch latency and prologue
+    // with the predecessor's last epilogue (see pdl_wait / pdl_trigger in the kernel).  AANET_NO_PDL=1 disables it.
+    static const bool pdl = getenv("AANET_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kUThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    if (cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, DEFORM, MULTI>, batch) != cudaSuccess) return check_launch();
     return check_launch();
 }
 
