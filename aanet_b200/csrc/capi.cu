@@ -1,4 +1,5 @@
 // Status strings / version for the C-ABI (include/aanet_b200.h).
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -7,6 +8,10 @@ static thread_local char g_last_err[256] = "";
 void set_last_cuda_error(const char *msg) {
     strncpy(g_last_err, msg ? msg : "", sizeof(g_last_err) - 1);
     g_last_err[sizeof(g_last_err) - 1] = 0;
+}
+bool pdl_enabled() {
+    static const bool on = getenv("AANET_NO_PDL") == nullptr;
+    return on;
 }
 }  // namespace aanet
 

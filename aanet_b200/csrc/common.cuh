@@ -23,6 +23,25 @@ inline int check_launch() {
 
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Programmatic dependent launch.  A kernel launched through launch_pdl may be scheduled while the previous
+// kernel of the stream is still running (after that kernel's CTAs have all called pdl_trigger() or exited); it
+// must call pdl_wait() before touching global memory.  AANET_NO_PDL=1 turns the attribute off.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    return check_launch();
+}
+
 template <typename T>
 __host__ __device__ inline bool aligned16(const T *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

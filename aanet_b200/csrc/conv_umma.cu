@@ -38,7 +38,6 @@
 // carve-out at 164 KB, i.e. ~90 KB of L1 for the gathers; multi-tap convolutions use 16 x 8 pixel tiles so
 // that a tile's footprint over all taps fits it (1-D 128-pixel tiles + 206 KB of smem gave a 13 % L1 hit rate
 // and 579 MB of L2->L1 traffic per 1/3-scale deformable conv).
-#include <cstdlib>
 #include "conv_engine.cuh"
 #include "umma.cuh"
 
@@ -124,6 +123,8 @@ __global__ void conv_pack_weights_kernel(const float *__restrict__ w, float *__r
 __global__ void __launch_bounds__(256)
 transpose_kernel(const float *__restrict__ src, float *__restrict__ dst, int R, long Cc) {
     __shared__ float tile[32][33];
+    pdl_wait();
+    pdl_trigger();
     const long c0 = (long)blockIdx.x * 32;
     const int r0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
@@ -276,7 +277,7 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
     const uint32_t tmem_base = s_tmem;
     // Everything above (barriers, TMEM, chunk tables) only reads kernel parameters: with programmatic dependent
     // launch it overlaps the tail of the previous kernel of the stream.  Global memory is touched from here on.
-    umma::pdl_wait();
+    pdl_wait();
     bool triggered = false;
 
     if (warp < kProdWarps) {
@@ -600,7 +601,7 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
         };
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
             if (t + (int)gridDim.x >= total_tiles) {     // last tile: the next kernel's launch + prologue overlap
-                umma::pdl_trigger();                     // this CTA's last epilogue
+                pdl_trigger();                     // this CTA's last epilogue
                 triggered = true;
             }
             tc = tile_coord(prob, n_prob, t);
@@ -679,7 +680,7 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
             PROF_FLUSH(0); PROF_FLUSH(7); PROF_FLUSH(8); PROF_FLUSH(9); PROF_FLUSH(10); PROF_FLUSH(11);
         }
     }
-    if (!triggered) umma::pdl_trigger();
+    if (!triggered) pdl_trigger();
     umma::tc_fence_before();
     __syncthreads();
     if (warp == kMmaWarp) {
@@ -731,8 +732,7 @@ int conv_umma_pack(const float *weight, void *wpack, const MdcnDims &d, int bn, 
 // [B][R][Cc] -> [B][Cc][R]
 int conv_umma_transpose(const float *src, float *dst, int B, int R, long Cc, cudaStream_t stream) {
     const dim3 grid((unsigned)ceil_div_ll(Cc, 32), ceil_div(R, 32), B);
-    transpose_kernel<<<grid, 256, 0, stream>>>(src, dst, R, Cc);
-    return check_launch();
+    return launch_pdl(transpose_kernel, grid, dim3(256), 0, stream, src, dst, R, Cc);
 }
 
 template <int BN, bool DEFORM, bool MULTI>
@@ -745,16 +745,8 @@ static int launch_inst(const ConvBatch &batch, cudaStream_t stream) {
     const int rounds = ceil_div(batch.total_tiles, kNumSMs);
     const int grid = ceil_div(batch.total_tiles, rounds);
     // Programmatic dependent launch: consecutive engine kernels of a stream overlap launch latency and prologue
-    // with the predecessor's last epilogue (see pdl_wait / pdl_trigger in the kernel).  AANET_NO_PDL=1 disables it.
-    static const bool pdl = getenv("AANET_NO_PDL") == nullptr;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kUThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    if (cudaLaunchKernelEx(&cfg, conv_umma_kernel<BN, DEFORM, MULTI>, batch) != cudaSuccess) return check_launch();
-    return check_launch();
+    // with the predecessor's last epilogue (see pdl_wait / pdl_trigger in the kernel).
+    return launch_pdl(conv_umma_kernel<BN, DEFORM, MULTI>, dim3(grid), dim3(kUThreads), smem, stream, batch);
 }
 
 template <int BN, bool DEFORM>

@@ -178,6 +178,8 @@ csa_fuse_tiled_kernel(CsaTerms t, CsaTile g, float *__restrict__ out, int H, int
     const int h0 = ty * kFuseTH, w0 = tx * kFuseTW;
     const int nh = min(kFuseTH, H - h0), nw = min(kFuseTW, W - w0);
     const int tid = threadIdx.x;
+    pdl_wait();          // launched with programmatic stream serialization: the exchange convs may still be running
+    pdl_trigger();       // the next kernel of the stream may be scheduled as soon as SMs free up
 
     // 1. tables (one thread per row / column entry and term)
 #pragma unroll
@@ -376,8 +378,8 @@ extern "C" int aanet_csa_fuse_nhwc(const float *const *terms, const int *th, con
         const size_t smem = (size_t)smem_v * 16;
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(csa_fuse_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        csa_fuse_tiled_kernel<<<B * g.tiles_x * g.tiles_y, kFuseThreads, smem, as_stream(stream)>>>(t, g, out, H, W, C, slope);
-        return check_launch();
+        return launch_pdl(csa_fuse_tiled_kernel, dim3(B * g.tiles_x * g.tiles_y), dim3(kFuseThreads), smem,
+                          as_stream(stream), t, g, out, H, W, C, slope);
     }
     const int tpp = ceil_div(C / 4, kCsaChunks);
     const long n = (long)B * H * W * tpp;

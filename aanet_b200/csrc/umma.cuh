@@ -92,14 +92,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  : "memory");
 }
 
-// Programmatic dependent launch (launch attribute programmaticStreamSerialization): a kernel launched with it
-// may start while its predecessor in the stream is still running; it must not touch global memory before
-// pdl_wait() (returns when the predecessor grids have completed and their writes are visible).
-// pdl_trigger() lets the NEXT kernel of the stream be scheduled once every CTA of this grid has called it or
-// exited.  Both are no-ops for a kernel launched without the attribute.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
 // ---------------------------------------------------------------------------------- TMEM
 template <uint32_t COLS>   // power of two >= 32; executed by one full warp
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem) {
