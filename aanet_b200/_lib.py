@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libaanet_b200.so")
+# AANET_B200_LIB: load another build of the same library (A/B timing of kernel variants in one process tree)
+LIB_PATH = os.environ.get("AANET_B200_LIB") or os.path.join(_HERE, "lib", "libaanet_b200.so")
 ABI_VERSION = 1
 
 _vp, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
