@@ -204,3 +204,32 @@ def test_training_step_runs():
     assert all(torch.isfinite(l.grad).all() for l in Ls)
     g = agg.fusions[3].branches[0][0].conv2.offset_conv.weight.grad
     assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0
+
+
+def test_host_pipeline_matches_direct_forward():
+    """HostPipeline (pinned host buffers in, pinned disparity out, graph replay on two slots) returns what a
+    direct forward of the same HotPath returns -- through the one-DMA staging block and through per-tensor
+    copies, with the slots reused several times and a different pair in every submission."""
+    from aanet_b200.pipeline import HostPipeline, HotPath
+    torch.manual_seed(326)
+    dev = torch.device("cuda:0")
+    hp = HotPath(96, num_deform_blocks=3, intermediate_supervision=False).to(dev).eval()
+    shapes = [(1, 32, 24 >> s, 48 >> s) for s in range(3)]
+    pairs = [([torch.relu(torch.randn(s)) for s in shapes], [torch.relu(torch.randn(s)) for s in shapes])
+             for _ in range(5)]
+    with torch.no_grad():
+        want = [hp([t.to(dev) for t in L], [t.to(dev) for t in R])[-1].cpu() for L, R in pairs]
+    pipe = HostPipeline(hp, shapes, dev)
+    assert pipe.h2d_bytes == 2 * 4 * sum(int(np.prod(s)) for s in shapes)
+    got = []
+    for k, (L, R) in enumerate(pairs):
+        if k % 2 == 0:                         # contiguous staging block, one copy
+            hL, hR = pipe.staging()
+            for dst, src in zip(hL + hR, L + R):
+                dst.copy_(src)
+            slot = pipe.submit()
+        else:                                  # caller-owned pinned tensors, one copy per tensor
+            slot = pipe.submit([t.pin_memory() for t in L], [t.pin_memory() for t in R])
+        got.append(HostPipeline.result(slot).clone())
+    for g, w in zip(got, want):
+        assert torch.equal(g, w)
