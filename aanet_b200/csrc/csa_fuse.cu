@@ -179,7 +179,6 @@ csa_fuse_tiled_kernel(CsaTerms t, CsaTile g, float *__restrict__ out, int H, int
     const int nh = min(kFuseTH, H - h0), nw = min(kFuseTW, W - w0);
     const int tid = threadIdx.x;
     pdl_wait();          // launched with programmatic stream serialization: the exchange convs may still be running
-    pdl_trigger();       // the next kernel of the stream may be scheduled as soon as SMs free up
 
     // 1. tables (one thread per row / column entry and term)
 #pragma unroll
@@ -262,6 +261,7 @@ csa_fuse_tiled_kernel(CsaTerms t, CsaTile g, float *__restrict__ out, int H, int
         acc.z = acc.z > 0.f ? acc.z : acc.z * slope; acc.w = acc.w > 0.f ? acc.w : acc.w * slope;
         reinterpret_cast<float4 *>(out)[opix * Cv + cv] = acc;
     }
+    pdl_trigger();       // the next kernel's launch latency overlaps this kernel's drain
 }
 
 // Backward, same-size term: g * LeakyReLU'(pre); sign(pre) == sign(out) because slope > 0.
