@@ -9,6 +9,8 @@ double-buffered host entry point (pinned H2D copy of the next pair overlapped wi
 """
 import contextlib
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -68,6 +70,30 @@ class HotPath(nn.Module):
         return graph, outs
 
 
+def bind_host_to_gpu_numa(device):
+    """Pin the calling process to the CPUs of the NUMA node the GPU hangs off (sysfs local_cpulist of its PCI
+    function), so that the pinned staging blocks allocated afterwards are node-local (on a two-socket host a
+    DMA from the remote socket crosses the inter-socket link).  Returns a short description, or None when the
+    topology is not visible (no sysfs, single-node hosts or VMs, restricted cpusets) -- then nothing changes."""
+    try:
+        pr = torch.cuda.get_device_properties(device)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        node = int(open(base + "/numa_node").read())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if node < 0 or not use or use == allowed:
+            return "numa node %d, affinity unchanged" % node
+        os.sched_setaffinity(0, use)
+        return "numa node %d, bound to %d of %d cpus" % (node, len(use), len(allowed))
+    except (OSError, ValueError, AttributeError):
+        return None
+
+
 class HostPipeline:
     """Host-buffer entry point: pinned feature pyramids in, pinned disparity out, H2D/D2H inside.
 
@@ -77,6 +103,7 @@ class HostPipeline:
 
     def __init__(self, hot_path, shapes, device, n_slots=2):
         self.hp, self.device, self.n = hot_path, device, n_slots
+        self.numa = bind_host_to_gpu_numa(device)          # before the pinned blocks are allocated
         self.copy_stream = torch.cuda.Stream(device)
         self.compute_stream = torch.cuda.Stream(device)
         self.slots = []

@@ -257,21 +257,28 @@ def run_gpu(args):
         hL, hR = pipe.slots[k]["host_L"], pipe.slots[k]["host_R"]
         for dst, src in zip(hL + hR, L + R):
             dst.copy_(src)
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, 4) + args.steps):     # the first pass over the pinned blocks is slow (564 vs 750)
         HostPipeline.result(pipe.submit())
-    barrier()
-    t0 = time.perf_counter()
-    pending = []
-    for i in range(args.steps):
-        pending.append(pipe.submit())
-        if len(pending) >= pipe.n:
-            HostPipeline.result(pending.pop(0))
-    for s in pending:
-        HostPipeline.result(s)
-    torch.cuda.synchronize(device)
-    e2e_s = max_over_ranks(time.perf_counter() - t0, device)
+    # K steps take only tens of milliseconds and the PCIe rate of a (virtualised) host wanders from run to run
+    # (670 .. 750 pairs/s seen back to back on one box), so the K-step measurement is repeated and the median kept.
+    e2e_runs = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        pending = []
+        for i in range(args.steps):
+            pending.append(pipe.submit())
+            if len(pending) >= pipe.n:
+                HostPipeline.result(pending.pop(0))
+        for s in pending:
+            HostPipeline.result(s)
+        torch.cuda.synchronize(device)
+        e2e_runs.append(max_over_ranks(time.perf_counter() - t0, device))
+    e2e_s = statistics.median(e2e_runs)
     e2e = {"value": world * B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
-           "d2h_bytes_per_step": pipe.d2h_bytes}
+           "d2h_bytes_per_step": pipe.d2h_bytes,
+           "h2d_gbs_per_gpu": B * args.steps / e2e_s * pipe.h2d_bytes / 1e9, "host_numa": pipe.numa,
+           "runs_pairs_per_s": [world * B * args.steps / t for t in e2e_runs], "stat": "median of 3 x K steps"}
 
     out = None
     if rank == 0:
