@@ -49,9 +49,15 @@ constexpr int kGroups = 3;               // producer groups; each fills one whol
 constexpr int kProdWarps = 4 * kGroups;  // A producers: kGroups groups of 4 warps
 constexpr int kTileW = 16, kTileH = 8;   // 2-D pixel tile (multi-tap convolutions): 128 = 16 x 8 output pixels
 constexpr int kMmaWarp = kProdWarps + 4, kLoadWarp = kProdWarps + 5;   // warps kProdWarps..+3: epilogue
-constexpr int kUThreads = (kProdWarps + 6) * 32;                        // 576 threads -> 112 registers each
-// (setmaxnreg rebalancing between the roles faulted on the B200 test box with "unspecified launch failure";
-// the producers fit in the uniform budget without spills.)
+// 20 warps = 5 complete warpgroups: 3 producer groups, the epilogue, and {MMA issuer, weight loader, 2 idle warps}.
+// Every SM sub-partition hosts 5 warps, so a uniform allocation stops at 96 registers per thread (16384 / 160) and
+// the DEFORM producers spilled 80-96 bytes.  setmaxnreg (warpgroup-collective, hence the two padding warps) moves
+// registers from the control warpgroup (96 -> 40) to the producers (96 -> 112); the epilogue keeps its 96.
+// What the B200 accepted: 3 x 112 + 96 + 40.  120 for the producers, or 72 for the epilogue / 32 for the control
+// warps, ended in "unspecified launch failure" (allocation is per sub-partition and, it seems, in units of 16
+// registers per thread; code that needs more than its decreased budget faults instead of spilling).
+constexpr int kUThreads = (kProdWarps + 8) * 32;                        // 640 threads
+constexpr int kRegsProducer = 112, kRegsControl = 40;
 constexpr int kATileBytes = kUM * kUK * 4;   // 16 KB (hi); same for lo
 constexpr int kSmemBudget = 150 * 1024;   // dynamic (3 stages x <= 48 KB); ~9 KB of static tables on top.  Staying
                                           // under the 164 KB carve-out leaves ~90 KB of L1 for the gathers.
@@ -279,6 +285,8 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
     // launch it overlaps the tail of the previous kernel of the stream.  Global memory is touched from here on.
     pdl_wait();
     bool triggered = false;
+    if (warp >= kMmaWarp) umma::setmaxnreg_dec<kRegsControl>();
+    else if (warp < kProdWarps) umma::setmaxnreg_inc<kRegsProducer>();
 
     if (warp < kProdWarps) {
         // ================================ A producers ===========================================
@@ -408,7 +416,7 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
                     v[2] = w4[0] * q[0].z + w4[1] * q[1].z + w4[2] * q[2].z + w4[3] * q[3].z;
                     v[3] = w4[0] * q[0].w + w4[1] * q[1].w + w4[2] * q[2].w + w4[3] * q[3].w;
                 };
-                constexpr int kPf = 3;             // rows of gathers in flight per lane
+                constexpr int kPf = 3;             // rows of gathers in flight per lane (4: 891 vs 913 pairs/s)
                 int ri[kPf][4];
                 float rw[kPf][4];
                 float4 q[kPf][4];
