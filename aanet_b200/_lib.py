@@ -24,6 +24,7 @@ SIGNATURES = {
     "aanet_corr_bwd": (_i, [_vp] * 5 + [_i] * 5 + [_vp]),
     "aanet_softargmin_fwd": (_i, [_vp, _vp] + [_i] * 5 + [_vp]),
     "aanet_softargmin_bwd": (_i, [_vp, _vp, _vp] + [_i] * 5 + [_vp]),
+    "aanet_refine_frontend_fwd": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),
     "aanet_mdcn_workspace_bytes": (_sz, [_i] * 13),
     "aanet_mdcn_fwd": (_i, [_vp] * 6 + [_i] * 12 + [_vp, _vp, _i, _vp, _sz, _vp]),
     "aanet_mdcn_bwd": (_i, [_vp] * 10 + [_i] * 12 + [_vp, _sz, _vp]),

@@ -41,6 +41,10 @@ def patch(ref_nets):
     aanet_mod.CostVolumePyramid = _nets.CostVolumePyramid
     aanet_mod.AdaptiveAggregation = _nets.AdaptiveAggregation
     aanet_mod.DisparityEstimation = _nets.DisparityEstimation
+    # refinement nets with the fused upsample/warp/error front end (aanet.py:9 imports them by name)
+    for attr in ("StereoDRNetRefinement", "HourglassRefinement"):
+        if hasattr(aanet_mod, attr):
+            setattr(aanet_mod, attr, getattr(_nets, attr))
     deform_mod = sys.modules.get(ref_nets.__name__ + ".deform")
     if deform_mod is not None:      # feature extractor / refinement build DeformConv2d from here
         deform_mod.DeformConv = _nets.DeformConv

@@ -6,8 +6,10 @@ from .deform import (DeformConv2d, DeformBottleneck, SimpleBottleneck, DeformSim
 from .deform_conv import (DeformConv, DeformConvPack, ModulatedDeformConv, ModulatedDeformConvPack,
                           deform_conv, modulated_deform_conv)
 from .aggregation import AdaptiveAggregationModule, AdaptiveAggregation
+from .refine import StereoDRNetRefinement, HourglassRefinement
 
 __all__ = ['CostVolume', 'CostVolumePyramid', 'DisparityEstimation', 'DeformConv2d', 'DeformBottleneck',
            'SimpleBottleneck', 'DeformSimpleBottleneck', 'conv1x1', 'conv3x3', 'DeformConv',
            'DeformConvPack', 'ModulatedDeformConv', 'ModulatedDeformConvPack', 'deform_conv',
-           'modulated_deform_conv', 'AdaptiveAggregationModule', 'AdaptiveAggregation']
+           'modulated_deform_conv', 'AdaptiveAggregationModule', 'AdaptiveAggregation',
+           'StereoDRNetRefinement', 'HourglassRefinement']

@@ -129,6 +129,25 @@ def soft_argmin(cost, similarity=True):
     return _SoftArgmin.apply(cost, bool(similarity))
 
 
+def refine_frontend(low_disp, left_img, right_img):
+    """(low_disp [B,h,w], left [B,C,H,W], right [B,C,H,W]) -> (cat(warped_right - left, left) [B,2C,H,W],
+    disp [B,1,H,W]): upsample + rescale + disp_warp + error + concat of refinement.py:80-95 / warp.py:41-64 in
+    one launch and without the reference's host synchronisation.  Inference only (no autograd)."""
+    low = _prep(low_disp, "refine_frontend")
+    left, right = _prep(left_img, "refine_frontend"), _prep(right_img, "refine_frontend")
+    if low.dim() != 3 or left.dim() != 4 or left.shape != right.shape or low.shape[0] != left.shape[0]:
+        raise ValueError("refine_frontend: low_disp [B,h,w], left/right [B,C,H,W] expected")
+    B, C, H, W = left.shape
+    concat = left.new_empty(B, 2 * C, H, W)
+    disp = left.new_empty(B, 1, H, W)
+    with torch.cuda.device(left.device):
+        _lib.check(_lib.load().aanet_refine_frontend_fwd(_ptr(low), _ptr(left), _ptr(right), _ptr(concat), _ptr(disp),
+                                                         B, C, low.shape[1], low.shape[2], H, W, _stream(left)),
+                   "aanet_refine_frontend_fwd")
+    _count()
+    return concat, disp
+
+
 # ------------------------------------------------------------------------------------ mdconv
 def _out_hw(H, W, kh, kw, stride, pad, dil):
     return ((H + 2 * pad - (dil * (kh - 1) + 1)) // stride + 1,

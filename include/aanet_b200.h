@@ -217,6 +217,18 @@ AANET_API int aanet_csa_fuse_bwd(const float *out, const float *gout, float *con
                        const int *th, const int *tw, int n_terms,
                        int B, int C, int H, int W, float slope, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Refinement front end (widening step).  Replaces the lines of
+ * StereoDRNetRefinement / HourglassRefinement.forward before the first convolution
+ * (nets/refinement.py:80-95, :144-160) and disp_warp (nets/warp.py:41-64):
+ *   disp   = bilinear(low_disp, (H,W), align_corners=False) * (W/w)    (low_disp itself when W == w)
+ *   concat = cat(grid_sample(right, (x - disp, y), bilinear, border, align_corners=True) - left, left)
+ * low_disp: [B,h,w]   left, right: [B,C,H,W]   concat: [B,2C,H,W]   disp: [B,1,H,W]   (all overwritten
+ * outputs; the reference's `assert disp.min() >= 0` device synchronisation (warp.py:51) is not performed).
+ * ------------------------------------------------------------------------------------------- */
+AANET_API int aanet_refine_frontend_fwd(const float *low_disp, const float *left, const float *right, float *concat,
+                                        float *disp, int B, int C, int h, int w, int H, int W, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -417,6 +417,67 @@ void FN(orc_csa_fuse_bwd)(const REAL *out, const REAL *gout, REAL *const *gterms
     }
 }
 
+/* ------------------------------------------------------------------ */
+/* Refinement front end.  nets/refinement.py:80-95 (= :144-160) and     */
+/* nets/warp.py:41-64:                                                   */
+/*   disp  = bilinear(low_disp, size=(H,W), align_corners=False) * (W/w) */
+/*           (low_disp itself when W == w, refinement.py:84-88)          */
+/*   grid  = (x - disp, y), normalised to [-1,1] as warp.py:12-13 does,  */
+/*           2*(g/(size-1)) - 1, and un-normalised again by grid_sample  */
+/*           (align_corners=True): ((g+1)/2)*(size-1) -- both in the     */
+/*           working precision, so the sampling position carries the     */
+/*           same rounding as the reference's                            */
+/*   warped = bilinear sample of right at grid, padding_mode='border'    */
+/*           (coordinates clipped to [0,size-1]; ATen grid_sampler_2d:   */
+/*           weights nw=(xse-x)(yse-y) ..., out-of-range corners skipped) */
+/*   concat = cat(warped - left, left)   [B,2C,H,W]                      */
+/* ------------------------------------------------------------------ */
+void FN(orc_refine_frontend_fwd)(const REAL *low, const REAL *left, const REAL *right, REAL *concat,
+                                 REAL *disp, int B, int C, int h, int w, int H, int W)
+{
+    const REAL scale = (REAL)((double)W / (double)w);
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int b = 0; b < B; ++b)
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                REAL d;
+                if (W == w) {
+                    d = low[((long)b * h + y) * w + x];
+                } else {
+                    const REAL *src = low + (long)b * h * w;
+                    int h0, h1, w0, w1; REAL a0, a1, b0, b1;
+                    FN(src_index)(y, h, H, &h0, &h1, &a0, &a1);
+                    FN(src_index)(x, w, W, &w0, &w1, &b0, &b1);
+                    d = a0 * (b0 * src[(long)h0 * w + w0] + b1 * src[(long)h0 * w + w1]) +
+                        a1 * (b0 * src[(long)h1 * w + w0] + b1 * src[(long)h1 * w + w1]);
+                    d = d * scale;
+                }
+                disp[((long)b * H + y) * W + x] = d;
+                REAL gx = (REAL)x - d, gy = (REAL)y;
+                gx = (REAL)2 * (gx / (REAL)(W - 1)) - (REAL)1;
+                gy = (REAL)2 * (gy / (REAL)(H - 1)) - (REAL)1;
+                REAL ix = ((gx + (REAL)1) / (REAL)2) * (REAL)(W - 1);
+                REAL iy = ((gy + (REAL)1) / (REAL)2) * (REAL)(H - 1);
+                ix = ix < 0 ? 0 : (ix > (REAL)(W - 1) ? (REAL)(W - 1) : ix);
+                iy = iy < 0 ? 0 : (iy > (REAL)(H - 1) ? (REAL)(H - 1) : iy);
+                const int xw = (int)floor((double)ix), yn = (int)floor((double)iy);
+                const REAL fxw = (REAL)xw, fyn = (REAL)yn;
+                const REAL nw = (fxw + 1 - ix) * (fyn + 1 - iy), ne = (ix - fxw) * (fyn + 1 - iy);
+                const REAL sw = (fxw + 1 - ix) * (iy - fyn), se = (ix - fxw) * (iy - fyn);
+                for (int c = 0; c < C; ++c) {
+                    const REAL *img = right + ((long)b * C + c) * H * W;
+                    REAL v = 0;
+                    if (yn >= 0 && yn < H && xw >= 0 && xw < W) v += img[(long)yn * W + xw] * nw;
+                    if (yn >= 0 && yn < H && xw + 1 < W) v += img[(long)yn * W + xw + 1] * ne;
+                    if (yn + 1 < H && xw >= 0 && xw < W) v += img[(long)(yn + 1) * W + xw] * sw;
+                    if (yn + 1 < H && xw + 1 < W) v += img[(long)(yn + 1) * W + xw + 1] * se;
+                    const REAL l = left[(((long)b * C + c) * H + y) * W + x];
+                    concat[(((long)b * 2 * C + c) * H + y) * W + x] = v - l;
+                    concat[(((long)b * 2 * C + C + c) * H + y) * W + x] = l;
+                }
+            }
+}
+
 #undef FN
 #undef CAT
 #undef CAT_

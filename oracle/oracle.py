@@ -167,3 +167,17 @@ def csa_fuse_bwd(out, gout, term_hws, slope=0.2):
     getattr(lib(), "orc_csa_fuse_bwd" + s)(_p(out), _p(gout), _ptr_array(gts), th, tw, len(gts),
                                            B, C, H, W, ct(slope))
     return gts
+
+
+def refine_frontend_fwd(low, left, right):
+    """(low_disp [B,h,w], left [B,C,H,W], right [B,C,H,W]) -> (cat(warped - left, left) [B,2C,H,W],
+    disp [B,1,H,W]): refinement.py:80-95 + warp.py:41-64."""
+    low = _c(low); left = _c(left, low.dtype); right = _c(right, low.dtype)
+    B, h, w = low.shape
+    _, C, H, W = left.shape
+    concat = np.empty((B, 2 * C, H, W), low.dtype)
+    disp = np.empty((B, 1, H, W), low.dtype)
+    s, _ = _sfx(low)
+    getattr(lib(), "orc_refine_frontend_fwd" + s)(_p(low), _p(left), _p(right), _p(concat), _p(disp),
+                                                  B, C, h, w, H, W)
+    return concat, disp

@@ -178,5 +178,12 @@ h1 = [rnd(1, 64, 208, 64) for _ in range(n)]
 h2 = [rnd(1, 32, 104, 64) for _ in range(n)]
 report("CSA fuse out0, channels-last (tiled)", timeit(lambda i: ops.csa_fuse_nhwc([h0[i], h1[i], h2[i]], 0.2), n),
        4.0 * 64 * (2 * 128 * 416 + 64 * 208 + 32 * 104) / 1e6)
+# refinement front end at KITTI size: fused kernel vs the torch composite (reference arithmetic, no sync)
+from aanet_b200.nets.refine import refine_frontend_torch  # noqa: E402
+lows = [torch.rand(1, 128, 416, device=dev) * 60 for _ in range(n)]
+imgs = [(torch.rand(1, 3, 384, 1248, device=dev), torch.rand(1, 3, 384, 1248, device=dev)) for _ in range(n)]
+rf_mb = 4.0 * (128 * 416 + 6 * 384 * 1248 + 7 * 384 * 1248) / 1e6
+report("refine front end (fused)", timeit(lambda i: ops.refine_frontend(lows[i], *imgs[i]), n), rf_mb)
+report("refine front end (torch ops, reference arithmetic)", timeit(lambda i: refine_frontend_torch(lows[i], *imgs[i]), n), rf_mb)
 if "--json" in sys.argv:
     print(json.dumps(results))

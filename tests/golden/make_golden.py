@@ -239,13 +239,47 @@ def gen_aggregation(nets, cost_mod, est_mod):
         save(tag, **cases)
 
 
+def gen_refinement(nets):
+    """Refinement: the front end of StereoDRNetRefinement / HourglassRefinement.forward
+    (refinement.py:80-95, :144-160 -> warp.py:41-64) captured with forward hooks on the reference modules
+    themselves -- conv1 sees cat(error, left), conv2 sees the upsampled, rescaled disparity -- plus the whole
+    StereoDRNetRefinement output and state_dict (the hourglass weights would be 9 MB: its key/shape parity is
+    checked against the live reference in tests/test_host.py instead)."""
+    torch.manual_seed(327)
+    from nets.refinement import StereoDRNetRefinement
+    cases = {}
+    net = StereoDRNetRefinement().eval()
+    randomize(net)
+    seen = {}
+    net.conv1.register_forward_hook(lambda m, i, o: seen.__setitem__("concat", i[0].clone()))
+    net.conv2.register_forward_hook(lambda m, i, o: seen.__setitem__("disp", i[0].clone()))
+    shapes = {"x3": (2, 8, 12, 24, 36), "same": (1, 10, 14, 10, 14), "odd": (1, 5, 7, 13, 20),
+              "x2": (1, 16, 24, 32, 48)}
+    for tag, (B, h, w, H, W) in shapes.items():
+        low = torch.rand(B, h, w) * (w / 2.5)            # positive; x - disp leaves the image on the left
+        left, right = torch.rand(B, 3, H, W), torch.rand(B, 3, H, W)
+        with torch.no_grad():
+            out = net(low, left, right)
+        cases.update({tag + "_low": npf(low), tag + "_left": npf(left), tag + "_right": npf(right),
+                      tag + "_concat": npf(seen["concat"]), tag + "_disp": npf(seen["disp"]),
+                      tag + "_drnet_out": npf(out)})
+    for k, v in net.state_dict().items():
+        if not k.endswith("num_batches_tracked"):
+            cases["drnet_sd/" + k] = npf(v)
+    save("refinement", **cases)
+
+
 if __name__ == "__main__":
     cost_mod = load_by_path("ref_cost", "nets/cost.py")
     est_mod = load_by_path("ref_estimation", "nets/estimation.py")
     nets = load_nets()
+    if "--only-refinement" in sys.argv:     # added after the other fixtures were committed; own seed
+        gen_refinement(nets)
+        sys.exit(0)
     gen_corr(cost_mod)
     gen_softargmin(est_mod)
     gen_mdcn(nets)
     gen_deformconv2d(nets)
     gen_csa()
     gen_aggregation(nets, cost_mod, est_mod)
+    gen_refinement(nets)

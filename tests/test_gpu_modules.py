@@ -233,3 +233,37 @@ def test_host_pipeline_matches_direct_forward():
         got.append(HostPipeline.result(slot).clone())
     for g, w in zip(got, want):
         assert torch.equal(g, w)
+
+
+def test_stereodrnet_refinement_golden(golden):
+    """Whole StereoDRNetRefinement (fused front end + cuDNN glue) vs the reference module's output, with the
+    reference's state_dict loaded strict=True."""
+    import aanet_b200.nets as n
+    z = golden("refinement")
+    net = n.StereoDRNetRefinement().eval()
+    net.load_state_dict(_sd(z, "drnet_sd/"), strict=False)        # num_batches_tracked is not stored
+    net.cuda()
+    for tag in ("x3", "same", "odd", "x2"):
+        with torch.no_grad():
+            out = net(torch.from_numpy(z[tag + "_low"]).cuda(), torch.from_numpy(z[tag + "_left"]).cuda(),
+                      torch.from_numpy(z[tag + "_right"]).cuda())
+        ref = z[tag + "_drnet_out"]
+        assert np.abs(npy(out) - ref).max() < 1e-3 * max(1.0, np.abs(ref).max())     # disparity, px
+
+
+def test_hourglass_refinement_runs_and_trains():
+    """HourglassRefinement: inference through the fused front end + the tcgen05 deformable layers, and one
+    backward through the differentiable front end; both paths agree."""
+    import aanet_b200.nets as n
+    torch.manual_seed(326)
+    net = n.HourglassRefinement().cuda().eval()
+    low = (torch.rand(1, 16, 24, device="cuda") * 8)
+    left, right = torch.rand(1, 3, 32, 48, device="cuda"), torch.rand(1, 3, 32, 48, device="cuda")
+    with torch.no_grad():
+        a = net(low, left, right)
+    lg = low.clone().requires_grad_()
+    b = net(lg, left, right)
+    assert a.shape == (1, 32, 48) and torch.isfinite(a).all()
+    assert (a - b.detach()).abs().max() < 1e-3
+    b.sum().backward()
+    assert lg.grad is not None and torch.isfinite(lg.grad).all() and lg.grad.abs().sum() > 0

@@ -424,3 +424,35 @@ def test_errors(ops):
                                   torch.randn(4, 3, 3, 3, device="cuda"), None, 1, 1, 1, 1, 1)
     with pytest.raises(TypeError):
         ops.soft_argmin(xc.double(), True)
+
+
+# ------------------------------------------------------------------------------------ refinement front end
+@pytest.mark.parametrize("tag", ["x3", "same", "odd", "x2"])
+def test_refine_frontend_golden(ops, golden, tag):
+    """Fused upsample + rescale + disp_warp + error + concat vs tensors captured inside the reference's
+    StereoDRNetRefinement.forward (refinement.py:80-95, warp.py:41-64)."""
+    z = golden("refinement")
+    concat, disp = ops.refine_frontend(cu(z[tag + "_low"]), cu(z[tag + "_left"]), cu(z[tag + "_right"]))
+    assert np.abs(npy(disp) - z[tag + "_disp"]).max() < 1e-5 * max(1.0, np.abs(z[tag + "_disp"]).max())
+    assert np.abs(npy(concat) - z[tag + "_concat"]).max() < 1e-5
+    assert np.array_equal(npy(concat)[:, 3:], z[tag + "_left"])
+
+
+def test_refine_frontend_full_size_vs_oracle_and_torch(ops):
+    """KITTI size (low_disp at 1/3 -> 384x1248): against the oracle, and against the differentiable torch
+    composite the modules use when autograd is on (same arithmetic as the reference, minus its sync)."""
+    from aanet_b200.nets.refine import refine_frontend_torch
+    torch.manual_seed(326)
+    low = torch.rand(1, 128, 416, device="cuda") * 60
+    left, right = torch.rand(1, 3, 384, 1248, device="cuda"), torch.rand(1, 3, 384, 1248, device="cuda")
+    concat, disp = ops.refine_frontend(low, left, right)
+    # same device, same arithmetic as the reference (F.interpolate + grid_sample): disparity within 1e-3 px
+    tc, td = refine_frontend_torch(low, left, right)
+    assert (td.detach() - disp).abs().max() < 1e-3 and (tc.detach() - concat).abs().max() < 1e-3
+    # CPU oracle: the upsampling source index is an FMA on the GPU (as in ATen's CUDA kernel) and two roundings on
+    # the CPU, which moves a ~180 px disparity by up to a few 1e-3 px: relative bound
+    rc, rd = orc.refine_frontend_fwd(npy(low), npy(left), npy(right))
+    assert np.abs(npy(disp) - rd).max() < 1e-4 * np.abs(rd).max()
+    assert np.abs(npy(concat) - rc).max() < 1e-2 and np.abs(npy(concat) - rc).mean() < 1e-4
+    with pytest.raises(RuntimeError):
+        ops.refine_frontend(low[:, :100], left[..., :416].contiguous(), right[..., :416].contiguous())   # W == w, H != h

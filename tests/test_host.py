@@ -137,7 +137,16 @@ else:
     sys.modules["nets.deform_conv.deform_conv_cuda"] = types.ModuleType("stub")
     import nets
 m = nets.AANet(192, 0, feature_type='aanet', feature_pyramid_network=True, no_intermediate_supervision=True)
-print(json.dumps({k: list(v.shape) for k, v in m.state_dict().items()}))
+out = {k: list(v.shape) for k, v in m.state_dict().items()}
+# AANet+ (GANet features, hourglass refinement with deformable layers) and the StereoDRNet refinement variant
+p = nets.AANet(192, 0, feature_type='ganet', feature_pyramid=True, refinement_type='hourglass',
+               no_intermediate_supervision=True)
+out.update({"plus/" + k: list(v.shape) for k, v in p.state_dict().items()})
+out["plus/refinement_class"] = [type(r).__module__.split(".")[0] for r in p.refinement]
+q = nets.AANet(192, 0, feature_type='aanet', feature_pyramid_network=True, refinement_type='stereodrnet',
+               no_intermediate_supervision=True)
+out.update({"drnet/" + k: list(v.shape) for k, v in q.state_dict().items() if k.startswith("refinement")})
+print(json.dumps(out))
 """ % (REF, ROOT)
     import json
     import subprocess
@@ -146,9 +155,13 @@ print(json.dumps({k: list(v.shape) for k, v in m.state_dict().items()}))
         r = subprocess.run([sys.executable, "-c", code, mode], capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-2000:]
         outs[mode] = json.loads(r.stdout.strip().splitlines()[-1])
+    assert outs["ours"].pop("plus/refinement_class") == ["aanet_b200"] * 2      # ours are really swapped in
+    assert outs["stock"].pop("plus/refinement_class") == ["nets"] * 2
     assert outs["ours"] == outs["stock"]
     assert sum(int(np.prod(s)) for k, s in outs["ours"].items() if "num_batches" not in k
-               and "running" not in k) == 3931676
+               and "running" not in k and "/" not in k) == 3931676
+    assert sum(int(np.prod(s)) for k, s in outs["ours"].items() if k.startswith("plus/") and "num_batches" not in k
+               and "running" not in k) == 8442850
 
 
 # ------------------------------------------------------------------------------------ sharding (gloo)

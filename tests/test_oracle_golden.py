@@ -119,3 +119,14 @@ def test_hot_path_port(golden, name):
     disps = [port.disparity_estimation(o) for o in reversed(outs)]
     for i, d in enumerate(disps):
         assert np.abs(d.numpy() - z["disp%d" % i]).max() < 1e-3
+
+
+# ------------------------------------------------------------------------------------ refinement front end
+@pytest.mark.parametrize("tag", ["x3", "same", "odd", "x2"])
+def test_refine_frontend_oracle_vs_reference(golden, tag):
+    """Oracle vs tensors captured inside the reference's StereoDRNetRefinement.forward (inputs of conv1 / conv2)."""
+    z = golden("refinement")
+    concat, disp = orc.refine_frontend_fwd(z[tag + "_low"], z[tag + "_left"], z[tag + "_right"])
+    assert np.abs(disp - z[tag + "_disp"]).max() < 1e-5 * max(1.0, np.abs(z[tag + "_disp"]).max())
+    assert np.abs(concat - z[tag + "_concat"]).max() < 1e-5
+    assert np.array_equal(concat[:, 3:], z[tag + "_left"])
