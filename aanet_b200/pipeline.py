@@ -103,7 +103,10 @@ class HostPipeline:
 
     def __init__(self, hot_path, shapes, device, n_slots=2):
         self.hp, self.device, self.n = hot_path, device, n_slots
-        self.numa = bind_host_to_gpu_numa(device)          # before the pinned blocks are allocated
+        # pinned blocks are allocated with the process bound to the GPU's NUMA node; the caller's CPU affinity is
+        # restored afterwards (first-touch placement keeps the pages node-local)
+        affinity = os.sched_getaffinity(0)
+        self.numa = bind_host_to_gpu_numa(device)
         self.copy_stream = torch.cuda.Stream(device)
         self.compute_stream = torch.cuda.Stream(device)
         self.slots = []
@@ -133,6 +136,7 @@ class HostPipeline:
                                    copied=torch.cuda.Event(), done=torch.cuda.Event(),
                                    free=torch.cuda.Event()))
             self.slots[-1]["free"].record(self.compute_stream)
+        os.sched_setaffinity(0, affinity)
         self.i = 0
         self.h2d_bytes = 4 * total
         self.d2h_bytes = 4 * self.slots[0]["out"].numel()
