@@ -17,16 +17,17 @@
 // The epilogue writes channels-last or NCHW; the NCHW <-> NHWC conversions needed at the reference-
 // shaped boundary are done by transpose_kernel.
 //
-// Blackwell mapping.  A CTA is persistent (grid = #SMs) and walks 128-pixel tiles.  M = 128 pixels is
-// the UMMA M (one TMEM lane per pixel), N = BN <= 64 output channels (wider layers = several N tiles), K walks (tap, channel) in blocks of
-// 32 tf32 = one 128-byte swizzle row.  Warp roles:
+// Blackwell mapping.  A CTA is persistent (grid <= #SMs) and walks 128-pixel tiles.  M = 128 pixels is the UMMA M
+// (one TMEM lane per pixel), N = BN <= 64 output channels (wider layers = several N tiles), K walks (tap, channel)
+// in blocks of 32 tf32 = one 128-byte swizzle row.  Warp roles (20 warps = 5 warpgroups, see kUThreads):
 //   warps 0-11  A producers, 3 groups of 4 warps; a group fills a whole stage, so three K blocks are in
 //               production at once.  lane = (pixel row, 16-byte chunk): LDG.128 (4 per item for DEFORM, 1
-//               for DENSE), bilinear combine, split into tf32 hi + lo (cvt.rna + exact remainder), two
-//               STS.128 into SWIZZLE_128B K-major tiles; fence.proxy.async + mbarrier arrive.  Each lane
-//               owns the geometry (output coordinates, bilinear sample) of ONE of the 8 rows its row group
-//               covers and broadcasts it with __shfl_sync, so the sampling math is done once per
-//               (pixel, tap, deformable group) instead of once per 16-byte chunk.
+//               for DENSE), bilinear combine, split into tf32 hi + lo (mantissa mask + exact remainder), two
+//               STS.128 into SWIZZLE_128B K-major tiles; fence.proxy.async + mbarrier arrive.  DEFORM: each
+//               lane owns the bilinear sample of ONE of the 8 rows its row group covers and broadcasts it with
+//               __shfl_sync, so the sampling math is done once per (pixel, tap, deformable group) instead of
+//               once per 16-byte chunk.  DENSE: a thread's 8 rows are 8 consecutive pixels, one address
+//               computation per K block.
 //   warp 17     streams the pre-split, pre-swizzled weight block of the stage with one cp.async.bulk.
 //   warp 16     one thread issues the 3xTF32 products per K step (hi*hi + hi*lo + lo*hi: fp32-grade accuracy,
 //               the parity bar is 1e-4) as tcgen05.mma.kind::tf32 into one of two TMEM accumulators -- two
@@ -34,7 +35,9 @@
 //               stage with tcgen05.commit.
 //   warps 12-15 epilogue: tcgen05.ld (lane = pixel), bias / folded-BN affine / residual / activation,
 //               128-bit channels-last stores (or coalesced NCHW stores); runs one tile behind the MMA.
-// All hand-offs are mbarriers; the 3-stage ring runs across tile boundaries.  3 stages x 48 KB keep the smem
+//   warps 18-19 pad the control warpgroup (setmaxnreg is warpgroup-collective).
+// Launches are chained with programmatic dependent launch (pdl_wait after the prologue, pdl_trigger when a CTA
+// starts its last epilogue).  All hand-offs are mbarriers; the 3-stage ring runs across tile boundaries.  3 stages x 48 KB keep the smem
 // carve-out at 164 KB, i.e. ~90 KB of L1 for the gathers; multi-tap convolutions use 16 x 8 pixel tiles so
 // that a tile's footprint over all taps fits it (1-D 128-pixel tiles + 206 KB of smem gave a 13 % L1 hit rate
 // and 579 MB of L2->L1 traffic per 1/3-scale deformable conv).
@@ -291,7 +294,7 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
     if (warp < kProdWarps) {
         // ================================ A producers ===========================================
         // Group g (4 warps) fills every kGroups-th K block of the CTA's (tile, K block) sequence on its own,
-        // so four stages are in production concurrently and the wait / fence / arrive chain is paid once per
+        // so kGroups stages are in production concurrently and the wait / fence / arrive chain is paid once per
         // 8 rows per thread.  Inside a group, the 8 lanes t..t+7 of a "row group" cover the eight 16-byte
         // chunks of rows row0..row0+7: lane j handles chunk j of every row and OWNS the geometry of row
         // row0 + j (output coordinates; for DEFORM the bilinear sample), broadcast with __shfl_sync.
