@@ -273,9 +273,20 @@ mdcn_bwd_bias_kernel(const float *__restrict__ gout, float *__restrict__ gbias, 
     if (threadIdx.x == 0) gbias[o] = red[0];
 }
 
-size_t mdcn_bwd_workspace_bytes(const MdcnDims &d) {
+// mdcn_bwd_umma.cu: input / offset / mask gradients through the tcgen05 engine + vector atomics
+bool mdcn_bwd_umma_supported(const MdcnDims &d);
+size_t mdcn_bwd_umma_workspace_bytes(const MdcnDims &d);
+int mdcn_bwd_input_umma(const float *x, const float *offset, const float *mask, const float *weight,
+                        const float *gout, float *gx, float *goffset, float *gmask, const MdcnDims &d, void *ws,
+                        cudaStream_t stream);
+
+static size_t weight_partial_bytes(const MdcnDims &d) {
     const WeightPlan wp = make_weight_plan(d);
-    return (size_t)wp.splits * d.Cout * d.Cg * d.K * sizeof(float);
+    return (((size_t)wp.splits * d.Cout * d.Cg * d.K * sizeof(float)) + 255) & ~(size_t)255;
+}
+
+size_t mdcn_bwd_workspace_bytes(const MdcnDims &d) {
+    return weight_partial_bytes(d) + (mdcn_bwd_umma_supported(d) ? mdcn_bwd_umma_workspace_bytes(d) : 0);
 }
 
 int mdcn_bwd_launch(const float *x, const float *offset, const float *mask, const float *weight,
@@ -284,18 +295,26 @@ int mdcn_bwd_launch(const float *x, const float *offset, const float *mask, cons
     const WeightPlan wp = make_weight_plan(d);
     const size_t need = (size_t)wp.splits * d.Cout * d.Cg * d.K * sizeof(float);
     if (!ws || ws_bytes < need) return AANET_ERR_WORKSPACE;
+    int rc;
 
     // ---- grad_input / grad_offset / grad_mask
-    const size_t smem = ((size_t)d.Cout * kBP + (size_t)d.Og * kBC) * sizeof(float);
-    if (smem > 200 * 1024) return AANET_ERR_UNSUPPORTED;
-    cudaFuncSetAttribute(mdcn_bwd_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)d.B * d.Cin * d.HW, stream) != cudaSuccess)
-        return check_launch();
-    const long n_ptiles = ceil_div_ll(d.P, kBP);
-    mdcn_bwd_input_kernel<<<dim3((unsigned)n_ptiles, d.B), kBP, smem, stream>>>(
-        x, offset, mask, weight, gout, gx, goffset, gmask, d);
-    int rc = check_launch();
-    if (rc) return rc;
+    const size_t part = weight_partial_bytes(d);
+    if (mdcn_bwd_umma_supported(d) && ws_bytes >= part + mdcn_bwd_umma_workspace_bytes(d)) {
+        rc = mdcn_bwd_input_umma(x, offset, mask, weight, gout, gx, goffset, gmask, d, static_cast<char *>(ws) + part,
+                                 stream);
+        if (rc) return rc;
+    } else {
+        const size_t smem = ((size_t)d.Cout * kBP + (size_t)d.Og * kBC) * sizeof(float);
+        if (smem > 200 * 1024) return AANET_ERR_UNSUPPORTED;
+        cudaFuncSetAttribute(mdcn_bwd_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)d.B * d.Cin * d.HW, stream) != cudaSuccess)
+            return check_launch();
+        const long n_ptiles = ceil_div_ll(d.P, kBP);
+        mdcn_bwd_input_kernel<<<dim3((unsigned)n_ptiles, d.B), kBP, smem, stream>>>(
+            x, offset, mask, weight, gout, gx, goffset, gmask, d);
+        rc = check_launch();
+        if (rc) return rc;
+    }
 
     // ---- grad_weight
     float *partial = static_cast<float *>(ws);
