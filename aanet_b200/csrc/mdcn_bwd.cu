@@ -280,9 +280,21 @@ int mdcn_bwd_input_umma(const float *x, const float *offset, const float *mask, 
                         const float *gout, float *gx, float *goffset, float *gmask, const MdcnDims &d, void *ws,
                         cudaStream_t stream);
 
+size_t mdcn_bwd_weight_mma_partial_bytes(const MdcnDims &d);
+int mdcn_bwd_weight_mma(const float *x_nhwc, const float *offset, const float *mask, const float *gout_nhwc,
+                        float *partial, const MdcnDims &d, int *splits_out, cudaStream_t stream);
+const float *mdcn_bwd_umma_x_nhwc(const MdcnDims &d, const void *ws);
+const float *mdcn_bwd_umma_gout_nhwc(const MdcnDims &d, const void *ws);
+
+// room for the per-split partial weight gradients of whichever weight kernel runs
 static size_t weight_partial_bytes(const MdcnDims &d) {
     const WeightPlan wp = make_weight_plan(d);
-    return (((size_t)wp.splits * d.Cout * d.Cg * d.K * sizeof(float)) + 255) & ~(size_t)255;
+    size_t n = (((size_t)wp.splits * d.Cout * d.Cg * d.K * sizeof(float)) + 255) & ~(size_t)255;
+    if (mdcn_bwd_umma_supported(d)) {
+        const size_t m = mdcn_bwd_weight_mma_partial_bytes(d);
+        n = n > m ? n : m;
+    }
+    return n;
 }
 
 size_t mdcn_bwd_workspace_bytes(const MdcnDims &d) {
@@ -318,14 +330,21 @@ int mdcn_bwd_launch(const float *x, const float *offset, const float *mask, cons
 
     // ---- grad_weight
     float *partial = static_cast<float *>(ws);
-    // padding items (nc == 0) leave holes only in slices that are never read; real slices are
-    // fully written because every (o, c, k) belongs to exactly one item.
-    mdcn_bwd_weight_kernel<<<dim3(wp.n_items, wp.splits), kWThreads, 0, stream>>>(x, offset, mask, gout,
-                                                                                 partial, d, wp);
-    rc = check_launch();
-    if (rc) return rc;
     const int n = d.Cout * d.Cg * d.K;
-    mdcn_bwd_weight_reduce_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(partial, gweight, n, wp.splits);
+    int splits = wp.splits;
+    if (mdcn_bwd_umma_supported(d) && ws_bytes >= part + mdcn_bwd_umma_workspace_bytes(d)) {
+        const void *uws = static_cast<char *>(ws) + part;      // channels-last x and gout are already there
+        rc = mdcn_bwd_weight_mma(mdcn_bwd_umma_x_nhwc(d, uws), offset, mask, mdcn_bwd_umma_gout_nhwc(d, uws), partial, d,
+                                 &splits, stream);
+    } else {
+        // padding items (nc == 0) leave holes only in slices that are never read; real slices are
+        // fully written because every (o, c, k) belongs to exactly one item.
+        mdcn_bwd_weight_kernel<<<dim3(wp.n_items, wp.splits), kWThreads, 0, stream>>>(x, offset, mask, gout,
+                                                                                     partial, d, wp);
+        rc = check_launch();
+    }
+    if (rc) return rc;
+    mdcn_bwd_weight_reduce_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(partial, gweight, n, splits);
     rc = check_launch();
     if (rc) return rc;
 

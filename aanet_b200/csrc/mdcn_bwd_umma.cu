@@ -98,6 +98,153 @@ mdcn_bwd_scatter_kernel(const float *__restrict__ x_nhwc, const float *__restric
     }
 }
 
+static size_t align256_(size_t n) { return (n + 255) & ~(size_t)255; }
+
+// ------------------------------------------------------------------------------------------------ grad_weight
+// grad_weight[o, c, k] = sum_{b,p} gout[b,p,o] * col[b,p,(k,c)],  col = mask * bilinear(x) -- a GEMM whose reduction
+// runs over the pixels, which the convolution engine (M = pixels) cannot express.  Warp-level tensor cores instead:
+// a CTA owns (tap k, 32 input channels inside one deformable group, 64 output channels) and a strided share of the
+// 64-pixel tiles.  Per tile the modulated columns are gathered from channels-last x with LDG.128 (8 lanes per pixel)
+// into shared memory, the gout tile is copied next to them, and four warps accumulate D[64 o x 32 c] with
+// mma.sync.m16n8k8 tf32, each product issued three times (hi*hi + hi*lo + lo*hi, operands split by mantissa mask).
+// Per-split partials are summed in a fixed order by mdcn_bwd_weight_reduce_kernel (deterministic grad_weight).
+constexpr int kMP = 64, kMC = 32, kMO = 64, kMThreads = 128;
+constexpr int kMColStride = kMC + 8, kMGStride = kMO + 8;      // = 8 mod 32: conflict-free fragment loads
+
+__device__ __forceinline__ void mma_tf32_m16n8k8(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void split_bits(float x, uint32_t &hi, uint32_t &lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
+}
+
+__global__ void __launch_bounds__(kMThreads)
+mdcn_bwd_weight_mma_kernel(const float *__restrict__ x_nhwc, const float *__restrict__ offset,
+                           const float *__restrict__ mask, const float *__restrict__ gout_nhwc,
+                           float *__restrict__ partial, MdcnDims d, int n_cchunks, int n_otiles, int tiles_per_img,
+                           int splits) {
+    __shared__ __align__(16) float s_col[kMP][kMColStride];
+    __shared__ __align__(16) float s_g[kMP][kMGStride];
+    int item = blockIdx.x;
+    const int ot = item % n_otiles; item /= n_otiles;
+    const int ci = item % n_cchunks;
+    const int k = item / n_cchunks;
+    const int split = blockIdx.y;
+    // channel chunks of 32 never straddle a deformable group: chunks per group = ceil(Cd / 32)
+    const int cpg = (d.Cd + kMC - 1) / kMC;
+    const int g = ci / cpg, c0 = g * d.Cd + (ci % cpg) * kMC;
+    const int nc = min(kMC, (g + 1) * d.Cd - c0);
+    const int o0 = ot * kMO;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int fg = lane >> 2, ft = lane & 3;              // fragment row group / thread-in-group
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const int chunk = tid & 7;                            // gather role: 16-byte channel chunk, pixel (tid >> 3) + 16 i
+    const long T = (long)d.B * tiles_per_img;
+    for (long t = split; t < T; t += splits) {
+        const long b = t / tiles_per_img;
+        const long p0 = (t % tiles_per_img) * kMP;
+        const float *off_b = offset + b * d.dg * 2 * d.K * d.P;
+        const float *x_b = x_nhwc + b * d.HW * d.Cin + c0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int px = (tid >> 3) + 16 * i;
+            const long p = p0 + px;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p < d.P && chunk * 4 < nc) {
+                const Sample s = sample_at(d, off_b, g, k, (int)(p / d.Wo), (int)(p % d.Wo), p);
+                const float m = mask ? mask[(b * d.dg * d.K + g * d.K + k) * d.P + p] : 1.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if ((s.ok >> q) & 1) {
+                        const float4 xv = __ldg(reinterpret_cast<const float4 *>(x_b + (long)s.i[q] * d.Cin) + chunk);
+                        const float wq = s.w[q] * m;
+                        v.x = fmaf(wq, xv.x, v.x); v.y = fmaf(wq, xv.y, v.y);
+                        v.z = fmaf(wq, xv.z, v.z); v.w = fmaf(wq, xv.w, v.w);
+                    }
+                }
+            }
+            *reinterpret_cast<float4 *>(&s_col[px][chunk * 4]) = v;
+        }
+        for (int i = tid; i < kMP * (kMO / 4); i += kMThreads) {     // gout tile: 64 px x 16 chunks
+            const int px = i / (kMO / 4), oc = (i % (kMO / 4)) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p0 + px < d.P && o0 + oc < d.Cout)
+                v = __ldg(reinterpret_cast<const float4 *>(gout_nhwc + (b * d.P + p0 + px) * d.Cout + o0 + oc));
+            *reinterpret_cast<float4 *>(&s_g[px][oc]) = v;
+        }
+        __syncthreads();
+        const int ow = warp * 16;                                     // this warp's 16 output channels
+#pragma unroll 2
+        for (int kk = 0; kk < kMP; kk += 8) {
+            uint32_t ah[4], al[4];
+            split_bits(s_g[kk + ft][ow + fg], ah[0], al[0]);
+            split_bits(s_g[kk + ft][ow + fg + 8], ah[1], al[1]);
+            split_bits(s_g[kk + ft + 4][ow + fg], ah[2], al[2]);
+            split_bits(s_g[kk + ft + 4][ow + fg + 8], ah[3], al[3]);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                uint32_t bh[2], bl[2];
+                split_bits(s_col[kk + ft][nt * 8 + fg], bh[0], bl[0]);
+                split_bits(s_col[kk + ft + 4][nt * 8 + fg], bh[1], bl[1]);
+                mma_tf32_m16n8k8(acc[nt], ah, bh);
+                mma_tf32_m16n8k8(acc[nt], ah, bl);
+                mma_tf32_m16n8k8(acc[nt], al, bh);
+            }
+        }
+        __syncthreads();
+    }
+    // partial[split][o][c][k]; fragment: acc[nt][0..3] = D[fg][2 ft], D[fg][2 ft + 1], D[fg + 8][2 ft], D[fg + 8][2 ft + 1]
+    float *dst = partial + (size_t)split * d.Cout * d.Cin * d.K;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int o = o0 + warp * 16 + fg + (e >> 1) * 8;
+            const int cc = nt * 8 + 2 * ft + (e & 1);
+            if (cc < nc && o < d.Cout) dst[((size_t)o * d.Cin + c0 + cc) * d.K + k] = acc[nt][e];
+        }
+}
+
+struct WeightMmaPlan { int n_cchunks, n_otiles, n_items, tiles_per_img, splits; };
+
+static WeightMmaPlan plan_weight_mma(const MdcnDims &d) {
+    WeightMmaPlan w;
+    w.n_cchunks = d.dg * ((d.Cd + kMC - 1) / kMC);
+    w.n_otiles = ceil_div(d.Cout, kMO);
+    w.n_items = d.K * w.n_cchunks * w.n_otiles;
+    w.tiles_per_img = (int)ceil_div_ll(d.P, kMP);
+    const long T = (long)d.B * w.tiles_per_img;
+    long s = ceil_div_ll(8 * kNumSMs, w.n_items);
+    if (s < 1) s = 1;
+    if (s > 128) s = 128;
+    if (s > T) s = T;
+    w.splits = (int)s;
+    return w;
+}
+
+size_t mdcn_bwd_weight_mma_partial_bytes(const MdcnDims &d) {
+    return align256_((size_t)plan_weight_mma(d).splits * d.Cout * d.Cin * d.K * sizeof(float));
+}
+
+// x_nhwc / gout_nhwc: the channels-last copies mdcn_bwd_input_umma left in its workspace
+int mdcn_bwd_weight_mma(const float *x_nhwc, const float *offset, const float *mask, const float *gout_nhwc,
+                        float *partial, const MdcnDims &d, int *splits_out, cudaStream_t stream) {
+    const WeightMmaPlan w = plan_weight_mma(d);
+    mdcn_bwd_weight_mma_kernel<<<dim3(w.n_items, w.splits), kMThreads, 0, stream>>>(
+        x_nhwc, offset, mask, gout_nhwc, partial, d, w.n_cchunks, w.n_otiles, w.tiles_per_img, w.splits);
+    *splits_out = w.splits;
+    return check_launch();
+}
+
 // dimensions of the column-gradient GEMM as a 1x1 convolution over the OUTPUT pixel grid
 static int gcol_dims(const MdcnDims &d, MdcnDims &g) {
     return mdcn_make_dims(g, d.B, d.Cout, d.Ho, d.Wo, d.K * d.Cin, 1, 1, 1, 0, 1, 1, 1);
@@ -107,6 +254,9 @@ static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 
 bool mdcn_bwd_umma_supported(const MdcnDims &d) {
     if (d.groups != 1 || d.Cin % 4 || d.Cout % 4 || d.Cd % 4) return false;
+    // 8 lanes / 32-channel MMA chunks per (pixel, tap, deformable group): with fewer than 12 channels per deformable
+    // group most of them idle and the FFMA kernels are faster (config-4 sweep: Cd = 8 is 10-15 % slower, Cd = 4 40 %)
+    if (d.Cd < 12) return false;
     if ((long)d.K * d.Cin > 0xffff) return false;
     MdcnDims g;
     return gcol_dims(d, g) == AANET_OK && conv_umma_supported(g, false);
@@ -132,6 +282,12 @@ static BwdUmmaWs plan_ws(const MdcnDims &d) {
 }
 
 size_t mdcn_bwd_umma_workspace_bytes(const MdcnDims &d) { return plan_ws(d).total; }
+const float *mdcn_bwd_umma_x_nhwc(const MdcnDims &d, const void *ws) {
+    return reinterpret_cast<const float *>(static_cast<const char *>(ws) + plan_ws(d).x_t);
+}
+const float *mdcn_bwd_umma_gout_nhwc(const MdcnDims &d, const void *ws) {
+    return reinterpret_cast<const float *>(static_cast<const char *>(ws) + plan_ws(d).gout_t);
+}
 
 int mdcn_bwd_input_umma(const float *x, const float *offset, const float *mask, const float *weight,
                         const float *gout, float *gx, float *goffset, float *gmask, const MdcnDims &d, void *ws,
