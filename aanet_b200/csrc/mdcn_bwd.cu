@@ -281,9 +281,9 @@ int mdcn_bwd_input_umma(const float *x, const float *offset, const float *mask, 
                         cudaStream_t stream);
 
 size_t mdcn_bwd_weight_mma_partial_bytes(const MdcnDims &d);
-int mdcn_bwd_weight_mma(const float *x_nhwc, const float *offset, const float *mask, const float *gout_nhwc,
-                        float *partial, const MdcnDims &d, int *splits_out, cudaStream_t stream);
-const float *mdcn_bwd_umma_x_nhwc(const MdcnDims &d, const void *ws);
+int mdcn_bwd_weight_mma(const float *col, const float *gout_nhwc, float *partial, const MdcnDims &d,
+                        int *splits_out, cudaStream_t stream);
+const float *mdcn_bwd_umma_col(const MdcnDims &d, const void *ws);
 const float *mdcn_bwd_umma_gout_nhwc(const MdcnDims &d, const void *ws);
 
 // room for the per-split partial weight gradients of whichever weight kernel runs
@@ -333,9 +333,8 @@ int mdcn_bwd_launch(const float *x, const float *offset, const float *mask, cons
     const int n = d.Cout * d.Cg * d.K;
     int splits = wp.splits;
     if (mdcn_bwd_umma_supported(d) && ws_bytes >= part + mdcn_bwd_umma_workspace_bytes(d)) {
-        const void *uws = static_cast<char *>(ws) + part;      // channels-last x and gout are already there
-        rc = mdcn_bwd_weight_mma(mdcn_bwd_umma_x_nhwc(d, uws), offset, mask, mdcn_bwd_umma_gout_nhwc(d, uws), partial, d,
-                                 &splits, stream);
+        const void *uws = static_cast<char *>(ws) + part;      // the modulated columns and channels-last gout are there
+        rc = mdcn_bwd_weight_mma(mdcn_bwd_umma_col(d, uws), mdcn_bwd_umma_gout_nhwc(d, uws), partial, d, &splits, stream);
     } else {
         // padding items (nc == 0) leave holes only in slices that are never read; real slices are
         // fully written because every (o, c, k) belongs to exactly one item.

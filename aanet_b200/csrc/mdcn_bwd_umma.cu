@@ -37,7 +37,8 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
 __global__ void __launch_bounds__(256)
 mdcn_bwd_scatter_kernel(const float *__restrict__ x_nhwc, const float *__restrict__ offset,
                         const float *__restrict__ mask, const float *__restrict__ gcol, float *__restrict__ gx_nhwc,
-                        float *__restrict__ goffset, float *__restrict__ gmask, MdcnDims d, long n_items) {
+                        float *__restrict__ goffset, float *__restrict__ gmask, float *__restrict__ col, MdcnDims d,
+                        long n_items) {
     const int lane8 = threadIdx.x & 7;
     const long item0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const long stride_items = ((long)gridDim.x * blockDim.x) >> 3;
@@ -54,6 +55,13 @@ mdcn_bwd_scatter_kernel(const float *__restrict__ x_nhwc, const float *__restric
         const float m = mask ? mask[(b * d.dg * d.K + g * d.K + k) * d.P + p] : 1.f;
         const float hh = 1.f - s.lh, hw = 1.f - s.lw;
         float a_m = 0.f, a_oh = 0.f, a_ow = 0.f;
+        // modulated column of this item (the forward's A operand), kept for the weight gradient: the corners are in
+        // registers here anyway, and the weight kernel then needs no gather of its own
+        float *col_p = col + ((b * d.P + p) * d.K + k) * d.Cin + g * d.Cd;
+        if (!s.valid) {
+            for (int ch = lane8; ch < cv; ch += 8)
+                reinterpret_cast<float4 *>(col_p)[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         if (s.valid) {
             const float *gc_p = gcol + ((b * d.P + p) * d.K + k) * d.Cin + g * d.Cd;
             const float *x_b = x_nhwc + b * d.HW * d.Cin + g * d.Cd;
@@ -68,15 +76,18 @@ mdcn_bwd_scatter_kernel(const float *__restrict__ x_nhwc, const float *__restric
                 const float gcs[4] = {gc.x, gc.y, gc.z, gc.w};
                 const float vv[4][4] = {{v[0].x, v[0].y, v[0].z, v[0].w}, {v[1].x, v[1].y, v[1].z, v[1].w},
                                         {v[2].x, v[2].y, v[2].z, v[2].w}, {v[3].x, v[3].y, v[3].z, v[3].w}};
-                float t[4];
+                float t[4], cl[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float v1 = vv[0][e], v2 = vv[1][e], v3 = vv[2][e], v4 = vv[3][e];
-                    a_m = fmaf(gcs[e], s.w[0] * v1 + s.w[1] * v2 + s.w[2] * v3 + s.w[3] * v4, a_m);
+                    const float val = s.w[0] * v1 + s.w[1] * v2 + s.w[2] * v3 + s.w[3] * v4;
+                    cl[e] = val * m;
+                    a_m = fmaf(gcs[e], val, a_m);
                     t[e] = gcs[e] * m;
                     a_oh = fmaf(t[e], -hw * v1 - s.lw * v2 + hw * v3 + s.lw * v4, a_oh);
                     a_ow = fmaf(t[e], -hh * v1 + hh * v2 - s.lh * v3 + s.lh * v4, a_ow);
                 }
+                reinterpret_cast<float4 *>(col_p)[ch] = make_float4(cl[0], cl[1], cl[2], cl[3]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     if ((s.ok >> i) & 1)
@@ -104,8 +115,8 @@ static size_t align256_(size_t n) { return (n + 255) & ~(size_t)255; }
 // grad_weight[o, c, k] = sum_{b,p} gout[b,p,o] * col[b,p,(k,c)],  col = mask * bilinear(x) -- a GEMM whose reduction
 // runs over the pixels, which the convolution engine (M = pixels) cannot express.  Warp-level tensor cores instead:
 // a CTA owns (tap k, 32 input channels inside one deformable group, 64 output channels) and a strided share of the
-// 64-pixel tiles.  Per tile the modulated columns are gathered from channels-last x with LDG.128 (8 lanes per pixel)
-// into shared memory, the gout tile is copied next to them, and four warps accumulate D[64 o x 32 c] with
+// 64-pixel tiles.  Per tile the modulated columns (written by the scatter kernel, which has the corners in registers
+// anyway) and the gout tile are copied into shared memory with LDG.128, and four warps accumulate D[64 o x 32 c] with
 // mma.sync.m16n8k8 tf32, each product issued three times (hi*hi + hi*lo + lo*hi, operands split by mantissa mask).
 // Per-split partials are summed in a fixed order by mdcn_bwd_weight_reduce_kernel (deterministic grad_weight).
 constexpr int kMP = 64, kMC = 32, kMO = 64, kMThreads = 128;
@@ -123,8 +134,7 @@ __device__ __forceinline__ void split_bits(float x, uint32_t &hi, uint32_t &lo) 
 }
 
 __global__ void __launch_bounds__(kMThreads)
-mdcn_bwd_weight_mma_kernel(const float *__restrict__ x_nhwc, const float *__restrict__ offset,
-                           const float *__restrict__ mask, const float *__restrict__ gout_nhwc,
+mdcn_bwd_weight_mma_kernel(const float *__restrict__ col, const float *__restrict__ gout_nhwc,
                            float *__restrict__ partial, MdcnDims d, int n_cchunks, int n_otiles, int tiles_per_img,
                            int splits) {
     __shared__ __align__(16) float s_col[kMP][kMColStride];
@@ -152,26 +162,13 @@ mdcn_bwd_weight_mma_kernel(const float *__restrict__ x_nhwc, const float *__rest
     for (long t = split; t < T; t += splits) {
         const long b = t / tiles_per_img;
         const long p0 = (t % tiles_per_img) * kMP;
-        const float *off_b = offset + b * d.dg * 2 * d.K * d.P;
-        const float *x_b = x_nhwc + b * d.HW * d.Cin + c0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 4; ++i) {                                 // column tile: 64 px x 8 chunks of 16 bytes
             const int px = (tid >> 3) + 16 * i;
             const long p = p0 + px;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p < d.P && chunk * 4 < nc) {
-                const Sample s = sample_at(d, off_b, g, k, (int)(p / d.Wo), (int)(p % d.Wo), p);
-                const float m = mask ? mask[(b * d.dg * d.K + g * d.K + k) * d.P + p] : 1.f;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if ((s.ok >> q) & 1) {
-                        const float4 xv = __ldg(reinterpret_cast<const float4 *>(x_b + (long)s.i[q] * d.Cin) + chunk);
-                        const float wq = s.w[q] * m;
-                        v.x = fmaf(wq, xv.x, v.x); v.y = fmaf(wq, xv.y, v.y);
-                        v.z = fmaf(wq, xv.z, v.z); v.w = fmaf(wq, xv.w, v.w);
-                    }
-                }
-            }
+            if (p < d.P && chunk * 4 < nc)
+                v = __ldg(reinterpret_cast<const float4 *>(col + ((b * d.P + p) * d.K + k) * d.Cin + c0) + chunk);
             *reinterpret_cast<float4 *>(&s_col[px][chunk * 4]) = v;
         }
         for (int i = tid; i < kMP * (kMO / 4); i += kMThreads) {     // gout tile: 64 px x 16 chunks
@@ -235,12 +232,12 @@ size_t mdcn_bwd_weight_mma_partial_bytes(const MdcnDims &d) {
     return align256_((size_t)plan_weight_mma(d).splits * d.Cout * d.Cin * d.K * sizeof(float));
 }
 
-// x_nhwc / gout_nhwc: the channels-last copies mdcn_bwd_input_umma left in its workspace
-int mdcn_bwd_weight_mma(const float *x_nhwc, const float *offset, const float *mask, const float *gout_nhwc,
-                        float *partial, const MdcnDims &d, int *splits_out, cudaStream_t stream) {
+// col / gout_nhwc: the modulated columns and the channels-last gout that mdcn_bwd_input_umma left in its workspace
+int mdcn_bwd_weight_mma(const float *col, const float *gout_nhwc, float *partial, const MdcnDims &d,
+                        int *splits_out, cudaStream_t stream) {
     const WeightMmaPlan w = plan_weight_mma(d);
     mdcn_bwd_weight_mma_kernel<<<dim3(w.n_items, w.splits), kMThreads, 0, stream>>>(
-        x_nhwc, offset, mask, gout_nhwc, partial, d, w.n_cchunks, w.n_otiles, w.tiles_per_img, w.splits);
+        col, gout_nhwc, partial, d, w.n_cchunks, w.n_otiles, w.tiles_per_img, w.splits);
     *splits_out = w.splits;
     return check_launch();
 }
@@ -263,7 +260,7 @@ bool mdcn_bwd_umma_supported(const MdcnDims &d) {
 }
 
 struct BwdUmmaWs {
-    size_t gout_t, x_t, gx_t, gcol, wt, wpack, total;
+    size_t gout_t, x_t, gx_t, gcol, col, wt, wpack, total;
 };
 
 static BwdUmmaWs plan_ws(const MdcnDims &d) {
@@ -275,6 +272,7 @@ static BwdUmmaWs plan_ws(const MdcnDims &d) {
     w.x_t = o;    o += align256((size_t)d.B * d.HW * d.Cin * sizeof(float));
     w.gx_t = o;   o += align256((size_t)d.B * d.HW * d.Cin * sizeof(float));
     w.gcol = o;   o += align256((size_t)d.B * d.P * d.K * d.Cin * sizeof(float));
+    w.col = o;    o += align256((size_t)d.B * d.P * d.K * d.Cin * sizeof(float));
     w.wt = o;     o += align256((size_t)d.K * d.Cin * d.Cout * sizeof(float));
     w.wpack = o;  o += align256(conv_umma_wpack_bytes(g, 0));
     w.total = o;
@@ -282,8 +280,8 @@ static BwdUmmaWs plan_ws(const MdcnDims &d) {
 }
 
 size_t mdcn_bwd_umma_workspace_bytes(const MdcnDims &d) { return plan_ws(d).total; }
-const float *mdcn_bwd_umma_x_nhwc(const MdcnDims &d, const void *ws) {
-    return reinterpret_cast<const float *>(static_cast<const char *>(ws) + plan_ws(d).x_t);
+const float *mdcn_bwd_umma_col(const MdcnDims &d, const void *ws) {
+    return reinterpret_cast<const float *>(static_cast<const char *>(ws) + plan_ws(d).col);
 }
 const float *mdcn_bwd_umma_gout_nhwc(const MdcnDims &d, const void *ws) {
     return reinterpret_cast<const float *>(static_cast<const char *>(ws) + plan_ws(d).gout_t);
@@ -296,6 +294,7 @@ int mdcn_bwd_input_umma(const float *x, const float *offset, const float *mask, 
     char *base = static_cast<char *>(ws);
     float *gout_t = reinterpret_cast<float *>(base + w.gout_t), *x_t = reinterpret_cast<float *>(base + w.x_t);
     float *gx_t = reinterpret_cast<float *>(base + w.gx_t), *gcol = reinterpret_cast<float *>(base + w.gcol);
+    float *col = reinterpret_cast<float *>(base + w.col);
     float *wt = reinterpret_cast<float *>(base + w.wt);
     void *wpack = base + w.wpack;
     MdcnDims g;
@@ -315,7 +314,7 @@ int mdcn_bwd_input_umma(const float *x, const float *offset, const float *mask, 
     const long n_items = (long)d.B * d.K * d.dg * d.P;
     const long blocks = ceil_div_ll(n_items * 8, 256);
     mdcn_bwd_scatter_kernel<<<(int)(blocks < 16L * kNumSMs ? blocks : 16L * kNumSMs), 256, 0, stream>>>(
-        x_t, offset, mask, gcol, gx_t, goffset, gmask, d, n_items);
+        x_t, offset, mask, gcol, gx_t, goffset, gmask, col, d, n_items);
     if ((rc = check_launch()) != AANET_OK) return rc;
     return conv_umma_transpose(gx_t, gx, d.B, (int)d.HW, d.Cin, stream);
 }
