@@ -11,6 +11,8 @@ This is SURVEY.md 8(f) ranks 1-2.  It is used automatically by AdaptiveAggregati
 is in eval mode, autograd is off and every channel count is a multiple of 4; otherwise the module-by-module
 path (torch convs + the same sm_100a operators) runs.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -28,9 +30,18 @@ class _Conv:
         self.groups = conv.groups
         self.stride, self.pad, self.dil = conv.stride[0], conv.padding[0], conv.dilation[0]
         self.wpack = ops.pack_conv_weight(w, conv.groups)
+        self._w, self._packs = w, {}
         self.bias = None if conv.bias is None else conv.bias.detach().float().contiguous()
         self.scale, self.shift = (None, None) if bn is None else bn_affine(bn)
         self.act, self.slope = act, slope
+
+    def problem(self, x, bn):
+        """Descriptor of this conv for a multi-problem launch whose N tile is `bn` wide."""
+        if bn not in self._packs:
+            self._packs[bn] = ops.pack_conv_weight(self._w, self.groups, bn)
+        return dict(x=x, wpack=self._packs[bn], Cout=self.Cout, kh=self.kh, kw=self.kw, bias=self.bias,
+                    scale=self.scale, shift=self.shift, act=self.act, slope=self.slope, stride=self.stride,
+                    pad=self.pad, dil=self.dil, groups=self.groups)
 
     def __call__(self, x, residual=None, out_nchw=False, n_offset_ch=0, mask_scale=1.0, act=None):
         return ops.conv2d_nhwc(x, self.wpack, self.Cout, self.kh, self.kw, self.bias, self.scale, self.shift,
@@ -73,6 +84,11 @@ class _Bottleneck:
 
     def __call__(self, x):
         return self.c3(self.c2(self.c1(x)), residual=x)
+
+
+# One multi-problem launch for the last conv of all exchange chains of a CSA row (A/B on one box: 913 vs 910
+# pairs/s, 10 launches fewer per pair).  AANET_BATCH_EXCHANGE=0 restores one launch per conv.
+BATCH_EXCHANGE = os.environ.get("AANET_BATCH_EXCHANGE", "1") == "1"
 
 
 def _exchange(seq):
@@ -141,12 +157,25 @@ class FusedAggregation:
             # CSA: output scale i needs every input scale; the output scales are independent
             def fuse_row(row):
                 def go():
-                    terms = []
+                    # the last conv of every exchange chain of this row in ONE multi-problem launch (they are
+                    # independent and all produce this row's channel count); longer chains run their head first
+                    terms, last, where = [], [], []
                     for j, chain in enumerate(row):
                         t = xs[j]
-                        for conv in chain:
+                        for conv in chain[:-1]:
                             t = track(conv(t))
                         terms.append(t)
+                        if chain:
+                            last.append((chain[-1], t))
+                            where.append(j)
+                    if len(last) > 1 and BATCH_EXCHANGE:
+                        bn = max(ops.natural_bn(c.Cout // c.groups) for c, _ in last)
+                        outs = ops.conv_batch([c.problem(t, bn) for c, t in last], bn=bn)
+                        for j, o in zip(where, outs):
+                            terms[j] = track(o)
+                    else:
+                        for j, (c, t) in zip(where, last):
+                            terms[j] = track(c(t))
                     return track(ops.csa_fuse_nhwc(terms, slope))
                 return go
             xs = fork_join(dev, [fuse_row(row) for row in fuse])
