@@ -43,13 +43,37 @@ class HotPath(nn.Module):
                                                intermediate_supervision=intermediate_supervision)
         self.disparity_estimation = DisparityEstimation(self.max_disp, True)
         self._graphs = {}
+        self.max_pairs_per_pass = None                      # None: derived from free device memory
+
+    def _one_pass(self, left_pyramid, right_pyramid):
+        cost = self.cost_volume(list(left_pyramid), list(right_pyramid))
+        agg = self.aggregation(cost)
+        return [self.disparity_estimation(a) for a in reversed(agg)]
+
+    def pairs_per_pass(self, left_pyramid):
+        """How many pairs one inference pass may take.  The fused executor keeps every intermediate of the
+        aggregation alive until its final stream join (~70 volumes of the 1/3-scale size per pair, x 21/16 for the
+        coarser scales), so a large batch is run in slices that fit in half of the free device memory (config 5:
+        32 pairs at 1104x1920, D0 = 96, would need ~170 GB in one pass)."""
+        if self.max_pairs_per_pass is not None:
+            return max(1, int(self.max_pairs_per_pass))
+        B, _, H, W = left_pyramid[0].shape
+        per_pair = 70 * 4 * self.max_disp * H * W * 21 // 16
+        free, _ = torch.cuda.mem_get_info(left_pyramid[0].device)
+        return max(1, min(B, int(free // 2 // max(per_pair, 1))))
 
     def forward(self, left_pyramid, right_pyramid):
         """Feature pyramids (finest first) -> list of disparities, coarse to fine (aanet.py:156-167)."""
         with exact_fp32():
-            cost = self.cost_volume(list(left_pyramid), list(right_pyramid))
-            agg = self.aggregation(cost)
-            return [self.disparity_estimation(a) for a in reversed(agg)]
+            B = left_pyramid[0].shape[0]
+            if torch.is_grad_enabled() or self.training or not left_pyramid[0].is_cuda:
+                return self._one_pass(left_pyramid, right_pyramid)
+            n = self.pairs_per_pass(left_pyramid)
+            if n >= B:
+                return self._one_pass(left_pyramid, right_pyramid)
+            parts = [self._one_pass([t[i:i + n] for t in left_pyramid], [t[i:i + n] for t in right_pyramid])
+                     for i in range(0, B, n)]
+            return [torch.cat(ds, dim=0) for ds in zip(*parts)]
 
     # ------------------------------------------------------------------ CUDA graph
     @torch.no_grad()

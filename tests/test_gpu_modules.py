@@ -267,3 +267,20 @@ def test_hourglass_refinement_runs_and_trains():
     assert (a - b.detach()).abs().max() < 1e-3
     b.sum().backward()
     assert lg.grad is not None and torch.isfinite(lg.grad).all() and lg.grad.abs().sum() > 0
+
+
+def test_hot_path_batch_slicing():
+    """A batch that does not fit one pass is run in slices; the result equals the single pass."""
+    from aanet_b200.pipeline import HotPath
+    torch.manual_seed(326)
+    hp = HotPath(48, num_deform_blocks=3).cuda().eval()
+    L = [torch.relu(torch.randn(5, 16, 24 >> s, 40 >> s, device="cuda")) for s in range(3)]
+    R = [torch.relu(torch.randn(5, 16, 24 >> s, 40 >> s, device="cuda")) for s in range(3)]
+    with torch.no_grad():
+        assert hp.pairs_per_pass(L) == 5                      # tiny volumes: everything fits
+        whole = hp(L, R)
+        hp.max_pairs_per_pass = 2                             # 2 + 2 + 1
+        sliced = hp(L, R)
+    assert len(whole) == len(sliced)
+    for a, b in zip(whole, sliced):
+        assert a.shape == b.shape and torch.equal(a, b)
