@@ -21,6 +21,7 @@ SIGNATURES = {
     "aanet_last_cuda_error": (ctypes.c_char_p, []),
     "aanet_corr_fwd": (_i, [_vp, _vp, _vp] + [_i] * 5 + [_vp]),
     "aanet_corr_fwd_bf16": (_i, [_vp, _vp, _vp] + [_i] * 5 + [_vp]),
+    "aanet_corr_fwd_nhwc": (_i, [_vp, _vp, _vp] + [_i] * 5 + [_vp]),
     "aanet_corr_bwd": (_i, [_vp] * 5 + [_i] * 5 + [_vp]),
     "aanet_softargmin_fwd": (_i, [_vp, _vp] + [_i] * 5 + [_vp]),
     "aanet_softargmin_bwd": (_i, [_vp, _vp, _vp] + [_i] * 5 + [_vp]),

@@ -353,7 +353,7 @@ corr_bwd_kernel(const float *__restrict__ L, const float *__restrict__ R, const 
 namespace aanet {
 // correlation_umma.cu
 bool corr_umma_supported(int B, int C, int H, int W, int D);
-int corr_umma_launch(const float *L, const float *R, float *cost, int B, int C, int H, int W, int D,
+int corr_umma_launch(const float *L, const float *R, float *cost, int B, int C, int H, int W, int D, bool nhwc,
                      cudaStream_t stream);
 }  // namespace aanet
 
@@ -365,7 +365,7 @@ extern "C" int aanet_corr_fwd(const float *L, const float *R, float *cost, int B
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || D <= 0) return AANET_ERR_SHAPE;
     if (H > 65535 || B > 65535) return AANET_ERR_UNSUPPORTED;
     // tensor-core path (D <= 128); the FFMA kernels below remain for wider searches
-    if (corr_umma_supported(B, C, H, W, D)) return corr_umma_launch(L, R, cost, B, C, H, W, D, as_stream(stream));
+    if (corr_umma_supported(B, C, H, W, D)) return corr_umma_launch(L, R, cost, B, C, H, W, D, false, as_stream(stream));
     const int n_wtiles = ceil_div(W, kTW), n_dtiles = ceil_div(D, kTD);
     const dim3 grid(n_wtiles * n_dtiles, H, B);
     if (W % 4 == 0 && aligned16(L) && aligned16(R) && aligned16(cost))
@@ -373,6 +373,14 @@ extern "C" int aanet_corr_fwd(const float *L, const float *R, float *cost, int B
     else
         corr_fwd_kernel<<<grid, kCorrThreads, 0, as_stream(stream)>>>(L, R, cost, C, H, W, D, n_wtiles);
     return check_launch();
+}
+
+extern "C" int aanet_corr_fwd_nhwc(const float *L, const float *R, float *cost, int B, int C, int H, int W, int D,
+                                   void *stream) {
+    if (!L || !R || !cost) return AANET_ERR_NULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || D <= 0) return AANET_ERR_SHAPE;
+    if (!corr_umma_supported(B, C, H, W, D)) return AANET_ERR_UNSUPPORTED;
+    return corr_umma_launch(L, R, cost, B, C, H, W, D, true, as_stream(stream));
 }
 
 extern "C" int aanet_corr_fwd_bf16(const void *L, const void *R, float *cost, int B, int C, int H, int W, int D,

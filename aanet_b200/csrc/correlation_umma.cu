@@ -26,7 +26,9 @@ constexpr int kCuM = 128;          // w per CTA (UMMA M)
 constexpr int kCuThreads = 256;
 constexpr int kCuTmemCols = 256;   // one accumulator of N <= 256 columns; two CTAs per SM
 
-template <int N>
+// NHWC = false: cost is [B,D,H,W] (the reference's layout); true: channels-last [B,H,W,D] for the fused aggregation
+// executor (D % 4 == 0), which saves the layout kernel in front of the first 1x1 convolution.
+template <int N, bool NHWC>
 __global__ void __launch_bounds__(kCuThreads, 2)
 corr_umma_kernel(const float *__restrict__ L, const float *__restrict__ R, float *__restrict__ cost, int C, int H,
                  int W, int D) {
@@ -153,7 +155,7 @@ corr_umma_kernel(const float *__restrict__ L, const float *__restrict__ R, float
     }
     umma::tc_fence_before();
     __syncthreads();
-    {
+    if (!NHWC) {
         const float inv = 1.f / (float)C;
         const int w = w0 + m;
         if (w < W) {
@@ -161,6 +163,26 @@ corr_umma_kernel(const float *__restrict__ L, const float *__restrict__ R, float
             for (int d = half; d < D; d += 2) {
                 const float v = stage[m * kPitch + lane + Dp - d];
                 orow[(long)d * HW] = (w >= d) ? v * inv : 0.f;
+            }
+        }
+    } else {
+        // channels-last: the D values of a pixel are contiguous.  16 lanes x float4 cover 64 disparities of one pixel
+        // (two pixels per instruction); a warp takes 16 of its quarter's 32 pixels.
+        const float inv = 1.f / (float)C;
+        const int sub = lane >> 4, l16 = lane & 15;
+        for (int it = 0; it < 8; ++it) {
+            const int pl = half * 16 + it * 2 + sub;          // pixel within the quarter (= its lane index in stage)
+            const int mm = q * 32 + pl, w = w0 + mm;
+            if (w >= W) continue;
+            float *orow = cost + (((long)b * H + h) * W + w) * D;
+            for (int d = l16 * 4; d < D; d += 64) {
+                const float *sp = stage + mm * kPitch + pl + Dp - d;
+                float4 o;
+                o.x = (w >= d) ? sp[0] * inv : 0.f;
+                o.y = (w >= d + 1) ? sp[-1] * inv : 0.f;
+                o.z = (w >= d + 2) ? sp[-2] * inv : 0.f;
+                o.w = (w >= d + 3) ? sp[-3] * inv : 0.f;
+                *reinterpret_cast<float4 *>(orow + d) = o;
             }
         }
     }
@@ -173,11 +195,16 @@ corr_umma_kernel(const float *__restrict__ L, const float *__restrict__ R, float
 
 template <int N>
 static int launch_corr_umma(const float *L, const float *R, float *cost, int B, int C, int H, int W, int D,
-                            cudaStream_t stream) {
+                            bool nhwc, cudaStream_t stream) {
     constexpr size_t smem = 2 * (kCuM * 32 * 4) + 2 * (N * 32 * 4) + 1024;
-    cudaFuncSetAttribute(corr_umma_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const dim3 grid(ceil_div(W, kCuM), H, B);
-    corr_umma_kernel<N><<<grid, kCuThreads, smem, stream>>>(L, R, cost, C, H, W, D);
+    if (nhwc) {
+        cudaFuncSetAttribute(corr_umma_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        corr_umma_kernel<N, true><<<grid, kCuThreads, smem, stream>>>(L, R, cost, C, H, W, D);
+    } else {
+        cudaFuncSetAttribute(corr_umma_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        corr_umma_kernel<N, false><<<grid, kCuThreads, smem, stream>>>(L, R, cost, C, H, W, D);
+    }
     return check_launch();
 }
 
@@ -185,13 +212,14 @@ bool corr_umma_supported(int B, int C, int H, int W, int D) {
     return D <= 128 && H <= 65535 && B <= 65535 && (long)C * H * W < 0x7fffffffL;
 }
 
-int corr_umma_launch(const float *L, const float *R, float *cost, int B, int C, int H, int W, int D,
+int corr_umma_launch(const float *L, const float *R, float *cost, int B, int C, int H, int W, int D, bool nhwc,
                      cudaStream_t stream) {
-    if (D <= 16) return launch_corr_umma<144>(L, R, cost, B, C, H, W, D, stream);
-    if (D <= 32) return launch_corr_umma<160>(L, R, cost, B, C, H, W, D, stream);
-    if (D <= 64) return launch_corr_umma<192>(L, R, cost, B, C, H, W, D, stream);
-    if (D <= 96) return launch_corr_umma<224>(L, R, cost, B, C, H, W, D, stream);
-    return launch_corr_umma<256>(L, R, cost, B, C, H, W, D, stream);
+    if (nhwc && (D % 4 || !aligned16(cost))) return AANET_ERR_UNSUPPORTED;
+    if (D <= 16) return launch_corr_umma<144>(L, R, cost, B, C, H, W, D, nhwc, stream);
+    if (D <= 32) return launch_corr_umma<160>(L, R, cost, B, C, H, W, D, nhwc, stream);
+    if (D <= 64) return launch_corr_umma<192>(L, R, cost, B, C, H, W, D, nhwc, stream);
+    if (D <= 96) return launch_corr_umma<224>(L, R, cost, B, C, H, W, D, nhwc, stream);
+    return launch_corr_umma<256>(L, R, cost, B, C, H, W, D, nhwc, stream);
 }
 
 }  // namespace aanet

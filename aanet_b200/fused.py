@@ -132,7 +132,9 @@ class FusedAggregation:
             self.stages.append((branches, fuse, mod.relu.negative_slope))
         self.final = [_Conv(c) for c in agg.final_conv]
 
-    def __call__(self, cost_volume):
+    def __call__(self, cost_volume, nhwc=False):
+        """cost_volume: the pyramid of volumes, [B,D,H,W] each -- or already channels-last [B,H,W,D] (nhwc=True,
+        ops.correlation_nhwc), which saves the three layout kernels."""
         dev = cost_volume[0].device
         keep = []                       # every intermediate stays alive until the final join (streams.py)
 
@@ -148,7 +150,10 @@ class FusedAggregation:
                 return y
             return go
 
-        xs = fork_join(dev, [(lambda c=c: track(ops.nchw_to_nhwc(c))) for c in cost_volume])
+        if nhwc:
+            xs = list(cost_volume)
+        else:
+            xs = fork_join(dev, [(lambda c=c: track(ops.nchw_to_nhwc(c))) for c in cost_volume])
         for branches, fuse, slope in self.stages:
             # ISA: the scales are independent -> one stream each
             xs = fork_join(dev, [branch(s, blocks, xs[s]) for s, blocks in enumerate(branches)])
@@ -184,9 +189,9 @@ class FusedAggregation:
         return outs
 
 
-def run(agg, cost_volume):
+def run(agg, cost_volume, nhwc=False):
     fused = getattr(agg, "_aanet_fused", None)
     if fused is None or fused.key != _state_key(agg):
         fused = FusedAggregation(agg)
         agg._aanet_fused = fused
-    return fused(cost_volume)
+    return fused(cost_volume, nhwc)

@@ -77,6 +77,21 @@ def correlation(left, right, max_disp):
     return _Correlation.apply(left, right, int(max_disp))
 
 
+def correlation_nhwc(left, right, max_disp):
+    """The same volume written channels-last, [B,H,W,D], for the fused aggregation executor (inference only;
+    needs max_disp % 4 == 0 and max_disp <= 128 -- AanetError otherwise)."""
+    left, right = _prep(left, "correlation_nhwc"), _prep(right, "correlation_nhwc")
+    if left.shape != right.shape or left.dim() != 4:
+        raise ValueError("correlation_nhwc: left/right must be [B,C,H,W] tensors of equal shape")
+    B, C, H, W = left.shape
+    out = left.new_empty(B, H, W, int(max_disp))
+    with torch.cuda.device(left.device):
+        _lib.check(_lib.load().aanet_corr_fwd_nhwc(_ptr(left), _ptr(right), _ptr(out), B, C, H, W, int(max_disp),
+                                                   _stream(left)), "aanet_corr_fwd_nhwc")
+    _count()
+    return out
+
+
 def correlation_bf16(left, right, max_disp):
     """BASELINE config 5 variant: bf16 features, fp32 accumulation and fp32 volume (no autograd)."""
     if not left.is_cuda:

@@ -14,7 +14,10 @@ import os
 import torch
 import torch.nn as nn
 
+from . import fused, ops
 from .nets import AdaptiveAggregation, CostVolumePyramid, DisparityEstimation
+from .nets.deform import _inference_mode
+from .streams import fork_join
 
 
 @contextlib.contextmanager
@@ -46,8 +49,18 @@ class HotPath(nn.Module):
         self.max_pairs_per_pass = None                      # None: derived from free device memory
 
     def _one_pass(self, left_pyramid, right_pyramid):
-        cost = self.cost_volume(list(left_pyramid), list(right_pyramid))
-        agg = self.aggregation(cost)
+        agg_mod = self.aggregation
+        D = [self.max_disp // 2 ** s for s in range(len(left_pyramid))]
+        if (agg_mod.use_fused_inference and _inference_mode(agg_mod) and left_pyramid[0].is_cuda
+                and left_pyramid[0].dtype == torch.float32 and all(d % 4 == 0 and 0 < d <= 128 for d in D)
+                and fused.supported(agg_mod)):
+            # fused inference: the correlation writes channels-last volumes straight into the executor's layout
+            cost = fork_join(left_pyramid[0].device,
+                             [(lambda l=l, r=r, d=d: ops.correlation_nhwc(l, r, d))
+                              for l, r, d in zip(left_pyramid, right_pyramid, D)])
+            agg = fused.run(agg_mod, cost, nhwc=True)
+        else:
+            agg = agg_mod(self.cost_volume(list(left_pyramid), list(right_pyramid)))
         return [self.disparity_estimation(a) for a in reversed(agg)]
 
     def pairs_per_pass(self, left_pyramid):

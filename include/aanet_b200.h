@@ -56,6 +56,11 @@ AANET_API const char *aanet_last_cuda_error(void);
 AANET_API int aanet_corr_fwd(const float *L, const float *R, float *cost,
                    int B, int C, int H, int W, int D, void *stream);
 
+/* Same volume written channels-last, cost: [B,H,W,D] (D % 4 == 0, D <= 128), for the fused aggregation executor:
+ * its first 1x1 convolutions read channels-last activations.  AANET_ERR_UNSUPPORTED otherwise. */
+AANET_API int aanet_corr_fwd_nhwc(const float *L, const float *R, float *cost, int B, int C, int H, int W, int D,
+                                  void *stream);
+
 /* bf16-feature variant (BASELINE config 5): L, R are bfloat16 [B,C,H,W]; products, channel sum and the
  * volume stay fp32.  Not bit-comparable with the reference (features are rounded to 8 mantissa bits); the
  * tests state the resulting end-point error.  Requires W % 8 == 0 (else AANET_ERR_UNSUPPORTED).  Inference

@@ -456,3 +456,20 @@ def test_refine_frontend_full_size_vs_oracle_and_torch(ops):
     assert np.abs(npy(concat) - rc).max() < 1e-2 and np.abs(npy(concat) - rc).mean() < 1e-4
     with pytest.raises(RuntimeError):
         ops.refine_frontend(low[:, :100], left[..., :416].contiguous(), right[..., :416].contiguous())   # W == w, H != h
+
+
+@pytest.mark.parametrize("shape", [(1, 128, 3, 416, 64), (2, 32, 2, 208, 32), (1, 16, 2, 104, 16), (1, 20, 3, 131, 96),
+                                   (1, 8, 2, 300, 128), (1, 12, 2, 70, 4)])
+def test_corr_nhwc_equals_nchw(ops, shape):
+    """Channels-last volume of the fused path == the reference-layout volume, element for element."""
+    B, C, H, W, D = shape
+    torch.manual_seed(5)
+    L = torch.relu(torch.randn(B, C, H, W, device="cuda"))
+    R = torch.relu(torch.randn(B, C, H, W, device="cuda"))
+    a = ops.correlation(L, R, D)
+    b = ops.correlation_nhwc(L, R, D)
+    assert b.shape == (B, H, W, D) and torch.equal(b.permute(0, 3, 1, 2), a)
+    with pytest.raises(RuntimeError):
+        ops.correlation_nhwc(L, R, 130)
+    with pytest.raises(RuntimeError):
+        ops.correlation_nhwc(L, R, 6)
