@@ -198,7 +198,10 @@ __device__ __forceinline__ void tile_row(const ConvParams &p, int ti, int r, int
 
 // MULTI = false: one problem, its descriptor stays in the constant bank (operands come straight from c[][]);
 // MULTI = true: up to kMaxProblems descriptors staged in shared memory and selected per tile.
-template <int BN, bool DEFORM, bool MULTI>
+// RES = false: no problem of the launch has a residual input; the epilogue then does not carry the 16 residual
+// registers per 16-channel step (with them in every instantiation all launches were 4-5 % slower: 916 vs 960 pairs/s
+// in an experiment that compiled the residual path out).
+template <int BN, bool DEFORM, bool MULTI, bool RES>
 __global__ void __launch_bounds__(kUThreads, 1)
 conv_umma_kernel(const __grid_constant__ ConvBatch B) {
     using Cfg = EngineCfg<BN>;
@@ -539,7 +542,7 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
                 const bool live = p_ok && n0 < n_valid;
                 const bool full = vec_ok && n0 + 16 <= n_valid;
                 float res[16];
-                if (p.residual && live) {                  // issue the residual loads before the TMEM read
+                if (RES && p.residual && live) {           // issue the residual loads before the TMEM read
                     if (full) {
                         const float4 *rp = reinterpret_cast<const float4 *>(p.residual + pix_g * d.Cout + o_base + n0);
 #pragma unroll
@@ -574,7 +577,7 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
                     acc[i] = fmaf(acc[i], sc.x, sh.x); acc[i + 1] = fmaf(acc[i + 1], sc.y, sh.y);
                     acc[i + 2] = fmaf(acc[i + 2], sc.z, sh.z); acc[i + 3] = fmaf(acc[i + 3], sc.w, sh.w);
                 }
-                if (p.residual) {
+                if (RES && p.residual) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) acc[i] += res[i];
                 }
@@ -746,10 +749,10 @@ int conv_umma_transpose(const float *src, float *dst, int B, int R, long Cc, cud
     return launch_pdl(transpose_kernel, grid, dim3(256), 0, stream, src, dst, R, Cc);
 }
 
-template <int BN, bool DEFORM, bool MULTI>
+template <int BN, bool DEFORM, bool MULTI, bool RES>
 static int launch_inst(const ConvBatch &batch, cudaStream_t stream) {
     constexpr size_t smem = EngineCfg<BN>::kSmemBytes;
-    cudaFuncSetAttribute(conv_umma_kernel<BN, DEFORM, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(conv_umma_kernel<BN, DEFORM, MULTI, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     // Persistent grid: the fewest CTAs that still finish in ceil(tiles / #SMs) rounds (416 tiles -> 139 CTAs x 3
     // tiles instead of 148 CTAs of which 28 would idle in the last round): the SMs left free run the coarse-scale
     // kernels that the fused executor issues on parallel streams.
@@ -757,12 +760,16 @@ static int launch_inst(const ConvBatch &batch, cudaStream_t stream) {
     const int grid = ceil_div(batch.total_tiles, rounds);
     // Programmatic dependent launch: consecutive engine kernels of a stream overlap launch latency and prologue
     // with the predecessor's last epilogue (see pdl_wait / pdl_trigger in the kernel).
-    return launch_pdl(conv_umma_kernel<BN, DEFORM, MULTI>, dim3(grid), dim3(kUThreads), smem, stream, batch);
+    return launch_pdl(conv_umma_kernel<BN, DEFORM, MULTI, RES>, dim3(grid), dim3(kUThreads), smem, stream, batch);
 }
 
 template <int BN, bool DEFORM>
 static int launch_one(const ConvBatch &batch, cudaStream_t stream) {
-    return batch.n > 1 ? launch_inst<BN, DEFORM, true>(batch, stream) : launch_inst<BN, DEFORM, false>(batch, stream);
+    bool res = false;
+    for (int i = 0; i < batch.n; ++i) res |= batch.pr[i].residual != nullptr;
+    if (batch.n > 1)
+        return res ? launch_inst<BN, DEFORM, true, true>(batch, stream) : launch_inst<BN, DEFORM, true, false>(batch, stream);
+    return res ? launch_inst<BN, DEFORM, false, true>(batch, stream) : launch_inst<BN, DEFORM, false, false>(batch, stream);
 }
 
 #ifdef AANET_PROFILE
