@@ -201,7 +201,10 @@ __device__ __forceinline__ void tile_row(const ConvParams &p, int ti, int r, int
 // RES = false: no problem of the launch has a residual input; the epilogue then does not carry the 16 residual
 // registers per 16-channel step (with them in every instantiation all launches were 4-5 % slower: 916 vs 960 pairs/s
 // in an experiment that compiled the residual path out).
-template <int BN, bool DEFORM, bool MULTI, bool RES>
+// LEAN = true: every problem of the launch writes channels-last, has a multiple of 16 output channels per group and
+// no offset/mask head, so the epilogue only needs its 128-bit store path (the NCHW / ragged / sigmoid branches are
+// compiled out: 923 vs 942 pairs/s in an experiment that removed them everywhere).
+template <int BN, bool DEFORM, bool MULTI, bool RES, bool LEAN>
 __global__ void __launch_bounds__(kUThreads, 1)
 conv_umma_kernel(const __grid_constant__ ConvBatch B) {
     using Cfg = EngineCfg<BN>;
@@ -540,7 +543,7 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
 #pragma unroll 1
             for (int n0 = 0; n0 < BN; n0 += 16) {
                 const bool live = p_ok && n0 < n_valid;
-                const bool full = vec_ok && n0 + 16 <= n_valid;
+                const bool full = LEAN || (vec_ok && n0 + 16 <= n_valid);
                 float res[16];
                 if (RES && p.residual && live) {           // issue the residual loads before the TMEM read
                     if (full) {
@@ -550,7 +553,7 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
                             const float4 r4 = __ldg(rp + i);
                             res[4 * i] = r4.x; res[4 * i + 1] = r4.y; res[4 * i + 2] = r4.z; res[4 * i + 3] = r4.w;
                         }
-                    } else {
+                    } else if (!LEAN) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const int o = o_base + n0 + i;
@@ -587,7 +590,7 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
                 } else if (p.act == ACT_LEAKY) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) acc[i] = acc[i] > 0.f ? acc[i] : acc[i] * p.slope;
-                } else if (p.act == ACT_OFFSET_MASK) {
+                } else if (!LEAN && p.act == ACT_OFFSET_MASK) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
                         if (o_base + n0 + i >= p.n_offset_ch) acc[i] = __fdividef(p.mask_scale, 1.f + __expf(-acc[i]));
@@ -597,11 +600,11 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
-                } else if (p.out_nchw) {
+                } else if (!LEAN && p.out_nchw) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
                         if (n0 + i < n_valid) p.out[((long)tc.b * d.Cout + o_base + n0 + i) * d.P + pix] = acc[i];
-                } else {
+                } else if (!LEAN) {
                     float *dst = p.out + pix_g * d.Cout + o_base + n0;
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
@@ -749,10 +752,11 @@ int conv_umma_transpose(const float *src, float *dst, int B, int R, long Cc, cud
     return launch_pdl(transpose_kernel, grid, dim3(256), 0, stream, src, dst, R, Cc);
 }
 
-template <int BN, bool DEFORM, bool MULTI, bool RES>
+template <int BN, bool DEFORM, bool MULTI, bool RES, bool LEAN>
 static int launch_inst(const ConvBatch &batch, cudaStream_t stream) {
     constexpr size_t smem = EngineCfg<BN>::kSmemBytes;
-    cudaFuncSetAttribute(conv_umma_kernel<BN, DEFORM, MULTI, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(conv_umma_kernel<BN, DEFORM, MULTI, RES, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
     // Persistent grid: the fewest CTAs that still finish in ceil(tiles / #SMs) rounds (416 tiles -> 139 CTAs x 3
     // tiles instead of 148 CTAs of which 28 would idle in the last round): the SMs left free run the coarse-scale
     // kernels that the fused executor issues on parallel streams.
@@ -760,16 +764,28 @@ static int launch_inst(const ConvBatch &batch, cudaStream_t stream) {
     const int grid = ceil_div(batch.total_tiles, rounds);
     // Programmatic dependent launch: consecutive engine kernels of a stream overlap launch latency and prologue
     // with the predecessor's last epilogue (see pdl_wait / pdl_trigger in the kernel).
-    return launch_pdl(conv_umma_kernel<BN, DEFORM, MULTI, RES>, dim3(grid), dim3(kUThreads), smem, stream, batch);
+    return launch_pdl(conv_umma_kernel<BN, DEFORM, MULTI, RES, LEAN>, dim3(grid), dim3(kUThreads), smem, stream, batch);
+}
+
+template <int BN, bool DEFORM, bool MULTI, bool RES>
+static int launch_lean(const ConvBatch &batch, bool lean, cudaStream_t stream) {
+    return lean ? launch_inst<BN, DEFORM, MULTI, RES, true>(batch, stream)
+                : launch_inst<BN, DEFORM, MULTI, RES, false>(batch, stream);
 }
 
 template <int BN, bool DEFORM>
 static int launch_one(const ConvBatch &batch, cudaStream_t stream) {
-    bool res = false;
-    for (int i = 0; i < batch.n; ++i) res |= batch.pr[i].residual != nullptr;
+    bool res = false, lean = true;
+    for (int i = 0; i < batch.n; ++i) {
+        const ConvParams &p = batch.pr[i];
+        res |= p.residual != nullptr;
+        lean &= !p.out_nchw && p.act != ACT_OFFSET_MASK && p.d.Og % 16 == 0 && (p.d.Cout & 3) == 0;
+    }
     if (batch.n > 1)
-        return res ? launch_inst<BN, DEFORM, true, true>(batch, stream) : launch_inst<BN, DEFORM, true, false>(batch, stream);
-    return res ? launch_inst<BN, DEFORM, false, true>(batch, stream) : launch_inst<BN, DEFORM, false, false>(batch, stream);
+        return res ? launch_lean<BN, DEFORM, true, true>(batch, lean, stream)
+                   : launch_lean<BN, DEFORM, true, false>(batch, lean, stream);
+    return res ? launch_lean<BN, DEFORM, false, true>(batch, lean, stream)
+               : launch_lean<BN, DEFORM, false, false>(batch, lean, stream);
 }
 
 #ifdef AANET_PROFILE
