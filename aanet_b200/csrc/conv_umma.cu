@@ -204,9 +204,13 @@ __device__ __forceinline__ void tile_row(const ConvParams &p, int ti, int r, int
 // LEAN = true: every problem of the launch writes channels-last, has a multiple of 16 output channels per group and
 // no offset/mask head, so the epilogue only needs its 128-bit store path (the NCHW / ragged / sigmoid branches are
 // compiled out: 923 vs 942 pairs/s in an experiment that removed them everywhere).
-template <int BN, bool DEFORM, bool MULTI, bool RES, bool LEAN>
+// MODE: 0 = DENSE, 1 = DEFORM, 2 = DEFORM where every K block is one (tap, deformable group) run (channels per
+// conv group and per deformable group both multiples of 32: the ISA layers of the 1/3 scale) -- the producer then
+// carries one bilinear sample per lane instead of two and has no general path.
+template <int BN, int MODE, bool MULTI, bool RES, bool LEAN>
 __global__ void __launch_bounds__(kUThreads, 1)
 conv_umma_kernel(const __grid_constant__ ConvBatch B) {
+    constexpr bool DEFORM = MODE != 0, SINGLE_RUN = MODE == 2;
     using Cfg = EngineCfg<BN>;
     constexpr int S = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -395,7 +399,7 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
                     store_row(u, v);
                 }
             } else {
-                const uint8_t info = s_kbinfo[p.tbl_off + kb];
+                const uint8_t info = SINGLE_RUN ? (uint8_t)(16 | 8) : s_kbinfo[p.tbl_off + kb];
                 const int split = info & 15;
                 const float *off_b = p.offset + (long)tc.b * p.off_bs;
                 const float *mask_b = p.mask ? p.mask + (long)tc.b * p.mask_bs : nullptr;
@@ -752,10 +756,10 @@ int conv_umma_transpose(const float *src, float *dst, int B, int R, long Cc, cud
     return launch_pdl(transpose_kernel, grid, dim3(256), 0, stream, src, dst, R, Cc);
 }
 
-template <int BN, bool DEFORM, bool MULTI, bool RES, bool LEAN>
+template <int BN, int MODE, bool MULTI, bool RES, bool LEAN>
 static int launch_inst(const ConvBatch &batch, cudaStream_t stream) {
     constexpr size_t smem = EngineCfg<BN>::kSmemBytes;
-    cudaFuncSetAttribute(conv_umma_kernel<BN, DEFORM, MULTI, RES, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(conv_umma_kernel<BN, MODE, MULTI, RES, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)smem);
     // Persistent grid: the fewest CTAs that still finish in ceil(tiles / #SMs) rounds (416 tiles -> 139 CTAs x 3
     // tiles instead of 148 CTAs of which 28 would idle in the last round): the SMs left free run the coarse-scale
@@ -764,16 +768,16 @@ static int launch_inst(const ConvBatch &batch, cudaStream_t stream) {
     const int grid = ceil_div(batch.total_tiles, rounds);
     // Programmatic dependent launch: consecutive engine kernels of a stream overlap launch latency and prologue
     // with the predecessor's last epilogue (see pdl_wait / pdl_trigger in the kernel).
-    return launch_pdl(conv_umma_kernel<BN, DEFORM, MULTI, RES, LEAN>, dim3(grid), dim3(kUThreads), smem, stream, batch);
+    return launch_pdl(conv_umma_kernel<BN, MODE, MULTI, RES, LEAN>, dim3(grid), dim3(kUThreads), smem, stream, batch);
 }
 
-template <int BN, bool DEFORM, bool MULTI, bool RES>
+template <int BN, int MODE, bool MULTI, bool RES>
 static int launch_lean(const ConvBatch &batch, bool lean, cudaStream_t stream) {
-    return lean ? launch_inst<BN, DEFORM, MULTI, RES, true>(batch, stream)
-                : launch_inst<BN, DEFORM, MULTI, RES, false>(batch, stream);
+    return lean ? launch_inst<BN, MODE, MULTI, RES, true>(batch, stream)
+                : launch_inst<BN, MODE, MULTI, RES, false>(batch, stream);
 }
 
-template <int BN, bool DEFORM>
+template <int BN, int MODE>
 static int launch_one(const ConvBatch &batch, cudaStream_t stream) {
     bool res = false, lean = true;
     for (int i = 0; i < batch.n; ++i) {
@@ -782,10 +786,10 @@ static int launch_one(const ConvBatch &batch, cudaStream_t stream) {
         lean &= !p.out_nchw && p.act != ACT_OFFSET_MASK && p.d.Og % 16 == 0 && (p.d.Cout & 3) == 0;
     }
     if (batch.n > 1)
-        return res ? launch_lean<BN, DEFORM, true, true>(batch, lean, stream)
-                   : launch_lean<BN, DEFORM, true, false>(batch, lean, stream);
-    return res ? launch_lean<BN, DEFORM, false, true>(batch, lean, stream)
-               : launch_lean<BN, DEFORM, false, false>(batch, lean, stream);
+        return res ? launch_lean<BN, MODE, true, true>(batch, lean, stream)
+                   : launch_lean<BN, MODE, true, false>(batch, lean, stream);
+    return res ? launch_lean<BN, MODE, false, true>(batch, lean, stream)
+               : launch_lean<BN, MODE, false, false>(batch, lean, stream);
 }
 
 #ifdef AANET_PROFILE
@@ -828,9 +832,12 @@ int conv_umma_launch_batch(const ConvParams *probs, int n, bool deform, int bn, 
     }
     if (tbl > kMaxKB) return AANET_ERR_UNSUPPORTED;
     batch.total_tiles = (int)tiles;
+    bool single_run = deform;                  // every K block = 32 channels of one tap inside one deformable group
+    for (int i = 0; i < n; ++i) single_run &= batch.pr[i].d.Cg % kUK == 0 && batch.pr[i].d.Cd % kUK == 0;
 #define AANET_CONV_CASE(b)                                                              \
     case b:                                                                              \
-        return deform ? launch_one<b, true>(batch, stream) : launch_one<b, false>(batch, stream);
+        return !deform ? launch_one<b, 0>(batch, stream)                                 \
+                       : single_run ? launch_one<b, 2>(batch, stream) : launch_one<b, 1>(batch, stream);
     switch (BN) {
         AANET_CONV_CASE(16)
         AANET_CONV_CASE(32)
