@@ -180,7 +180,15 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvParams *pr, int n, int
 // Output pixel of row r (0..127) of tile `ti` of an image: 1-D tiles are 128 consecutive pixels (contiguous
 // channels-last input/output: best for 1x1 convolutions), 2-D tiles are 16 x 8 patches whose gather footprint
 // over all taps fits L1.  Out-of-range rows are clamped to a valid pixel and flagged.
+template <bool POINTWISE = false>
 __device__ __forceinline__ void tile_row(const ConvParams &p, int ti, int r, int &oh, int &ow, bool &ok) {
+    if (POINTWISE) {              // 1-D tiles only: the image is one row of P pixels, no divisions
+        const int px = ti * kUM + r, P32 = (int)p.d.P;
+        ok = px < P32;
+        oh = 0;
+        ow = ok ? px : P32 - 1;
+        return;
+    }
     if (p.tile2d) {
         const int ty = ti / p.tiles_x, tx = ti - ty * p.tiles_x;
         oh = ty * kTileH + (r >> 4);
@@ -206,11 +214,12 @@ __device__ __forceinline__ void tile_row(const ConvParams &p, int ti, int r, int
 // compiled out: 923 vs 942 pairs/s in an experiment that removed them everywhere).
 // MODE: 0 = DENSE, 1 = DEFORM, 2 = DEFORM where every K block is one (tap, deformable group) run (channels per
 // conv group and per deformable group both multiples of 32: the ISA layers of the 1/3 scale) -- the producer then
-// carries one bilinear sample per lane instead of two and has no general path.
+// carries one bilinear sample per lane instead of two and has no general path; 3 = DENSE with 1-D tiles only
+// (1x1 / stride 1 / pad 0 convolutions: a third of the launches), no 2-D tile arithmetic anywhere.
 template <int BN, int MODE, bool MULTI, bool RES, bool LEAN>
 __global__ void __launch_bounds__(kUThreads, 1)
 conv_umma_kernel(const __grid_constant__ ConvBatch B) {
-    constexpr bool DEFORM = MODE != 0, SINGLE_RUN = MODE == 2;
+    constexpr bool DEFORM = MODE == 1 || MODE == 2, SINGLE_RUN = MODE == 2, POINTWISE = MODE == 3;
     using Cfg = EngineCfg<BN>;
     constexpr int S = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -335,7 +344,7 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
         auto enter_tile = [&](const ConvParams &p) {
             if (DEFORM) {                              // coordinates of the row this lane owns
                 tile_row(p, tc.p0, row0 + j, my_oh, my_ow, my_ok);
-            } else if (p.tile2d) {                     // rows row0..row0+7 = 8 consecutive pixels of one tile row
+            } else if (!POINTWISE && p.tile2d) {       // rows row0..row0+7 = 8 consecutive pixels of one tile row
                 const int ty = tc.p0 / p.tiles_x, tx = tc.p0 - ty * p.tiles_x;
                 g_oh = ty * kTileH + (row0 >> 4);
                 g_ow0 = tx * kTileW + (row0 & 15);
@@ -372,7 +381,7 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
                 const float *base;
                 int step, w0, wlim;
                 bool row_ok;
-                if (p.tile2d) {
+                if (!POINTWISE && p.tile2d) {
                     const int hi_ = g_oh * d.stride - d.pad + ki * d.dil;
                     w0 = g_ow0 * d.stride - d.pad + kj * d.dil;
                     row_ok = k_ok && (unsigned)hi_ < (unsigned)d.H;
@@ -519,8 +528,8 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
             const int a = ti & 1;
             int e_oh, e_ow;
             bool p_ok;
-            tile_row(p, tc.p0, row, e_oh, e_ow, p_ok);
-            const int pix = e_oh * d.Wo + e_ow;
+            tile_row<POINTWISE>(p, tc.p0, row, e_oh, e_ow, p_ok);
+            const int pix = POINTWISE ? e_ow : e_oh * d.Wo + e_ow;
             const int o_base = tc.grp * d.Og + tc.nt * BN;          // first global out channel of the tile
             const int n_valid = min(BN, d.Og - tc.nt * BN);
             if ((tc.pi << 20) + tc.grp * p.n_tiles_n + tc.nt != cur_gn) {
@@ -832,11 +841,13 @@ int conv_umma_launch_batch(const ConvParams *probs, int n, bool deform, int bn, 
     }
     if (tbl > kMaxKB) return AANET_ERR_UNSUPPORTED;
     batch.total_tiles = (int)tiles;
+    bool pointwise = !deform;                  // only 1-D tiles in the launch
+    for (int i = 0; i < n; ++i) pointwise &= batch.pr[i].tile2d == 0;
     bool single_run = deform;                  // every K block = 32 channels of one tap inside one deformable group
     for (int i = 0; i < n; ++i) single_run &= batch.pr[i].d.Cg % kUK == 0 && batch.pr[i].d.Cd % kUK == 0;
 #define AANET_CONV_CASE(b)                                                              \
     case b:                                                                              \
-        return !deform ? launch_one<b, 0>(batch, stream)                                 \
+        return !deform ? (pointwise ? launch_one<b, 3>(batch, stream) : launch_one<b, 0>(batch, stream)) \
                        : single_run ? launch_one<b, 2>(batch, stream) : launch_one<b, 1>(batch, stream);
     switch (BN) {
         AANET_CONV_CASE(16)
