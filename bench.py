@@ -35,7 +35,7 @@ UNIT = "pairs/s"
 N_SETS = 4      # rotating input sets: 4 x 71.6 MB > 126 MB L2
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
 # (profiles/), MB; None until a capture of the current kernel exists.
-NCU_TRAFFIC_MB = {"mdconv": 27.6}   # profiles/r01_launches_and_engine.md: 25.52 MB read + 2.05 MB written
+NCU_TRAFFIC_MB = {"mdconv": 25.5}   # profiles/r01_launches_and_engine.md: 25.49 MB read + 0.0003 MB written
 
 
 def pyramid_shapes(batch):

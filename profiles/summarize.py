@@ -40,6 +40,12 @@ def kernel_table(path, n=24):
     rows = list(csv.reader(open(path)))
     h = rows[0]
     ix = h.index
+    units = rows[1]                 # ncu picks a unit per column (byte / Kbyte / Mbyte ...): normalise bytes to MB
+    to_mb = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
+
+    def value(r, c):
+        v = float(r[ix(c)].replace(",", ""))
+        return v * to_mb.get(units[ix(c)], 1.0) if "bytes" in c else v
     cols = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "l1tex__t_sector_hit_rate.pct",
             "lts__t_sector_hit_rate.pct", "sm__warps_active.avg.pct_of_peak_sustained_active",
             "sm__inst_issued.avg.pct_of_peak_sustained_active"]
@@ -47,7 +53,7 @@ def kernel_table(path, n=24):
     print("|---|---|---|---|---|---|---|---|---|---|")
     for r in rows[2:2 + n]:
         g = eval(r[ix("Grid Size")])
-        vals = ["%.2f" % float(r[ix(c)].replace(",", "")) for c in cols]
+        vals = ["%.2f" % value(r, c) for c in cols]
         print("| `%s` | %d | %s | %s |" % (short(r[ix("Kernel Name")]), g[0] * g[1] * g[2], " | ".join(vals),
                                            r[ix("launch__registers_per_thread")]))
 
