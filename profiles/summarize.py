@@ -108,8 +108,8 @@ repo).  First 24 rows:
 
 Dominant kernel = 1/3-scale deformable conv `conv_umma_kernel<64, 2, 0, 0, 1>`: DRAM read %.2f MB + %.2f MB written per
 launch in this capture = %.1f MB (`traffic` in bench.py) against 38.9 MB algorithmic (x 13.6 + offsets/mask 11.5 +
-output 13.6).  The inputs are read once; how much of the output is written back during the kernel depends on what
-the 126 MB L2 evicts (captures of the same kernel ranged from 0.002 to 17.2 MB) -- there are no wasted re-reads.
+output 13.6).  The inputs are read once and the output stays in the 126 MB L2 for the consumer (write-back happens
+later, outside this kernel) -- there are no wasted re-reads.
 The kernel is latency-bound in its producers (ENGINE_NOTES.md: role profile, stage timing).
 """ % (head, b["ms_per_step"], b["value"], table, engine, deform, corr, fuse, b["roofline"]["us_per_launch"],
        100 * 3 * b["roofline"]["us_per_launch"] / (1e3 * b["ms_per_step"]), b["ms_per_step"],
