@@ -20,13 +20,21 @@ names = {0: "MMA thread total", 1: "producer: load+compute+store", 2: "producer:
 
 
 def run(tag, fn):
-    for _ in range(3):
+    for _ in range(2):
         fn()
     torch.cuda.synchronize()
-    buf = (ctypes.c_longlong * (148 * 16))()
-    assert lib.aanet_profile_read(buf) == 0
-    a = np.ctypeslib.as_array(buf).reshape(148, 16).astype(np.float64)
-    a = a[a[:, 11] > 0]
+    for m in range(4):                       # drop what the warm-up calls accumulated
+        getattr(lib, "aanet_profile_read_m%d" % m)((ctypes.c_longlong * (148 * 16))())
+    fn()
+    torch.cuda.synchronize()
+    # one counter array per engine translation unit (MODE 0..3); reading clears it, so only the unit whose kernels
+    # ran since the last read has tiles > 0
+    a = np.zeros((0, 16))
+    for m in range(4):
+        buf = (ctypes.c_longlong * (148 * 16))()
+        assert getattr(lib, "aanet_profile_read_m%d" % m)(buf) == 0
+        b = np.ctypeslib.as_array(buf).reshape(148, 16).astype(np.float64)
+        a = np.concatenate([a, b[b[:, 11] > 0]])
     print("%s  (%d CTAs, %.1f tiles/CTA)" % (tag, len(a), a[:, 11].mean()))
     for k in (0, 10, 8, 9, 7, 1, 2, 3, 4, 5, 6):
         print("   %-32s %9.0f cycles/CTA   %8.0f per tile" % (names[k], a[:, k].mean(), (a[:, k] / a[:, 11]).mean()))
