@@ -229,8 +229,10 @@ csa_fuse_tiled_kernel(CsaTerms t, CsaTile g, float *__restrict__ out, int H, int
     __syncthreads();
     // 3. outputs: item = (pixel of the tile, 16-byte chunk); consecutive threads = consecutive chunks of a pixel
     const int items = nh * kFuseTW * Cv;
+    // Cv a power of two (16 / 8 / 4 for the pyramid's 64 / 32 / 16 channels): item -> (pixel, chunk) by shift and mask
+    const int cshift = (Cv & (Cv - 1)) == 0 ? 31 - __clz(Cv) : -1;
     for (int i = tid; i < items; i += kFuseThreads) {
-        const int pix = i / Cv, cv = i - pix * Cv;
+        const int pix = cshift >= 0 ? i >> cshift : i / Cv, cv = i - pix * Cv;
         const int r = pix / kFuseTW, c = pix - r * kFuseTW;
         if (c >= nw) continue;
         const long opix = ((long)b * H + (h0 + r)) * W + (w0 + c);
