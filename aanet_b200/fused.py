@@ -13,7 +13,6 @@ path (torch convs + the same sm_100a operators) runs.
 """
 import os
 
-import torch
 import torch.nn as nn
 
 from . import ops

@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 import bench  # noqa: E402
-from aanet_b200 import fused, ops  # noqa: E402
+from aanet_b200 import ops  # noqa: E402
 from aanet_b200.streams import fork_join  # noqa: E402
 
 dev = torch.device("cuda:0")
