@@ -211,3 +211,11 @@ def test_batch_sharding_world2_gloo():
         assert out == expect and mx == 2.0
         sizes[rank] = n[0]
     assert sizes == {0: 3, 1: 2}
+
+
+def test_build_lists_every_cuda_source():
+    """Every .cu file in csrc/ is compiled into the library (a forgotten file would only show up at link time
+    on the GPU box) and every listed source exists."""
+    from aanet_b200 import build
+    have = sorted(f for f in os.listdir(build.CSRC) if f.endswith(".cu"))
+    assert sorted(build.SOURCES) == have
