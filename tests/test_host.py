@@ -219,3 +219,21 @@ def test_build_lists_every_cuda_source():
     from aanet_b200 import build
     have = sorted(f for f in os.listdir(build.CSRC) if f.endswith(".cu"))
     assert sorted(build.SOURCES) == have
+
+
+def test_committed_bench_line_has_contract_keys():
+    """The bench lines committed under profiles/ carry every key of the bench.py contract (both arms)."""
+    import json
+    line = json.loads(open(os.path.join(ROOT, "profiles", "bench_r01.json")).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in line, k
+    assert line["config"]["workload"] and line["gpu_launches"] > 0 and line["vs_baseline"] is None
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["value"] < line["value"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
+    assert abs(line["roofline"]["frac"] - line["roofline"]["achieved"] / line["roofline"]["peak"]) < 1e-9
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(line["cpu_baseline"])
+    ref = json.loads(open(os.path.join(ROOT, "profiles", "bench_reference_arm_r01.json")).read().strip().splitlines()[-1])
+    assert ref["impl"] == "reference" and ref["metric"] == line["metric"] and ref["unit"] == line["unit"]
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["value"] == ref["value"]
