@@ -209,12 +209,14 @@ def gen_csa():
     save("csa", **cases)
 
 
-def gen_aggregation(nets, cost_mod, est_mod):
+def gen_aggregation(nets, cost_mod, est_mod, cases_=(("agg", False, 16, 24, 36), ("agg_inter", True, 16, 24, 36))):
     """End-to-end hot path on a miniature pyramid: CostVolumePyramid -> AdaptiveAggregation
-    (6 modules, last 3 deformable, as nets/aanet.py:31,92-99 builds it) -> DisparityEstimation."""
+    (6 modules, last 3 deformable, as nets/aanet.py:31,92-99 builds it) -> DisparityEstimation.
+    `agg32` (D0 = 32: 32/16/8 channels, every count a multiple of 4 * deformable_groups) is the fixture that
+    reaches the channels-last tcgen05 executor (aanet_b200/fused.py: supported())."""
     from nets.aggregation import AdaptiveAggregation
-    for tag, inter in (("agg", False), ("agg_inter", True)):
-        D0, H, W, C = 16, 24, 36, 8
+    for tag, inter, D0, H, W in cases_:
+        C = 8
         agg = AdaptiveAggregation(max_disp=D0, num_scales=3, num_fusions=6, num_stage_blocks=1,
                                   num_deform_blocks=3, intermediate_supervision=inter,
                                   deformable_groups=2, mdconv_dilation=2).eval()
@@ -275,6 +277,10 @@ if __name__ == "__main__":
     nets = load_nets()
     if "--only-refinement" in sys.argv:     # added after the other fixtures were committed; own seed
         gen_refinement(nets)
+        sys.exit(0)
+    if "--only-agg32" in sys.argv:          # round 2: a reference-made fixture that reaches the fused executor
+        torch.manual_seed(328)
+        gen_aggregation(nets, cost_mod, est_mod, (("agg32", False, 32, 20, 28),))
         sys.exit(0)
     gen_corr(cost_mod)
     gen_softargmin(est_mod)

@@ -1,5 +1,7 @@
 """GPU tests of the drop-in modules (reference API) against golden outputs of the reference's own
 modules and against the CPU port (oracle/torch_port.py) at larger sizes."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -51,10 +53,11 @@ def test_deform_bottleneck_golden(golden, grad):
     assert rel_err(npy(out), z["blk_out"]) < 1e-4
 
 
-@pytest.mark.parametrize("name", ["agg", "agg_inter"])
+@pytest.mark.parametrize("name", ["agg", "agg_inter", "agg32"])
 @pytest.mark.parametrize("grad", [False, True])
 def test_hot_path_golden(golden, name, grad):
-    """CostVolumePyramid -> AdaptiveAggregation -> DisparityEstimation vs the reference's outputs."""
+    """CostVolumePyramid -> AdaptiveAggregation -> DisparityEstimation vs the reference's outputs.
+    agg32 (D0 = 32) with grad=False is the reference-made fixture that runs on the fused tcgen05 executor."""
     import aanet_b200.nets as n
     z = golden(name)
     D0, inter = int(z["D0"]), bool(z["inter"])
@@ -73,6 +76,8 @@ def test_hot_path_golden(golden, name, grad):
         est = n.DisparityEstimation(D0)
         disps = [est(o) for o in reversed(outs)]
     assert len(outs) == (3 if inter else 1)
+    if name == "agg32":
+        assert hasattr(agg, "_aanet_fused") == (not grad)      # the fused executor ran iff autograd was off
     for i, o in enumerate(outs):
         assert rel_err(npy(o), z["agg%d" % i]) < 1e-4
     for i, d in enumerate(disps):
@@ -132,6 +137,66 @@ def test_fused_executor_matches_module_path(D0, H, W, B):
         agg.use_fused_inference = True
         again = agg([c.clone() for c in costs])
     assert rel_err(npy(again[0]), npy(slow[0] + 1.0)) < 1e-4
+
+
+def _bench_init(hp, randomize):
+    """bench.py's weight init (offset_conv ~ N(0, 0.05^2)); `randomize` additionally gives the BatchNorms
+    non-trivial statistics and the offset head a bias of +-0.5 px so that samples leave the image."""
+    for nm, m in hp.named_modules():
+        if nm.endswith("offset_conv"):
+            torch.nn.init.normal_(m.weight, std=0.05)
+            torch.nn.init.normal_(m.bias, std=0.5 if randomize else 0.05)
+        if randomize and isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.8, 1.2)
+            torch.nn.init.uniform_(m.weight, 0.8, 1.2); torch.nn.init.normal_(m.bias, std=0.1)
+
+
+@pytest.mark.parametrize("name,D0,Cs,H,W,B,randomize", [
+    ("config2 AANet KITTI 384x1248 (the bench workload, bench init)", 64, (128, 128, 128), 128, 416, 1, False),
+    ("config2, randomised BN statistics and offset bias", 64, (128, 128, 128), 128, 416, 1, True),
+    ("config3 AANet+ Scene Flow 576x960 (2 of the 64 pairs)", 64, (32, 64, 128), 192, 320, 2, False),
+    ("config5 AANet 1080p -> 1104x1920, max_disp 288", 96, (128, 128, 128), 368, 640, 1, False),
+])
+def test_hot_path_full_config_vs_port(name, D0, Cs, H, W, B, randomize):
+    """The benchmarked configurations at FULL size against the CPU port of the reference
+    (oracle/torch_port.py: torch CPU convs + torchvision deform_conv2d + the C oracle's correlation / CSA /
+    soft-argmin) -- not against this repo's own module path: cost volumes and the aggregated volume within 1e-4
+    relative, disparity within 1e-3 px (BASELINE north_star), through HotPath exactly as bench.py drives it
+    (fused channels-last executor: the MODE 2 deformable engine at D0 = 64, two N tiles per layer at D0 = 96).
+    Mirrors nets/aanet.py:216-219."""
+    import aanet_b200.nets as n
+    from aanet_b200 import fused
+    from aanet_b200.pipeline import HotPath
+    torch.manual_seed(326)
+    hp = HotPath(3 * D0, num_deform_blocks=3, intermediate_supervision=False).eval()
+    _bench_init(hp, randomize)
+    g = torch.Generator().manual_seed(326)
+    Ls = [torch.relu(torch.randn(B, Cs[s], H >> s, W >> s, generator=g)) for s in range(3)]
+    Rs = [torch.relu(torch.randn(B, Cs[s], H >> s, W >> s, generator=g)) for s in range(3)]
+    sd = {k: v.clone() for k, v in hp.aggregation.state_dict().items()}
+    try:
+        import torchvision  # noqa: F401
+        impl = "tv"
+    except Exception:
+        impl = "c"
+    torch.set_num_threads(max(1, (os.cpu_count() or 2)))
+    with torch.no_grad():
+        ref_costs = port.cost_volume_pyramid(Ls, Rs, D0, use_c=True)
+        ref_agg = port.adaptive_aggregation(ref_costs, sd, impl=impl)
+        ref_disp = port.disparity_estimation(ref_agg[0], True)
+    hp.cuda()
+    assert fused.supported(hp.aggregation)
+    Lc, Rc = [t.cuda() for t in Ls], [t.cuda() for t in Rs]
+    with torch.no_grad():
+        costs = n.CostVolumePyramid(D0)(Lc, Rc)
+        agg = hp.aggregation([c.clone() for c in costs])
+        disp = hp(Lc, Rc)[-1]               # correlation_nhwc -> fused executor -> soft-argmin (the bench's path)
+    assert hasattr(hp.aggregation, "_aanet_fused")
+    for s in range(3):
+        assert rel_err(npy(costs[s]), ref_costs[s].numpy()) < 1e-4, "cost volume, scale %d" % s
+    assert rel_err(npy(agg[0]), ref_agg[0].numpy()) < 1e-4
+    assert np.abs(npy(disp) - ref_disp.numpy()).max() < 1e-3
+    assert np.abs(npy(n.DisparityEstimation(D0)(agg[0])) - ref_disp.numpy()).max() < 1e-3
 
 
 @pytest.mark.parametrize("name,D0,C,H,W,B", [

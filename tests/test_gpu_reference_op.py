@@ -21,7 +21,8 @@ def ref_op():
     return mod
 
 
-@pytest.mark.parametrize("C,H,W,B", [(64, 64, 104, 1), (32, 32, 52, 2), (16, 16, 26, 1)])
+@pytest.mark.parametrize("C,H,W,B", [(64, 64, 104, 1), (32, 32, 52, 2), (16, 16, 26, 1),
+                                     (64, 128, 416, 1)])        # the bench's 1/3-scale ISA layer at full size
 def test_mdconv_matches_reference_cuda_op(ref_op, C, H, W, B):
     import aanet_b200.ops as ops
     torch.manual_seed(326)
@@ -45,3 +46,34 @@ def test_mdconv_matches_reference_cuda_op(ref_op, C, H, W, B):
     grads = torch.autograd.grad(out, (xs, offs, ms, ws), g)
     for name, a, r in zip(("gx", "goffset", "gmask", "gweight"), grads, (gx, goff, gm, gw)):
         assert rel_err(a.cpu().numpy(), r.cpu().numpy()) < 2e-4, name      # the reference sums gx with float atomics
+
+
+def test_engine_mode2_full_size_matches_reference_cuda_op(ref_op):
+    """The instantiation bench.py's roofline object times -- conv_umma_kernel<64, MODE 2> on channels-last input
+    [1,128,416,64] with channel-plane offsets/mask (2*randn px: fractional, some outside the image), dg = 2,
+    dil = 2, folded-BN affine + ReLU epilogue -- against the reference's own CUDA op
+    (deform_conv_cuda_kernel.cu:570-633 + cpp:539-561) followed by the same affine + ReLU in torch."""
+    import aanet_b200.ops as ops
+    torch.manual_seed(326)
+    dev = "cuda"
+    B, C, H, W = 1, 64, 128, 416
+    x = torch.randn(B, C, H, W, device=dev)
+    off = 2 * torch.randn(B, 36, H, W, device=dev)
+    msk = 2 * torch.sigmoid(torch.randn(B, 18, H, W, device=dev))
+    w = torch.randn(C, C, 3, 3, device=dev) / (C * 9) ** 0.5
+    sc, sh = torch.rand(C, device=dev) + 0.5, torch.randn(C, device=dev)
+    args = (3, 3, 1, 1, 2, 2, 2, 2, 1, 2, False)
+    out_ref = torch.empty(B, C, H, W, device=dev)
+    e0, e1, fake = torch.empty(0, device=dev), torch.empty(0, device=dev), torch.empty(1, device=dev)
+    ref_op.modulated_deform_conv_cuda_forward(x, w, fake, e0, off, msk, out_ref, e1, *args)
+    want = torch.relu(out_ref * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1))
+
+    x_cl = x.permute(0, 2, 3, 1).contiguous()
+    om = torch.cat([off, msk], 1).contiguous()                      # channel planes [B,54,H,W]
+    got = ops.mdcn_nhwc(x_cl, om, ops.pack_conv_weight(w), C, 3, 3, None, sc, sh, True, 1, 2, 2, 1, 2,
+                        om_nchw=True)
+    assert got.shape == (B, H, W, C)
+    assert rel_err(got.permute(0, 3, 1, 2).cpu().numpy(), want.cpu().numpy()) < 1e-4
+    om_cl = om.permute(0, 2, 3, 1).contiguous()                     # channels-last offsets/mask
+    got2 = ops.mdcn_nhwc(x_cl, om_cl, ops.pack_conv_weight(w), C, 3, 3, None, sc, sh, True, 1, 2, 2, 1, 2)
+    assert rel_err(got2.permute(0, 3, 1, 2).cpu().numpy(), want.cpu().numpy()) < 1e-4

@@ -102,7 +102,7 @@ def test_deform_layer_port(golden):
     assert rel_err(blk.numpy(), z["blk_out"]) < 1e-5
 
 
-@pytest.mark.parametrize("name", ["agg", "agg_inter"])
+@pytest.mark.parametrize("name", ["agg", "agg_inter", "agg32"])
 def test_hot_path_port(golden, name):
     z = golden(name)
     sd = _sd(z, "sd/")
