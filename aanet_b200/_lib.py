@@ -23,6 +23,8 @@ SIGNATURES = {
     "aanet_corr_fwd_bf16": (_i, [_vp, _vp, _vp] + [_i] * 5 + [_vp]),
     "aanet_corr_fwd_nhwc": (_i, [_vp, _vp, _vp] + [_i] * 5 + [_vp]),
     "aanet_corr_bwd": (_i, [_vp] * 5 + [_i] * 5 + [_vp]),
+    "aanet_cost5d_fwd": (_i, [_vp, _vp, _vp] + [_i] * 6 + [_vp]),
+    "aanet_cost5d_bwd": (_i, [_vp, _vp, _vp] + [_i] * 6 + [_vp]),
     "aanet_softargmin_fwd": (_i, [_vp, _vp] + [_i] * 5 + [_vp]),
     "aanet_softargmin_bwd": (_i, [_vp, _vp, _vp] + [_i] * 5 + [_vp]),
     "aanet_refine_frontend_fwd": (_i, [_vp] * 5 + [_i] * 6 + [_vp]),

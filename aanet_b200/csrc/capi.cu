@@ -9,6 +9,17 @@ void set_last_cuda_error(const char *msg) {
     strncpy(g_last_err, msg ? msg : "", sizeof(g_last_err) - 1);
     g_last_err[sizeof(g_last_err) - 1] = 0;
 }
+int num_sms() {
+    static int cache[64] = {0};          // benign race: every thread writes the same value
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return kNumSMs;
+    if (cache[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
+        cache[dev] = n;
+    }
+    return cache[dev];
+}
 bool pdl_enabled() {
     static const bool on = getenv("AANET_NO_PDL") == nullptr;
     return on;

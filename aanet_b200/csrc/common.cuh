@@ -6,7 +6,10 @@
 
 namespace aanet {
 
-constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
+constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs (sizing of static tables only)
+// SM count of the current device (cached per device ordinal): grids and split heuristics use this, so a MIG
+// slice or another SKU only changes the numbers, never correctness.
+int num_sms();
 
 // Records the CUDA error text of a failed launch for aanet_last_cuda_error().
 void set_last_cuda_error(const char *msg);

@@ -675,7 +675,7 @@ static int launch_inst(const ConvBatch &batch, cudaStream_t stream) {
     // Persistent grid: the fewest CTAs that still finish in ceil(tiles / #SMs) rounds (416 tiles -> 139 CTAs x 3
     // tiles instead of 148 CTAs of which 28 would idle in the last round): the SMs left free run the coarse-scale
     // kernels that the fused executor issues on parallel streams.
-    const int rounds = ceil_div(batch.total_tiles, kNumSMs);
+    const int rounds = ceil_div(batch.total_tiles, num_sms());
     const int grid = ceil_div(batch.total_tiles, rounds);
     // Programmatic dependent launch: consecutive engine kernels of a stream overlap launch latency and prologue
     // with the predecessor's last epilogue (see pdl_wait / pdl_trigger in the kernel).

@@ -405,11 +405,8 @@ extern "C" int aanet_corr_bwd(const float *L, const float *R, const float *gcost
     if (H > 65535 || B > 65535) return AANET_ERR_UNSUPPORTED;
     const size_t smem = sizeof(float) * (size_t)D * (kBW + D);
     if (smem > 200 * 1024) return AANET_ERR_UNSUPPORTED;
-    static bool attr_set = false;   // idempotent; benign if raced
-    if (!attr_set) {
-        cudaFuncSetAttribute(corr_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
+    // per launch: the attribute is per device (a process driving several GPUs, e.g. nn.DataParallel threads)
+    cudaFuncSetAttribute(corr_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const dim3 grid(ceil_div(W, kBW), H, B);
     corr_bwd_kernel<<<grid, kBwdThreads, smem, as_stream(stream)>>>(L, R, gcost, gL, gR, C, H, W, D);
     return check_launch();

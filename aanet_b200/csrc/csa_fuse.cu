@@ -314,7 +314,7 @@ csa_bwd_resize_kernel(const float *__restrict__ out, const float *__restrict__ g
 
 inline unsigned grid_for(long n, int block) {
     long g = ceil_div_ll(n, block);
-    const long cap = (long)kNumSMs * 16;   // grid-stride beyond 16 CTAs per SM
+    const long cap = (long)num_sms() * 16;   // grid-stride beyond 16 CTAs per SM
     return (unsigned)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 

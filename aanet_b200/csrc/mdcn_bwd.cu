@@ -143,7 +143,7 @@ inline WeightPlan make_weight_plan(const MdcnDims &d) {
     w.n_items = d.groups * d.K * w.n_cchunks * w.n_otiles;
     w.tiles_per_img = (int)ceil_div_ll(d.P, kWP);
     const long T = (long)d.B * w.tiles_per_img;
-    long s = ceil_div_ll(4 * kNumSMs, w.n_items);
+    long s = ceil_div_ll(4 * num_sms(), w.n_items);
     if (s < 1) s = 1;
     if (s > 64) s = 64;
     if (s > T) s = T;

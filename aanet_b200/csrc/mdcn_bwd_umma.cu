@@ -43,6 +43,9 @@ mdcn_bwd_scatter_kernel(const float *__restrict__ x_nhwc, const float *__restric
     const long item0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const long stride_items = ((long)gridDim.x * blockDim.x) >> 3;
     const int cv = d.Cd >> 2;                               // 16-byte chunks per deformable group
+    // The loop trip count is uniform per 8-lane group only (n_items need not be a multiple of 4): the shuffles
+    // below name just the 8 lanes of this group.
+    const unsigned group_mask = 0xffu << (threadIdx.x & 24);
     for (long it = item0; it < n_items; it += stride_items) {   // uniform per 8-lane group
         const long p = it % d.P;
         long r = it / d.P;
@@ -97,9 +100,9 @@ mdcn_bwd_scatter_kernel(const float *__restrict__ x_nhwc, const float *__restric
         }
 #pragma unroll
         for (int sh = 4; sh > 0; sh >>= 1) {
-            a_m += __shfl_xor_sync(0xffffffffu, a_m, sh);
-            a_oh += __shfl_xor_sync(0xffffffffu, a_oh, sh);
-            a_ow += __shfl_xor_sync(0xffffffffu, a_ow, sh);
+            a_m += __shfl_xor_sync(group_mask, a_m, sh);
+            a_oh += __shfl_xor_sync(group_mask, a_oh, sh);
+            a_ow += __shfl_xor_sync(group_mask, a_ow, sh);
         }
         if (lane8 == 0) {
             goffset[(b * d.dg * 2 * d.K + (long)(g * d.K + k) * 2 + 0) * d.P + p] = a_oh;
@@ -220,7 +223,7 @@ static WeightMmaPlan plan_weight_mma(const MdcnDims &d) {
     w.n_items = d.K * w.n_cchunks * w.n_otiles;
     w.tiles_per_img = (int)ceil_div_ll(d.P, kMP);
     const long T = (long)d.B * w.tiles_per_img;
-    long s = ceil_div_ll(8 * kNumSMs, w.n_items);
+    long s = ceil_div_ll(8 * num_sms(), w.n_items);
     if (s < 1) s = 1;
     if (s > 128) s = 128;
     if (s > T) s = T;
@@ -313,7 +316,7 @@ int mdcn_bwd_input_umma(const float *x, const float *offset, const float *mask, 
     if (cudaMemsetAsync(gx_t, 0, sizeof(float) * (size_t)d.B * d.HW * d.Cin, stream) != cudaSuccess) return check_launch();
     const long n_items = (long)d.B * d.K * d.dg * d.P;
     const long blocks = ceil_div_ll(n_items * 8, 256);
-    mdcn_bwd_scatter_kernel<<<(int)(blocks < 16L * kNumSMs ? blocks : 16L * kNumSMs), 256, 0, stream>>>(
+    mdcn_bwd_scatter_kernel<<<(int)(blocks < 16L * num_sms() ? blocks : 16L * num_sms()), 256, 0, stream>>>(
         x_t, offset, mask, gcol, gx_t, goffset, gmask, col, d, n_items);
     if ((rc = check_launch()) != AANET_OK) return rc;
     return conv_umma_transpose(gx_t, gx, d.B, (int)d.HW, d.Cin, stream);

@@ -13,6 +13,7 @@ path (torch convs + the same sm_100a operators) runs.
 """
 import os
 
+import torch
 import torch.nn as nn
 
 from . import ops
@@ -20,8 +21,22 @@ from .streams import fork_join
 from .nets.deform import DeformSimpleBottleneck, SimpleBottleneck, bn_affine
 
 
+def _own(t):
+    """Private fp32 copy whose address stays valid for the executor's lifetime (see refresh())."""
+    return None if t is None else t.detach().float().clone().contiguous()
+
+
+def _affine(bn):
+    return (None, None) if bn is None else tuple(_own(t) for t in bn_affine(bn))
+
+
 class _Conv:
-    """A convolution prepared for the engine: packed weights + epilogue vectors + geometry."""
+    """A convolution prepared for the engine: packed weights + epilogue vectors + geometry.
+
+    The packed weights and the folded-BN vectors are PRIVATE buffers; CUDA graphs captured over the executor
+    (HotPath.capture, HostPipeline) bake their addresses.  refresh() therefore rewrites them in place after a
+    weight update (load_state_dict, optimizer step) instead of allocating new ones, so a replay of an earlier
+    capture sees the new weights -- the same contract as a captured torch module."""
 
     def __init__(self, conv, bn=None, act=ops.ACT_NONE, slope=0.2):
         w = conv.weight
@@ -29,10 +44,21 @@ class _Conv:
         self.groups = conv.groups
         self.stride, self.pad, self.dil = conv.stride[0], conv.padding[0], conv.dilation[0]
         self.wpack = ops.pack_conv_weight(w, conv.groups)
-        self._w, self._packs = w, {}
-        self.bias = None if conv.bias is None else conv.bias.detach().float().contiguous()
-        self.scale, self.shift = (None, None) if bn is None else bn_affine(bn)
+        self._conv, self._bn, self._w, self._packs = conv, bn, w, {}
+        self.bias = _own(conv.bias)
+        self.scale, self.shift = _affine(bn)
         self.act, self.slope = act, slope
+
+    def refresh(self):
+        self._w = self._conv.weight
+        ops.pack_conv_weight(self._w, self.groups, out=self.wpack)
+        for bn, pack in self._packs.items():
+            ops.pack_conv_weight(self._w, self.groups, bn, out=pack)
+        if self.bias is not None:
+            self.bias.copy_(self._conv.bias.detach())
+        if self._bn is not None:
+            sc, sh = bn_affine(self._bn)
+            self.scale.copy_(sc); self.shift.copy_(sh)
 
     def problem(self, x, bn):
         """Descriptor of this conv for a multi-problem launch whose N tile is `bn` wide."""
@@ -58,10 +84,19 @@ class _Deform:
         self.mask_scale = 2.0 if dc2d.double_mask else 1.0
         self.Cout, _, self.kh, self.kw = dc.weight.shape
         self.wpack = ops.pack_conv_weight(dc.weight, dc.groups)
-        self.bias = None if dc.bias is None else dc.bias.detach().float().contiguous()
-        self.scale, self.shift = bn_affine(bn)
+        self._dc, self._bn = dc, bn
+        self.bias = _own(dc.bias)
+        self.scale, self.shift = _affine(bn)
         self.stride, self.pad, self.dil = dc.stride, dc.padding, dc.dilation
         self.groups, self.dg = dc.groups, dc.deformable_groups
+
+    def refresh(self):
+        self.head.refresh()
+        ops.pack_conv_weight(self._dc.weight, self.groups, out=self.wpack)
+        if self.bias is not None:
+            self.bias.copy_(self._dc.bias.detach())
+        sc, sh = bn_affine(self._bn)
+        self.scale.copy_(sc); self.shift.copy_(sh)
 
     def __call__(self, x):
         # offsets pass through, mask channels get mask_scale * sigmoid (deform.py:82-89), one tensor, written
@@ -80,6 +115,10 @@ class _Bottleneck:
         else:
             self.c2 = _Conv(blk.conv2, blk.bn2, ops.ACT_RELU)
         self.c3 = _Conv(blk.conv3, blk.bn3, ops.ACT_RELU)     # relu(bn3(conv3) + identity)
+
+    def refresh(self):
+        for c in (self.c1, self.c2, self.c3):
+            c.refresh()
 
     def __call__(self, x):
         return self.c3(self.c2(self.c1(x)), residual=x)
@@ -120,9 +159,13 @@ def _state_key(agg):
     return tuple((t.data_ptr(), t._version) for t in list(agg.parameters()) + list(agg.buffers()))
 
 
+def _shape_key(agg):
+    return tuple((tuple(t.shape), t.device) for t in list(agg.parameters()) + list(agg.buffers()))
+
+
 class FusedAggregation:
     def __init__(self, agg):
-        self.key = _state_key(agg)
+        self.key, self.shapes = _state_key(agg), _shape_key(agg)
         self.stages = []
         for mod in agg.fusions:
             branches = [[_Bottleneck(b) for b in br] for br in mod.branches]
@@ -131,35 +174,51 @@ class FusedAggregation:
             self.stages.append((branches, fuse, mod.relu.negative_slope))
         self.final = [_Conv(c) for c in agg.final_conv]
 
+    def refresh(self, agg):
+        """Re-pack every layer into the buffers it already owns (same addresses) after a weight update."""
+        for branches, fuse, _ in self.stages:
+            for br in branches:
+                for blk in br:
+                    blk.refresh()
+            for row in fuse or []:
+                for chain in row:
+                    for conv in chain:
+                        conv.refresh()
+        for conv in self.final:
+            conv.refresh()
+        self.key = _state_key(agg)
+
     def __call__(self, cost_volume, nhwc=False):
         """cost_volume: the pyramid of volumes, [B,D,H,W] each -- or already channels-last [B,H,W,D] (nhwc=True,
-        ops.correlation_nhwc), which saves the three layout kernels."""
+        ops.correlation_nhwc), which saves the three layout kernels.
+
+        Memory plan.  Lifetimes follow the stage structure: inside a branch or a CSA row every intermediate is
+        produced and consumed on ONE stream, so it is released as soon as its Python reference dies (the caching
+        allocator's stream-ordered reuse is then safe); the only tensors that cross streams are a stage's outputs,
+        and those stay referenced (`xs`) until the join that ends the NEXT stage, after which any reuse is ordered
+        behind that join by the following fork (streams.py).  Peak: the stage inputs + ~3 volumes per scale, i.e.
+        ~6 volumes of the 1/3-scale size per pair instead of the ~70 a keep-everything plan holds."""
         dev = cost_volume[0].device
-        keep = []                       # every intermediate stays alive until the final join (streams.py)
 
-        def track(t):
-            keep.append(t)
-            return t
-
-        def branch(s, blocks, x):
+        def branch(blocks, x):
             def go():
                 y = x
                 for blk in blocks:
-                    y = track(blk(y))
+                    y = blk(y)
                 return y
             return go
 
         if nhwc:
             xs = list(cost_volume)
         else:
-            xs = fork_join(dev, [(lambda c=c: track(ops.nchw_to_nhwc(c))) for c in cost_volume])
+            xs = fork_join(dev, [(lambda c=c: ops.nchw_to_nhwc(c)) for c in cost_volume])
         for branches, fuse, slope in self.stages:
             # ISA: the scales are independent -> one stream each
-            xs = fork_join(dev, [branch(s, blocks, xs[s]) for s, blocks in enumerate(branches)])
+            xs = fork_join(dev, [branch(blocks, xs[s]) for s, blocks in enumerate(branches)])
             if fuse is None:
                 continue
             # CSA: output scale i needs every input scale; the output scales are independent
-            def fuse_row(row):
+            def fuse_row(row, xs=xs):
                 def go():
                     # the last conv of every exchange chain of this row in ONE multi-problem launch (they are
                     # independent and all produce this row's channel count); longer chains run their head first
@@ -167,7 +226,7 @@ class FusedAggregation:
                     for j, chain in enumerate(row):
                         t = xs[j]
                         for conv in chain[:-1]:
-                            t = track(conv(t))
+                            t = conv(t)
                         terms.append(t)
                         if chain:
                             last.append((chain[-1], t))
@@ -176,21 +235,26 @@ class FusedAggregation:
                         bn = max(ops.natural_bn(c.Cout // c.groups) for c, _ in last)
                         outs = ops.conv_batch([c.problem(t, bn) for c, t in last], bn=bn)
                         for j, o in zip(where, outs):
-                            terms[j] = track(o)
+                            terms[j] = o
                     else:
                         for j, (c, t) in zip(where, last):
-                            terms[j] = track(c(t))
-                    return track(ops.csa_fuse_nhwc(terms, slope))
+                            terms[j] = c(t)
+                    return ops.csa_fuse_nhwc(terms, slope)
                 return go
             xs = fork_join(dev, [fuse_row(row) for row in fuse])
-        outs = fork_join(dev, [(lambda s=s, conv=conv: conv(xs[s], out_nchw=True)) for s, conv in enumerate(self.final)])
-        del keep
-        return outs
+        return fork_join(dev, [(lambda s=s, conv=conv: conv(xs[s], out_nchw=True)) for s, conv in enumerate(self.final)])
 
 
 def run(agg, cost_volume, nhwc=False):
     fused = getattr(agg, "_aanet_fused", None)
-    if fused is None or fused.key != _state_key(agg):
+    if fused is None or fused.shapes != _shape_key(agg):
         fused = FusedAggregation(agg)
         agg._aanet_fused = fused
+    elif fused.key != _state_key(agg):
+        # weights changed in place (or were re-assigned with the same shapes): re-pack into the SAME buffers so
+        # that CUDA graphs captured earlier keep reading valid, current data
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("aanet_b200.fused: weights changed since the last eager run; run one eager forward "
+                               "before capturing (the re-pack must not become part of the graph)")
+        fused.refresh(agg)
     return fused(cost_volume, nhwc)

@@ -1,9 +1,9 @@
 """Correlation cost volume modules -- drop-in for the reference's nets/cost.py.
 
 `CostVolume(max_disp, feature_similarity='correlation')` and `CostVolumePyramid(...)` keep the
-reference constructors and call conventions (nets/cost.py:5-76).  Only the correlation branch
-(cost.py:40-48) is on the hot path and implemented; 'difference' / 'concat' (cost.py:22-38) build
-5-D volumes for the StereoNet/PSMNet/GC-Net ablations and are out of scope.
+reference constructors and call conventions (nets/cost.py:5-76).  The correlation branch (cost.py:40-48) is
+the hot path (tcgen05 banded GEMM); 'difference' / 'concat' (cost.py:22-38), the 5-D volumes of the
+StereoNet/PSMNet/GC-Net style variants, are one memory-bound kernel each.
 """
 import torch
 import torch.nn as nn
@@ -19,9 +19,10 @@ class CostVolume(nn.Module):
         self.feature_similarity = feature_similarity
 
     def forward(self, left_feature, right_feature):
+        if self.feature_similarity in ('difference', 'concat'):
+            return ops.cost_volume_5d(left_feature, right_feature, self.max_disp, self.feature_similarity)
         if self.feature_similarity != 'correlation':
-            # cost.py:50-51 raises for unknown names; the two 5-D variants are not provided here
-            raise NotImplementedError("aanet_b200 implements feature_similarity='correlation' only")
+            raise NotImplementedError          # cost.py:50-51
         return ops.correlation(left_feature, right_feature, self.max_disp)
 
 
@@ -34,9 +35,10 @@ class CostVolumePyramid(nn.Module):
         self.feature_similarity = feature_similarity
 
     def forward(self, left_feature_pyramid, right_feature_pyramid):
-        if self.feature_similarity != 'correlation':
-            raise NotImplementedError("aanet_b200 implements feature_similarity='correlation' only")
         pairs = list(zip(left_feature_pyramid, right_feature_pyramid))
+        if self.feature_similarity != 'correlation':      # cost.py:64-76 builds a CostVolume per level
+            return [CostVolume(self.max_disp // (2 ** s), self.feature_similarity)(l, r)
+                    for s, (l, r) in enumerate(pairs)]
         if pairs and pairs[0][0].is_cuda and not torch.is_grad_enabled():
             # inference: the scales are independent, run them on parallel streams
             return fork_join(pairs[0][0].device,

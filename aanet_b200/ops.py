@@ -108,6 +108,41 @@ def correlation_bf16(left, right, max_disp):
     return out
 
 
+class _Cost5d(Function):
+    @staticmethod
+    def forward(ctx, left, right, max_disp, mode):
+        left, right = _prep(left, "cost_volume_5d"), _prep(right, "cost_volume_5d")
+        if left.dim() != 4 or left.shape != right.shape:
+            raise ValueError("cost_volume_5d: left/right must be [B,C,H,W] of equal shape")
+        B, C, H, W = left.shape
+        out = left.new_empty(B, C * (2 if mode else 1), max_disp, H, W)
+        with torch.cuda.device(left.device):
+            _lib.check(_lib.load().aanet_cost5d_fwd(_ptr(left), _ptr(right), _ptr(out), B, C, H, W, max_disp, mode,
+                                                    _stream(left)), "aanet_cost5d_fwd")
+        _count()
+        ctx.meta = (B, C, H, W, max_disp, mode)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        B, C, H, W, D, mode = ctx.meta
+        g = _prep(g, "cost_volume_5d")
+        gl, gr = g.new_empty(B, C, H, W), g.new_empty(B, C, H, W)
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.load().aanet_cost5d_bwd(_ptr(g), _ptr(gl), _ptr(gr), B, C, H, W, D, mode, _stream(g)),
+                       "aanet_cost5d_bwd")
+        _count()
+        return gl, gr, None, None
+
+
+def cost_volume_5d(left, right, max_disp, kind):
+    """'difference' [B,C,D,H,W] or 'concat' [B,2C,D,H,W] volume (nets/cost.py:22-38), zero where w < d."""
+    if kind not in ("difference", "concat"):
+        raise NotImplementedError(kind)
+    return _Cost5d.apply(left, right, int(max_disp), 1 if kind == "concat" else 0)
+
+
 # ------------------------------------------------------------------------------------ soft-argmin
 class _SoftArgmin(Function):
     @staticmethod
@@ -353,16 +388,19 @@ def natural_bn(out_per_group):
     return (per + 15) // 16 * 16
 
 
-def pack_conv_weight(weight, groups=1, bn=0):
+def pack_conv_weight(weight, groups=1, bn=0, out=None):
     """tf32 hi/lo split + 128-byte swizzle of a [Cout, Cin/groups, kh, kw] weight for the tcgen05 engine.
-    bn = N-tile width of the launch the layer will run in (0: the layer's own natural width)."""
+    bn = N-tile width of the launch the layer will run in (0: the layer's own natural width).
+    out: an earlier result for the same shape, overwritten in place (its address may be baked into CUDA graphs)."""
     weight = _prep(weight.detach(), "pack_conv_weight")
     Cout, cg, kh, kw = weight.shape
     lib = _lib.load()
     n = lib.aanet_conv_wpack_bytes(Cout, cg * groups, kh, kw, groups, bn)
     if n == 0:
         raise _lib.AanetError("conv engine needs Cin/groups %% 4 == 0 (got Cin=%d, groups=%d)" % (cg * groups, groups))
-    wpack = torch.empty(n, dtype=torch.uint8, device=weight.device)
+    if out is not None and (out.numel() != n or out.device != weight.device or out.dtype != torch.uint8):
+        raise ValueError("pack_conv_weight: `out` does not match this weight's packed size")
+    wpack = torch.empty(n, dtype=torch.uint8, device=weight.device) if out is None else out
     with torch.cuda.device(weight.device):
         _lib.check(lib.aanet_conv_pack_weights(_ptr(weight), _ptr(wpack), Cout, cg * groups, kh, kw, groups, bn,
                                                _stream(weight)), "aanet_conv_pack_weights")
@@ -374,6 +412,23 @@ def _dp(t):
     return None if t is None else t.data_ptr()
 
 
+def _cl(t, name, dev, shape=None):
+    """Descriptor operand of the channels-last engine: CUDA fp32, contiguous, on `dev`, optionally of `shape`.
+    The engine sees raw pointers, so anything else would be silent garbage or an illegal address."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NotImplementedError("aanet_b200.conv_batch: %s must be a CUDA tensor (no CPU fallback)" % name)
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise TypeError("aanet_b200.conv_batch: %s must be contiguous float32, got %s%s"
+                        % (name, t.dtype, "" if t.is_contiguous() else " (non-contiguous)"))
+    if t.device != dev:
+        raise ValueError("aanet_b200.conv_batch: %s is on %s, x is on %s" % (name, t.device, dev))
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError("aanet_b200.conv_batch: %s must be %s, got %s" % (name, tuple(shape), tuple(t.shape)))
+    return t
+
+
 def conv_batch(problems, deform=False, bn=0):
     """Run 1..3 problems (dicts, see conv_problem) as one persistent engine launch; returns their outputs."""
     n = len(problems)
@@ -381,11 +436,26 @@ def conv_batch(problems, deform=False, bn=0):
     outs = []
     for d, q in zip(descs, problems):
         x = q["x"]
+        if x.dim() != 4:
+            raise ValueError("aanet_b200.conv_batch: x must be channels-last [B,H,W,C]")
+        dev = x.device
+        _cl(x, "x", dev)
         B, H, W, Cin = x.shape
         Ho, Wo = _out_hw(H, W, q["kh"], q["kw"], q["stride"], q["pad"], q["dil"])
-        out = x.new_empty((B, q["Cout"], Ho, Wo) if q.get("out_nchw") else (B, Ho, Wo, q["Cout"]))
+        oshape = (B, q["Cout"], Ho, Wo) if q.get("out_nchw") else (B, Ho, Wo, q["Cout"])
+        out = x.new_empty(oshape)
         outs.append(out)
         om = q.get("offmask")
+        for nm in ("bias", "scale", "shift"):
+            _cl(q.get(nm), nm, dev, (q["Cout"],))
+        _cl(q.get("residual"), "residual", dev, oshape)
+        if om is not None:
+            if om.dim() != 4 or (tuple(om.shape[2:]) if q.get("om_nchw") else tuple(om.shape[1:3])) != (Ho, Wo) \
+                    or om.shape[0] != B:
+                raise ValueError("aanet_b200.conv_batch: offmask must be [B,om,Ho,Wo] (om_nchw) or [B,Ho,Wo,om]")
+            _cl(om, "offmask", dev)
+        if q["wpack"].device != dev:
+            raise ValueError("aanet_b200.conv_batch: packed weights are on %s, x is on %s" % (q["wpack"].device, dev))
         d.x, d.wpack, d.out = x.data_ptr(), q["wpack"].data_ptr(), out.data_ptr()
         d.bias, d.scale, d.shift = _dp(q.get("bias")), _dp(q.get("scale")), _dp(q.get("shift"))
         d.residual, d.offmask = _dp(q.get("residual")), _dp(om)
@@ -427,6 +497,10 @@ def csa_fuse_nhwc(terms, slope=0.2):
     """Channels-last csa_fuse (inference): terms [B,h,w,C] -> [B,H,W,C] of terms[0]'s size."""
     B, H, W, C = terms[0].shape
     n = len(terms)
+    for t in terms:
+        _cl(t, "csa term", terms[0].device)
+        if t.dim() != 4 or t.shape[0] != B or t.shape[3] != C:
+            raise ValueError("csa_fuse_nhwc: all terms must be [B,h,w,C] with the same B and C")
     th = (ctypes.c_int * n)(*[t.shape[1] for t in terms])
     tw = (ctypes.c_int * n)(*[t.shape[2] for t in terms])
     out = terms[0].new_empty(B, H, W, C)

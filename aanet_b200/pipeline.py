@@ -22,7 +22,11 @@ from .streams import fork_join
 
 @contextlib.contextmanager
 def exact_fp32():
-    """cuDNN/cuBLAS TF32 off: the reference's convs would otherwise wobble at ~1e-3 on B200."""
+    """cuDNN/cuBLAS TF32 off: the reference's convs would otherwise wobble at ~1e-3 on B200.
+    These are PROCESS-GLOBAL torch flags, so the context is entered only on the module-by-module path (training,
+    channel counts the engine does not take), whose glue convolutions are cuDNN's.  The fused inference executor
+    never touches cuDNN/cuBLAS and leaves the flags alone; a multi-threaded caller (nn.DataParallel) of the
+    module path should set the two flags once itself instead of relying on this per-call flip."""
     old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -60,33 +64,34 @@ class HotPath(nn.Module):
                               for l, r, d in zip(left_pyramid, right_pyramid, D)])
             agg = fused.run(agg_mod, cost, nhwc=True)
         else:
-            agg = agg_mod(self.cost_volume(list(left_pyramid), list(right_pyramid)))
+            with exact_fp32():
+                agg = agg_mod(self.cost_volume(list(left_pyramid), list(right_pyramid)))
         return [self.disparity_estimation(a) for a in reversed(agg)]
 
     def pairs_per_pass(self, left_pyramid):
-        """How many pairs one inference pass may take.  The fused executor keeps every intermediate of the
-        aggregation alive until its final stream join (~70 volumes of the 1/3-scale size per pair, x 21/16 for the
-        coarser scales), so a large batch is run in slices that fit in half of the free device memory (config 5:
-        32 pairs at 1104x1920, D0 = 96, would need ~170 GB in one pass)."""
+        """How many pairs one inference pass may take.  The fused executor's lifetime plan (fused.py) holds the
+        stage inputs plus ~3 volumes per scale: <= 8 volumes of the 1/3-scale size per pair including the cost
+        volumes (measured: tests/test_gpu_modules.py::test_fused_executor_peak_memory).  Config 5 (32 pairs at
+        1104x1920, D0 = 96: 90 MB per volume and pair) therefore takes ~23 GB and runs in ONE pass; slicing only
+        happens when less than twice that is free."""
         if self.max_pairs_per_pass is not None:
             return max(1, int(self.max_pairs_per_pass))
         B, _, H, W = left_pyramid[0].shape
-        per_pair = 70 * 4 * self.max_disp * H * W * 21 // 16
+        per_pair = 8 * 4 * self.max_disp * H * W
         free, _ = torch.cuda.mem_get_info(left_pyramid[0].device)
         return max(1, min(B, int(free // 2 // max(per_pair, 1))))
 
     def forward(self, left_pyramid, right_pyramid):
         """Feature pyramids (finest first) -> list of disparities, coarse to fine (aanet.py:156-167)."""
-        with exact_fp32():
-            B = left_pyramid[0].shape[0]
-            if torch.is_grad_enabled() or self.training or not left_pyramid[0].is_cuda:
-                return self._one_pass(left_pyramid, right_pyramid)
-            n = self.pairs_per_pass(left_pyramid)
-            if n >= B:
-                return self._one_pass(left_pyramid, right_pyramid)
-            parts = [self._one_pass([t[i:i + n] for t in left_pyramid], [t[i:i + n] for t in right_pyramid])
-                     for i in range(0, B, n)]
-            return [torch.cat(ds, dim=0) for ds in zip(*parts)]
+        B = left_pyramid[0].shape[0]
+        if torch.is_grad_enabled() or self.training or not left_pyramid[0].is_cuda:
+            return self._one_pass(left_pyramid, right_pyramid)
+        n = self.pairs_per_pass(left_pyramid)
+        if n >= B:
+            return self._one_pass(left_pyramid, right_pyramid)
+        parts = [self._one_pass([t[i:i + n] for t in left_pyramid], [t[i:i + n] for t in right_pyramid])
+                 for i in range(0, B, n)]
+        return [torch.cat(ds, dim=0) for ds in zip(*parts)]
 
     # ------------------------------------------------------------------ CUDA graph
     @torch.no_grad()

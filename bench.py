@@ -1,6 +1,7 @@
 """bench.py -- stereo pairs/s through the AANet hot path (cost volume + ISA/CSA + soft-argmin).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|5] [--batch B]
+                    [--bf16-cost]
 
 Workload (BASELINE.json configs[1]): AANet at KITTI 384x1248, max_disp=192, B=1, fp32, random-init
 weights (offset_conv re-initialised N(0,0.05^2)), synthetic features relu(randn) of the
@@ -29,23 +30,59 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-H_IMG, W_IMG, MAX_DISP, FEAT_C = 384, 1248, 192, 128
-METRIC = "384x1248 stereo pairs/s (cost+ISA/CSA+soft-argmin)"
 UNIT = "pairs/s"
-N_SETS = 4      # rotating input sets: 4 x 71.6 MB > 126 MB L2
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-# (profiles/), MB; None until a capture of the current kernel exists.
-NCU_TRAFFIC_MB = {"mdconv": 25.5}   # profiles/r01_launches_and_engine.md: 25.49 MB read + 0.0003 MB written
+# BASELINE.json configs (1-based numbering of SURVEY.md section 8): 2 = the metric's configuration (default);
+# 3 and 5 are the large-batch throughput sweeps, whose fixed total batch is split over the GPUs (strong scaling).
+CONFIGS = {
+    2: dict(name="configs[1]", model="AANet", h=384, w=1248, max_disp=192, feat=(128, 128, 128), total_batch=None,
+            what="KITTI 384x1248"),
+    3: dict(name="configs[2]", model="AANet+", h=576, w=960, max_disp=192, feat=(32, 64, 128), total_batch=64,
+            what="Scene Flow 576x960"),
+    5: dict(name="configs[4]", model="AANet", h=1104, w=1920, max_disp=288, feat=(128, 128, 128), total_batch=32,
+            what="1080x1920 zero-padded to 1104x1920 (inference.py:154-162)"),
+}
+CFG = CONFIGS[2]
+L2_MB = 126.0
+
+
+def metric_name():
+    return "%dx%d stereo pairs/s (cost+ISA/CSA+soft-argmin)" % (CFG["h"], CFG["w"])
+
+
+def workload(batch, bf16=False):
+    """The `config.workload` string -- identical in the GPU arm and in the reference arm."""
+    return ("%s hot path, %s, max_disp=%d, B=%d per GPU per step, %s, random-init weights (%s)"
+            % (CFG["model"], CFG["what"], CFG["max_disp"], batch,
+               "bf16 features -> fp32 cost volume -> fp32 aggregation" if bf16 else "fp32", CFG["name"]))
 
 
 def pyramid_shapes(batch):
-    return [(batch, FEAT_C, H_IMG // (3 * 2 ** s), W_IMG // (3 * 2 ** s)) for s in range(3)]
+    return [(batch, CFG["feat"][s], CFG["h"] // (3 * 2 ** s), CFG["w"] // (3 * 2 ** s)) for s in range(3)]
+
+
+def pair_mb():
+    return 2 * 4 * sum(c * (CFG["h"] // (3 * 2 ** s)) * (CFG["w"] // (3 * 2 ** s)) for s, c in enumerate(CFG["feat"])) / 1e6
+
+
+def n_sets_for(batch):
+    """Rotating input sets so that consecutive steps never find their inputs in L2."""
+    return max(1, min(4, int(L2_MB * 2 // (pair_mb() * batch)) + 1)) if pair_mb() * batch < 2 * L2_MB else 1
+
+
+def ncu_figures(key):
+    """Per-launch figures of the dominant kernel from the committed ncu capture (profiles/ncu_roofline.json, written
+    by profiles/ncu_extract.py from the raw CSV next to it); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "ncu_roofline.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        return json.load(f).get(key)
 
 
 def make_hot_path():
     from aanet_b200.pipeline import HotPath
     torch.manual_seed(326)
-    hp = HotPath(MAX_DISP, num_deform_blocks=3, intermediate_supervision=False)
+    hp = HotPath(CFG["max_disp"], num_deform_blocks=3, intermediate_supervision=False)
     for name, m in hp.named_modules():
         if name.endswith("offset_conv"):
             torch.nn.init.normal_(m.weight, std=0.05)
@@ -53,16 +90,23 @@ def make_hot_path():
     return hp.eval()
 
 
-def make_inputs(batch, n_sets, device, pin=False, seed=326):
+def make_inputs(batch, n_sets, device, pin=False, seed=326, dtype=None):
     g = torch.Generator().manual_seed(seed)
     sets = []
     for _ in range(n_sets):
-        L = [torch.relu(torch.randn(s, generator=g)) for s in pyramid_shapes(batch)]
-        R = [torch.relu(torch.randn(s, generator=g)) for s in pyramid_shapes(batch)]
-        if pin:
-            L, R = [t.pin_memory() for t in L], [t.pin_memory() for t in R]
-        elif device is not None:
-            L, R = [t.to(device) for t in L], [t.to(device) for t in R]
+        if device is not None and batch * pair_mb() > 512:       # large batches: generate on the device
+            gd = torch.Generator(device=device).manual_seed(seed + len(sets))
+            L = [torch.relu(torch.randn(s, generator=gd, device=device)) for s in pyramid_shapes(batch)]
+            R = [torch.relu(torch.randn(s, generator=gd, device=device)) for s in pyramid_shapes(batch)]
+        else:
+            L = [torch.relu(torch.randn(s, generator=g)) for s in pyramid_shapes(batch)]
+            R = [torch.relu(torch.randn(s, generator=g)) for s in pyramid_shapes(batch)]
+            if pin:
+                L, R = [t.pin_memory() for t in L], [t.pin_memory() for t in R]
+            elif device is not None:
+                L, R = [t.to(device) for t in L], [t.to(device) for t in R]
+        if dtype is not None:
+            L, R = [t.to(dtype) for t in L], [t.to(dtype) for t in R]
         sets.append((L, R))
     return sets
 
@@ -110,7 +154,7 @@ def cpu_port_step(sd, L, R):
     except Exception:
         impl = "c"
     with torch.no_grad():
-        return port.hot_path(L, R, sd, MAX_DISP // 3, corr_c=False, impl=impl, fuse_c=False)
+        return port.hot_path(L, R, sd, CFG["max_disp"] // 3, corr_c=False, impl=impl, fuse_c=False)
 
 
 def run_cpu_baseline(steps, warmup, batch=1):
@@ -163,20 +207,22 @@ def _timed(fn, n_sets, iters, device):
 
 def time_kernels(device, iters=20):
     """Live CUDA-event timing (launching stream, inputs rotated over sets larger than L2) of the dominant
-    kernel -- the ISA modulated deformable conv at the 1/3 scale as the fused path runs it (tcgen05 engine,
-    channels-last, packed weights) -- and of the other engine / memory-bound kernels for context."""
+    kernel -- the ISA modulated deformable conv at the 1/3 scale of config 2 as the fused path runs it (tcgen05
+    engine, channels-last, packed weights, channel-plane offsets/mask) -- and of the other engine / memory-bound
+    kernels for context.  Always config-2 shapes: the roofline object describes the metric's configuration."""
     from aanet_b200 import ops
     torch.manual_seed(326)
-    C, H, W = MAX_DISP // 3, H_IMG // 3, W_IMG // 3
+    C, H, W, FEAT_C = 64, 128, 416, 128
     n = 6      # (13.6 + 11.5 + 13.6) MB per set -> 232 MB > L2
     xs = [torch.randn(1, H, W, C, device=device) for _ in range(n)]
-    oms = [torch.cat([2 * torch.randn(1, H, W, 36, device=device),
-                      2 * torch.sigmoid(torch.randn(1, H, W, 18, device=device))], -1).contiguous() for _ in range(n)]
+    oms = [torch.cat([2 * torch.randn(1, 36, H, W, device=device),
+                      2 * torch.sigmoid(torch.randn(1, 18, H, W, device=device))], 1).contiguous() for _ in range(n)]
     wp3 = ops.pack_conv_weight(torch.randn(C, C, 3, 3, device=device) / 24)
     wp1 = ops.pack_conv_weight(torch.randn(C, C, 1, 1, device=device) / 8)
     sc, sh = torch.rand(C, device=device) + 0.5, torch.randn(C, device=device)
     out = {}
-    ms = _timed(lambda i: ops.mdcn_nhwc(xs[i], oms[i], wp3, C, 3, 3, None, sc, sh, True, 1, 2, 2, 1, 2), n, iters, device)
+    ms = _timed(lambda i: ops.mdcn_nhwc(xs[i], oms[i], wp3, C, 3, 3, None, sc, sh, True, 1, 2, 2, 1, 2, om_nchw=True),
+                n, iters, device)
     flops = 2.0 * C * C * 9 * H * W
     bytes_alg = 4.0 * (C * H * W + 27 * 2 * H * W + C * H * W) + 36.0 * C * C
     out["mdconv"] = (ms, flops, bytes_alg)
@@ -190,7 +236,25 @@ def time_kernels(device, iters=20):
     Ls = [torch.relu(torch.randn(1, FEAT_C, H, W, device=device)) for _ in range(4)]
     ms = _timed(lambda i: ops.correlation(Ls[i], Ls[(i + 1) % 4], C), 4, iters, device)
     out["correlation_s0"] = (ms, 2.0 * FEAT_C * H * (W * C - C * (C - 1) / 2), 4.0 * H * W * (2 * FEAT_C + C))
+    ts = [[torch.randn(1, H >> s, W >> s, C, device=device) for s in range(3)] for _ in range(n)]
+    ms = _timed(lambda i: ops.csa_fuse_nhwc(ts[i], 0.2), n, iters, device)
+    out["csa_fuse_out0"] = (ms, 0.0, 4.0 * C * H * W * (2 + 1 / 4 + 1 / 16))
     return out
+
+
+def copy_ceiling(device, nbytes, iters=20):
+    """Bare pinned host -> device copy of one step's input bytes, back to back on one stream: the PCIe ceiling the
+    end-to-end number is measured against (ms per copy, wall clock around a synchronised loop)."""
+    host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dev = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    for _ in range(3):
+        dev.copy_(host, non_blocking=True)
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        dev.copy_(host, non_blocking=True)
+    torch.cuda.synchronize(device)
+    return (time.perf_counter() - t0) / iters * 1e3
 
 
 def load_peaks():
@@ -206,13 +270,19 @@ def run_gpu(args):
     import torch.distributed as dist
     from aanet_b200 import ops
     from aanet_b200.pipeline import HostPipeline
-    from aanet_b200.sharding import max_over_ranks
+    from aanet_b200.sharding import max_over_ranks, shard_range
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
+
+    # The CPU leg (rank 0, N = 1 only) runs BEFORE any process group exists: at N > 1 the other ranks would spin
+    # in an NCCL barrier on the host cores it is timed on (round 1: 0.71 pairs/s alone, 0.11-0.13 next to them).
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == 2:
+        cpu = run_cpu_baseline(3, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
@@ -221,20 +291,41 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    B = args.batch
+    strong = CFG["total_batch"] is not None and args.batch is None
+    if strong:                      # fixed total batch, contiguous slices per rank (aanet_b200/sharding.py)
+        lo, hi = shard_range(CFG["total_batch"], rank, world)
+        B = hi - lo
+        total_pairs_per_step = CFG["total_batch"]
+    else:
+        B = args.batch or 1
+        total_pairs_per_step = world * B
+    n_sets = n_sets_for(B)
+    dtype = torch.bfloat16 if args.bf16_cost else None
     hp = make_hot_path().to(device)
-    sets = make_inputs(B, N_SETS, device)
+    sets = make_inputs(B, n_sets, device, dtype=dtype)
     with torch.no_grad():
         hp(*sets[0])                    # first pass packs the weights (one-off launches)
+        torch.cuda.synchronize(device)
+        torch.cuda.reset_peak_memory_stats(device)
         launches0 = ops.LAUNCHES
-        hp(*sets[0])
+        out0 = hp(*sets[0])
         per_step_launches = ops.LAUNCHES - launches0
+        torch.cuda.synchronize(device)
+        peak_gb = torch.cuda.max_memory_allocated(device) / 1e9
+        passes = -(-B // hp.pairs_per_pass(sets[0][0]))
+        epe = None
+        if args.bf16_cost:              # end-point error of the variant against the fp32 path, same weights
+            f32 = hp([t.float() for t in sets[0][0]], [t.float() for t in sets[0][1]])
+            epe = {"epe_px_vs_fp32": float((f32[-1] - out0[-1]).abs().mean()),
+                   "max_abs_px_vs_fp32": float((f32[-1] - out0[-1]).abs().max()),
+                   "note": "metric.py:7-14 EPE = mean |d_a - d_b| of the 1/3-scale disparity"}
+            del f32
         graphs = [hp.capture(L, R)[0] for (L, R) in sets]
     stream = torch.cuda.current_stream(device)
 
     # ---- device-resident throughput
     for i in range(args.warmup):
-        graphs[i % N_SETS].replay()
+        graphs[i % n_sets].replay()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -242,43 +333,62 @@ def run_gpu(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(args.steps):
-        graphs[i % N_SETS].replay()
+        graphs[i % n_sets].replay()
     e1.record(stream)
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1), device)
     clocks = sampler.summary() if sampler else None
-    value = world * B * args.steps / (ms_total / 1e3)
+    value = total_pairs_per_step * args.steps / (ms_total / 1e3)
 
     # ---- end to end: pinned host buffers -> HostPipeline -> pinned disparity
-    # Each pair is written into the pipeline's pinned staging block (two slots, two different pairs) before the
-    # timed region; every timed step then moves its 71.6 MB host -> device and its disparity device -> host.
-    pipe = HostPipeline(hp, pyramid_shapes(B), device)
-    for k, (L, R) in enumerate(make_inputs(B, pipe.n, None, seed=327)):
-        hL, hR = pipe.slots[k]["host_L"], pipe.slots[k]["host_R"]
-        for dst, src in zip(hL + hR, L + R):
-            dst.copy_(src)
-    for i in range(max(args.warmup, 4) + args.steps):     # the first pass over the pinned blocks is slow (564 vs 750)
-        HostPipeline.result(pipe.submit())
-    # K steps take only tens of milliseconds and the PCIe rate of a (virtualised) host wanders from run to run
-    # (670 .. 750 pairs/s seen back to back on one box), so the K-step measurement is repeated and the median kept.
-    e2e_runs = []
-    for _ in range(3):
+    # A step's B pairs cross PCIe in chunks of `chunk` pairs (one DMA each, from the pipeline's pinned staging
+    # blocks, filled before the timed region); every timed step moves all its input bytes host -> device and its
+    # disparities device -> host.  fp32 features (the parity path) even when --bf16-cost is given.
+    e2e = None
+    if not args.no_e2e:
+        chunk = max(1, min(B, int(256 // pair_mb()) or 1))
+        while B % chunk:
+            chunk -= 1
+        del graphs, sets
+        torch.cuda.empty_cache()
+        pipe = HostPipeline(hp, pyramid_shapes(chunk), device)
+        for k, (L, R) in enumerate(make_inputs(chunk, pipe.n, None, seed=327)):
+            hL, hR = pipe.slots[k]["host_L"], pipe.slots[k]["host_R"]
+            for dst, src in zip(hL + hR, L + R):
+                dst.copy_(src)
+        per_step = B // chunk
+        for i in range((max(args.warmup, 4) + args.steps) * per_step):   # the first pass over pinned blocks is slow
+            HostPipeline.result(pipe.submit())
+        # K steps take only tens of milliseconds and the PCIe rate of a (virtualised) host wanders from run to run,
+        # so the K-step measurement is repeated and the median kept.
+        e2e_runs = []
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            pending = []
+            for i in range(args.steps * per_step):
+                pending.append(pipe.submit())
+                if len(pending) >= pipe.n:
+                    HostPipeline.result(pending.pop(0))
+            for sl in pending:
+                HostPipeline.result(sl)
+            torch.cuda.synchronize(device)
+            e2e_runs.append(max_over_ranks(time.perf_counter() - t0, device))
+        e2e_s = statistics.median(e2e_runs)
         barrier()
-        t0 = time.perf_counter()
-        pending = []
-        for i in range(args.steps):
-            pending.append(pipe.submit())
-            if len(pending) >= pipe.n:
-                HostPipeline.result(pending.pop(0))
-        for s in pending:
-            HostPipeline.result(s)
-        torch.cuda.synchronize(device)
-        e2e_runs.append(max_over_ranks(time.perf_counter() - t0, device))
-    e2e_s = statistics.median(e2e_runs)
-    e2e = {"value": world * B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
-           "d2h_bytes_per_step": pipe.d2h_bytes,
-           "h2d_gbs_per_gpu": B * args.steps / e2e_s * pipe.h2d_bytes / 1e9, "host_numa": pipe.numa,
-           "runs_pairs_per_s": [world * B * args.steps / t for t in e2e_runs], "stat": "median of 3 x K steps"}
+        ceil_ms = max_over_ranks(copy_ceiling(device, pipe.h2d_bytes), device)     # all ranks copy at the same time
+        e2e_val = total_pairs_per_step * args.steps / e2e_s
+        ceil_val = total_pairs_per_step / (B // chunk) / (ceil_ms / 1e3) if strong else world * chunk / (ceil_ms / 1e3)
+        e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes * per_step,
+               "d2h_bytes_per_step": pipe.d2h_bytes * per_step,
+               "h2d_gbs_per_gpu": B * args.steps / e2e_s * pipe.h2d_bytes / chunk / 1e9, "host_numa": pipe.numa,
+               "pairs_per_dma": chunk,
+               "copy_ceiling": {"what": "bare pinned cudaMemcpyAsync loop of the same %d bytes per DMA, all ranks "
+                                        "at once, max over ranks" % pipe.h2d_bytes,
+                                "ms_per_dma": ceil_ms, "gbs_per_gpu": pipe.h2d_bytes / ceil_ms / 1e6,
+                                "pairs_per_s": ceil_val, "e2e_frac_of_ceiling": e2e_val / ceil_val},
+               "runs_pairs_per_s": [total_pairs_per_step * args.steps / t for t in e2e_runs],
+               "stat": "median of 3 x K steps"}
 
     out = None
     if rank == 0:
@@ -287,10 +397,19 @@ def run_gpu(args):
         k_ms, k_flops, k_bytes = kt["mdconv"]
         tf32_peak = bf16 / 2.0
         achieved = k_flops / (k_ms * 1e-3) / 1e12
-        roofline = {"kernel": "conv_umma_kernel<64,DEFORM> = ISA modulated deformable conv, 1/3 scale "
-                              "[1,64,128,416], dg=2, dil=2, 3xTF32 tcgen05",
+        ncu = ncu_figures("mdconv")
+        roofline = {"kernel": "ISA modulated deformable conv, 1/3 scale of config 2 [1,64,128,416], dg=2, dil=2, "
+                              "3xTF32 tcgen05 (aanet_b200.ops.mdcn_nhwc as the fused executor calls it)",
                     "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                    "frac": achieved / tf32_peak, "traffic": NCU_TRAFFIC_MB.get("mdconv"),
+                    "frac": achieved / tf32_peak,
+                    "traffic": None if ncu is None else ncu["traffic_mb"] * 1e6,
+                    "traffic_source": None if ncu is None else
+                    "%s (commit %s, kernel %s, %d launches)" % (ncu["capture"], ncu["commit"], ncu["kernel"], ncu["launches"]),
+                    "tensor_pipe_pct": None if ncu is None else ncu["tensor_pipe_pct"],
+                    "tensor_pipe_pct_model": 100.0 * (3.0 * k_flops / (tf32_peak * 1e12)) / (k_ms * 1e-3),
+                    "tensor_pipe_note": "model = 3 MMAs per logical product (hi*hi, hi*lo, lo*hi) at the TF32 peak / "
+                                        "live launch time; ncu = sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed "
+                                        "of the committed capture",
                     "us_per_launch": k_ms * 1e3, "algorithmic_mb": k_bytes / 1e6,
                     "hbm_frac_if_memory_bound": k_bytes / (k_ms * 1e-3) / 1e9 / hbm,
                     "peak_source": peak_src + "; TF32 dense taken as bf16_tflops/2 (burst, kernel timed alone); "
@@ -298,19 +417,21 @@ def run_gpu(args):
                     "other_kernels": {k: {"us": v[0] * 1e3, "tflops": v[1] / (v[0] * 1e-3) / 1e12,
                                           "gbs": v[2] / (v[0] * 1e-3) / 1e9, "hbm_frac": v[2] / (v[0] * 1e-3) / 1e9 / hbm}
                                       for k, v in kt.items() if k != "mdconv"}}
-        cpu = None if args.no_cpu_baseline else run_cpu_baseline(3, 1)
-        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        out = {"metric": metric_name(), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": "AANet hot path, KITTI 384x1248, max_disp=192, B=%d per GPU per step, fp32, "
-                                      "random-init weights (configs[1])" % B,
-                          "features": "relu(randn) [B,128,128,416],[B,128,64,208],[B,128,32,104]",
+               "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": workload(B, args.bf16_cost),
+                          "features": "relu(randn) " + ",".join(str(list(sh)) for sh in pyramid_shapes(B)),
                           "parallelism": "batch-sharded x%d, no collective" % world,
-                          "l2": "inputs rotated over %d sets (%.0f MB > 126 MB L2)" % (N_SETS, N_SETS * 71.6 * B),
-                          "launch": "CUDA graph replay"},
+                          "pairs_per_step_all_gpus": total_pairs_per_step,
+                          "l2": "inputs rotated over %d set(s) of %.0f MB (126 MB L2)" % (n_sets, pair_mb() * B),
+                          "launch": "CUDA graph replay", "passes_per_step": passes,
+                          "peak_device_memory_gb": peak_gb},
                "e2e": e2e, "gpu_launches": per_step_launches * args.steps,
                "gpu_launches_per_step": per_step_launches, "clocks": clocks, "roofline": roofline,
                "cpu_baseline": cpu}
+        if epe is not None:
+            out["bf16_cost_volume"] = epe
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -318,29 +439,38 @@ def run_gpu(args):
 
 
 def main():
+    global CFG
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS),
+                    help="BASELINE config: 2 = the metric's (default), 3 / 5 = the large-batch sweeps")
+    ap.add_argument("--batch", type=int, default=None,
+                    help="pairs per GPU per step (default: 1 for config 2; configs 3/5: their total batch / GPUs)")
+    ap.add_argument("--bf16-cost", action="store_true", help="config 5 variant: bf16 features for the cost volume")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    CFG = CONFIGS[args.config]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", 0))
     if args.impl == "reference":
         if rank != 0:
             return 0
-        steps = min(args.steps, 12)      # ~3.5 s of CPU per step: keep the whole run within minutes
-        r = run_cpu_baseline(steps, min(args.warmup, 2), args.batch)
-        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
-                "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2),
+        # One step = one full pair through the CPU path (~1.5 s on the box's cores): the driver's K and W are
+        # honoured as given (K = 20, W = 5 take about 40 s).
+        batch = args.batch or 1
+        r = run_cpu_baseline(args.steps, args.warmup, batch)
+        line = {"impl": "reference", "metric": metric_name(), "value": r["value"], "unit": UNIT,
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "AANet hot path, KITTI 384x1248, max_disp=192, B=%d per step, fp32, "
-                                       "random-init weights (configs[1])" % args.batch,
-                           "note": "reference's PyTorch CPU path restated (oracle port) on the host cores"},
+                "config": {"workload": workload(batch),
+                           "note": "reference's PyTorch CPU path restated (oracle port) on the host cores of rank 0; "
+                                   "one step = B full pairs"},
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))

@@ -74,6 +74,19 @@ AANET_API int aanet_corr_bwd(const float *L, const float *R, const float *gcost,
                    int B, int C, int H, int W, int D, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * 5-D cost volumes of the non-correlation variants.  Replaces CostVolume.forward, 'difference' and 'concat'
+ * branches (nets/cost.py:22-38; used by the StereoNet / PSMNet / GC-Net style models of nets/aanet.py).
+ *   mode 0 (difference): out[b,c,d,h,w] = L[b,c,h,w] - R[b,c,h,w-d]                       out: [B,C,D,H,W]
+ *   mode 1 (concat)    : out[b,c,d,h,w] = L[b,c,h,w], out[b,C+c,d,h,w] = R[b,c,h,w-d]     out: [B,2C,D,H,W]
+ * for w >= d, exactly 0 for w < d.  Bit-identical to the reference (one subtraction / a copy per element).
+ * aanet_cost5d_bwd: gL, gR [B,C,H,W] (overwritten) from gout of the forward's shape.
+ * ------------------------------------------------------------------------------------------- */
+AANET_API int aanet_cost5d_fwd(const float *L, const float *R, float *out, int B, int C, int H, int W, int D,
+                               int mode, void *stream);
+AANET_API int aanet_cost5d_bwd(const float *gout, float *gL, float *gR, int B, int C, int H, int W, int D, int mode,
+                               void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Soft-argmin disparity regression.  Replaces DisparityEstimation.forward
  * (nets/estimation.py:13-30):  disp[b,h,w] = sum_d d * softmax_d(sign * cost[b,:,h,w]),
  * sign = +1 when `similarity` != 0 (match_similarity=True, aanet.py:113), else -1.

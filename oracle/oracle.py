@@ -81,6 +81,35 @@ def corr_pyramid(Ls, Rs, D0):
     return [corr_fwd(l, r, D0 // (2 ** s)) for s, (l, r) in enumerate(zip(Ls, Rs))]
 
 
+def cost5d_fwd(L, R, D, kind):
+    """nets/cost.py:22-38 restated in numpy: 'difference' [B,C,D,H,W] / 'concat' [B,2C,D,H,W], zero for w < d."""
+    L = np.asarray(L); R = np.asarray(R)
+    B, C, H, W = L.shape
+    out = np.zeros((B, C if kind == "difference" else 2 * C, D, H, W), L.dtype)
+    for d in range(min(D, W)):
+        if kind == "difference":
+            out[:, :, d, :, d:] = L[..., d:] - R[..., :W - d]
+        else:
+            out[:, :C, d, :, d:] = L[..., d:]
+            out[:, C:, d, :, d:] = R[..., :W - d]
+    return out
+
+
+def cost5d_bwd(g, kind):
+    """Autograd of cost.py:22-38: (gL, gR) [B,C,H,W] from g of the forward's shape."""
+    g = np.asarray(g, np.float64)
+    B, Co, D, H, W = g.shape
+    C = Co if kind == "difference" else Co // 2
+    gL = np.zeros((B, C, H, W)); gR = np.zeros((B, C, H, W))
+    for d in range(min(D, W)):
+        gL[..., d:] += g[:, :C, d, :, d:]
+        if kind == "difference":
+            gR[..., :W - d] -= g[:, :C, d, :, d:]
+        else:
+            gR[..., :W - d] += g[:, C:, d, :, d:]
+    return gL, gR
+
+
 # ---------------------------------------------------------------- soft-argmin
 def softargmin_fwd(cost, similarity=True):
     cost = _c(cost)

@@ -278,6 +278,20 @@ if __name__ == "__main__":
     if "--only-refinement" in sys.argv:     # added after the other fixtures were committed; own seed
         gen_refinement(nets)
         sys.exit(0)
+    if "--only-cost5d" in sys.argv:         # round 2: the 5-D 'difference' / 'concat' volumes (cost.py:22-38)
+        torch.manual_seed(329)
+        cases = {}
+        for kind in ("difference", "concat"):
+            for tag, (B, C, H, W, D) in {"a": (2, 3, 4, 13, 6), "narrow": (1, 2, 2, 5, 8)}.items():
+                L = torch.randn(B, C, H, W).requires_grad_(); R = torch.randn(B, C, H, W).requires_grad_()
+                out = cost_mod.CostVolume(D, kind)(L, R)
+                g = torch.randn_like(out)
+                gL, gR = torch.autograd.grad(out, (L, R), g)
+                k = "%s_%s_" % (kind, tag)
+                cases.update({k + "L": npf(L), k + "R": npf(R), k + "D": np.int32(D), k + "out": npf(out),
+                              k + "g": npf(g), k + "gL": npf(gL), k + "gR": npf(gR)})
+        save("cost5d", **cases)
+        sys.exit(0)
     if "--only-agg32" in sys.argv:          # round 2: a reference-made fixture that reaches the fused executor
         torch.manual_seed(328)
         gen_aggregation(nets, cost_mod, est_mod, (("agg32", False, 32, 20, 28),))

@@ -349,3 +349,50 @@ def test_hot_path_batch_slicing():
     assert len(whole) == len(sliced)
     for a, b in zip(whole, sliced):
         assert a.shape == b.shape and torch.equal(a, b)
+
+
+def test_captured_graph_sees_weight_updates():
+    """the fused executor runs on private packed copies of the weights whose addresses are baked into
+    captured graphs.  After an in-place weight update + one eager forward (which re-packs into the SAME buffers),
+    replaying the OLD graph must give the NEW result, and the pack buffers must not have moved."""
+    from aanet_b200.pipeline import HotPath
+    torch.manual_seed(326)
+    hp = HotPath(96, num_deform_blocks=3).cuda().eval()
+    L = [torch.relu(torch.randn(1, 32, 24 >> s, 48 >> s, device="cuda")) for s in range(3)]
+    R = [torch.relu(torch.randn(1, 32, 24 >> s, 48 >> s, device="cuda")) for s in range(3)]
+    graph, outs = hp.capture(L, R)
+    graph.replay(); torch.cuda.synchronize()
+    before = outs[-1].clone()
+    fz = hp.aggregation._aanet_fused
+    ptr = fz.final[0].wpack.data_ptr()
+    with torch.no_grad():
+        hp.aggregation.final_conv[0].weight.mul_(0.5)
+        hp.aggregation.fusions[0].branches[0][0].conv2.weight.add_(0.01)
+        want = hp(L, R)[-1].clone()                      # eager forward: re-packs in place
+    assert hp.aggregation._aanet_fused is fz and fz.final[0].wpack.data_ptr() == ptr
+    graph.replay(); torch.cuda.synchronize()
+    assert not torch.equal(before, want)
+    assert torch.equal(outs[-1], want)
+
+
+def test_fused_executor_peak_memory():
+    """The executor's lifetime plan: peak extra memory of one aggregation pass stays below 8 volumes of the
+    1/3-scale size per pair (a keep-everything plan holds ~70), so configs 3 and 5 run in one pass."""
+    import aanet_b200.nets as n
+    torch.manual_seed(326)
+    D0, H, W, B = 64, 96, 160, 4
+    agg = n.AdaptiveAggregation(D0, num_deform_blocks=3, intermediate_supervision=False).cuda().eval()
+    costs = [torch.randn(B, H >> s, W >> s, D0 >> s, device="cuda") for s in range(3)]   # channels-last
+    from aanet_b200 import fused
+    with torch.no_grad():
+        fused.run(agg, costs, nhwc=True)                 # packs the weights
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        out = fused.run(agg, costs, nhwc=True)
+        torch.cuda.synchronize()
+    vol = 4 * B * D0 * H * W
+    peak = (torch.cuda.max_memory_allocated() - base) / vol
+    print("peak extra memory: %.2f volumes of the 1/3-scale size" % peak)
+    assert out[0].shape == (B, D0, H, W)
+    assert peak < 8.0

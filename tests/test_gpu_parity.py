@@ -69,6 +69,22 @@ def test_corr_oracle(ops, shape):
     assert rel_err(npy(gR), rR) < GRAD_TOL
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_corr_bwd_second_device_large_smem(ops):
+    """One process driving two GPUs (the reference's nn.DataParallel scripts): the backward kernel's > 48 KB
+    dynamic shared memory opt-in is per device."""
+    rng = np.random.default_rng(5)
+    L = np.maximum(rng.standard_normal((1, 8, 2, 150)), 0).astype(np.float32)
+    R = np.maximum(rng.standard_normal((1, 8, 2, 150)), 0).astype(np.float32)
+    g = rng.standard_normal((1, 96, 2, 150)).astype(np.float32)
+    rL, rR = orc.corr_bwd(L, R, g)
+    for dev in ("cuda:0", "cuda:1"):
+        Lc = torch.from_numpy(L).to(dev).requires_grad_(); Rc = torch.from_numpy(R).to(dev).requires_grad_()
+        out = ops.correlation(Lc, Rc, 96)
+        gL, gR = torch.autograd.grad(out, (Lc, Rc), torch.from_numpy(g).to(dev))
+        assert rel_err(npy(gL), rL) < GRAD_TOL and rel_err(npy(gR), rR) < GRAD_TOL
+
+
 def test_corr_full_size_properties(ops):
     """KITTI 1/3 scale (BASELINE config 2): linearity in L, zero band, d=0 plane = channel mean."""
     torch.manual_seed(326)
@@ -184,6 +200,7 @@ def test_mdcn_golden(ops, golden, tag, mdcn_path):
     (1, 96, 96, 9, 11, 1, 2, 1, 8, False),
     (2, 12, 18, 10, 10, 1, 1, 3, 2, True),       # conv groups straddling deformable groups
     (1, 128, 128, 6, 20, 1, 2, 1, 1, False),     # two output tiles
+    (1, 24, 24, 7, 9, 1, 2, 1, 2, False),        # tcgen05 backward with B*K*dg*Ho*Wo % 4 != 0 (partial warps in the scatter)
 ])
 def test_mdcn_oracle(ops, cfg, mdcn_path):
     B, Ci, Co, H, W, st, dil, grp, dg, bias = cfg
@@ -473,3 +490,37 @@ def test_corr_nhwc_equals_nchw(ops, shape):
         ops.correlation_nhwc(L, R, 130)
     with pytest.raises(RuntimeError):
         ops.correlation_nhwc(L, R, 6)
+
+
+# ------------------------------------------------------------------------------------ 5-D volumes (cost.py:22-38)
+@pytest.mark.parametrize("kind", ["difference", "concat"])
+@pytest.mark.parametrize("tag", ["a", "narrow"])
+def test_cost5d_golden(golden, kind, tag):
+    import aanet_b200.nets as n
+    z = golden("cost5d")
+    k = "%s_%s_" % (kind, tag)
+    L, R = cu(z[k + "L"]).requires_grad_(), cu(z[k + "R"]).requires_grad_()
+    out = n.CostVolume(int(z[k + "D"]), kind)(L, R)
+    assert np.array_equal(npy(out), z[k + "out"])                 # a subtraction / a copy: bit-exact
+    gL, gR = torch.autograd.grad(out, (L, R), cu(z[k + "g"]))
+    assert rel_err(npy(gL), z[k + "gL"]) < 1e-5 and rel_err(npy(gR), z[k + "gR"]) < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["difference", "concat"])
+@pytest.mark.parametrize("shape", [(1, 32, 20, 52, 48), (2, 5, 3, 31, 7)])
+def test_cost5d_oracle(kind, shape):
+    """StereoNet/PSMNet-like sizes (W % 4 == 0: 128-bit stores) and ragged ones, plus the pyramid wrapper."""
+    import aanet_b200.nets as n
+    B, C, H, W, D = shape
+    rng = np.random.default_rng(7)
+    L = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    R = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    Lc, Rc = cu(L).requires_grad_(), cu(R).requires_grad_()
+    out = n.CostVolume(D, kind)(Lc, Rc)
+    assert np.array_equal(npy(out), orc.cost5d_fwd(L, R, D, kind))
+    g = rng.standard_normal(out.shape).astype(np.float32)
+    gL, gR = torch.autograd.grad(out, (Lc, Rc), cu(g))
+    rL, rR = orc.cost5d_bwd(g, kind)
+    assert rel_err(npy(gL), rL) < 1e-5 and rel_err(npy(gR), rR) < 1e-5
+    pyr = n.CostVolumePyramid(D, kind)([cu(L), cu(L[..., ::2, ::2])], [cu(R), cu(R[..., ::2, ::2])])
+    assert np.array_equal(npy(pyr[1]), orc.cost5d_fwd(L[..., ::2, ::2], R[..., ::2, ::2], D // 2, kind))

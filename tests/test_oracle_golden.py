@@ -130,3 +130,16 @@ def test_refine_frontend_oracle_vs_reference(golden, tag):
     assert np.abs(disp - z[tag + "_disp"]).max() < 1e-5 * max(1.0, np.abs(z[tag + "_disp"]).max())
     assert np.abs(concat - z[tag + "_concat"]).max() < 1e-5
     assert np.array_equal(concat[:, 3:], z[tag + "_left"])
+
+
+@pytest.mark.parametrize("kind", ["difference", "concat"])
+@pytest.mark.parametrize("tag", ["a", "narrow"])
+def test_cost5d_oracle_golden(golden, kind, tag):
+    """numpy restatement of nets/cost.py:22-38 against the reference's own CostVolume (bit-exact forward)."""
+    from oracle import oracle as orc
+    z = golden("cost5d")
+    k = "%s_%s_" % (kind, tag)
+    out = orc.cost5d_fwd(z[k + "L"], z[k + "R"], int(z[k + "D"]), kind)
+    assert out.shape == z[k + "out"].shape and np.array_equal(out, z[k + "out"])
+    gL, gR = orc.cost5d_bwd(z[k + "g"], kind)
+    assert rel_err(gL, z[k + "gL"]) < 1e-6 and rel_err(gR, z[k + "gR"]) < 1e-6
