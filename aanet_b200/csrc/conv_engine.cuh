@@ -39,6 +39,16 @@ struct ConvBatch {
     int total_tiles;
 };
 
+// TMEM geometry of an N tile with the stacked [B_hi | B_lo] operand (2 * BN accumulator columns, two accumulators).
+template <int BN> struct EngineCfgLite {
+    static constexpr int kAccCols = 2 * BN;
+    static constexpr int kAccStride = kAccCols <= 32 ? 32 : kAccCols <= 64 ? 64 : 128;
+    static constexpr uint32_t kTmemCols = 2 * kAccStride;
+};
+
+// halo_engine.cu: TMA-halo kernels for stride-1 dense convolutions (AANET_ERR_UNSUPPORTED = take the gather engine)
+int conv_halo_launch(const ConvParams &p, int BN, cudaStream_t stream);
+
 bool conv_umma_supported(const MdcnDims &d, bool deform);
 int conv_umma_pick_bn(int Og);
 size_t conv_umma_wpack_bytes(const MdcnDims &d, int bn);

@@ -23,7 +23,7 @@ def _run(variant, model, weights, out, extra=()):
     return json.loads(p.stdout.strip().splitlines()[-1])
 
 
-@pytest.mark.parametrize("model,H,W", [("aanet", 384, 1248), ("aanet+", 192, 624)])
+@pytest.mark.parametrize("model,H,W", [("aanet", 384, 1248), ("aanet+", 576, 960)])
 def test_dropin_inside_reference_aanet(tmp_path, model, H, W):
     from oracle import build_ref, stage_ref
     if stage_ref.staged_path() is None or build_ref.built_path() is None:
