@@ -48,6 +48,10 @@ template <int BN> struct EngineCfgLite {
 
 // halo_engine.cu: TMA-halo kernels for stride-1 dense convolutions (AANET_ERR_UNSUPPORTED = take the gather engine)
 int conv_halo_launch(const ConvParams &p, int BN, cudaStream_t stream);
+// deform_halo.cu: DCNv2 with the bilinear gather served from a TMA-staged halo (same convention)
+int deform_halo_launch(const ConvParams &p, int BN, cudaStream_t stream);
+// deform_tmem.cu: the same with the sampled operand written straight into tensor memory (tcgen05.st, TMEM-A MMA)
+int deform_tmem_launch(const ConvParams &p, int BN, cudaStream_t stream);
 
 bool conv_umma_supported(const MdcnDims &d, bool deform);
 int conv_umma_pick_bn(int Og);

@@ -120,6 +120,12 @@ int conv_umma_launch_batch(const ConvParams *probs, int n, bool deform, int bn, 
         const int rc = conv_halo_launch(probs[0], BN, stream);
         if (rc != AANET_ERR_UNSUPPORTED) return rc;
     }
+    if (n == 1 && deform) {         // ISA layers with 32-channel deformable groups: gather from a TMA-staged halo
+        int rc = deform_tmem_launch(probs[0], BN, stream);
+        if (rc != AANET_ERR_UNSUPPORTED) return rc;
+        rc = deform_halo_launch(probs[0], BN, stream);
+        if (rc != AANET_ERR_UNSUPPORTED) return rc;
+    }
     ConvBatch batch{};
     batch.n = n;
     long tiles = 0;

@@ -1,0 +1,524 @@
+// Modulated deformable convolution (DCNv2, the ISA operator; reference deform_conv_cuda_kernel.cu:570-633 +
+// deform_conv_cuda.cpp:539-561) -- round-2 kernel: the sampled operand never touches shared memory.
+//
+//   input halo   ONE cp.async.bulk.tensor (4-D tensor map over the channels-last activation, SWIZZLE_128B) per
+//                (tile, 32-channel block) stages the patch a 16 x 8 tile can reach -- the dilated tap grid plus a
+//                margin for the learned offsets and the bilinear corner -- in shared memory as 128-byte lines
+//                [pixel][32 channels].  Out-of-image pixels are zero-filled by the TMA unit, which IS the operator's
+//                padding rule (every corner outside the image contributes 0, cu:467-497), so the fast path has no
+//                validity logic.  Two slots: the next block's halo streams in under the current one's taps.
+//   gather       thread = output pixel = TMEM lane.  Per K block (tap, 32 channels of one deformable group) a
+//                producer thread computes its own bilinear sample (no sharing, no shuffles), reads its four corner
+//                lines with LDS.128 (the 128-byte swizzle makes 8 neighbouring pixels hit 8 different bank groups),
+//                combines, splits into tf32 hi + lo and writes its row of the A operand straight into TENSOR MEMORY
+//                with tcgen05.st (32x32b: one lane per thread).  Samples whose 2 x 2 footprint leaves the staged
+//                patch fall back to a global gather with the reference's validity rules, per row.
+//   MMA          tcgen05.mma kind::tf32 with A in TMEM, B (pre-packed [B_hi | B_lo] weight block, cp.async.bulk)
+//                in shared memory: A_hi x [B_hi | B_lo] (N = 2 BN) + A_lo x B_hi (N = BN) per 8-channel step, i.e. the
+//                same 3xTF32 arithmetic as conv_umma_kernel.cuh, but the tensor core no longer re-reads a 32 KB
+//                hi/lo tile from shared memory per K block and the producers no longer store one.
+// Why: the round-1 gather engine and the shared-memory-halo variant (deform_halo.cu) are both bound by shared-memory
+// bandwidth -- per K block ~64 KB of corner reads + 32 KB of operand stores + 56 KB of tensor-core operand reads at
+// 128 B/clk (profiles/r02: deform_halo 50 % LSU + tensor reads).  Keeping A in TMEM removes 88 KB of the 180 KB.
+//
+// Roles (640 threads): warps 0-3 epilogue (TMEM lane quarters), 4-15 producers (3 groups x 4 warps, warp % 4 =
+// lane quarter; group g owns A stage g), 16 halo TMA, 17 weight loader, 18 MMA issuer, 19 idle.
+// TMEM (512 columns): two accumulators of 2 BN columns, three A stages of 64 columns (32 hi + 32 lo).
+// Requirements: stride 1, channels per conv group and per deformable group multiples of 32, channels-last output
+// with a multiple of 16 channels per group, no residual -- the ISA layer of nets/deform.py:216-236 as the fused
+// executor calls it.  Everything else takes the round-1 engine.
+#include <stdio.h>
+#include <stdlib.h>
+#include "conv_engine.cuh"
+#include "tma.cuh"
+#include "umma.cuh"
+
+namespace aanet {
+
+constexpr int kTM = 128, kTTW = 16, kTTH = 8;          // 16 x 8 output pixels per tile
+constexpr int kTGroups = 3, kTProdWarp0 = 4, kTProdWarps = 4 * kTGroups;
+constexpr int kTTmaWarp = kTProdWarp0 + kTProdWarps, kTLoadWarp = kTTmaWarp + 1, kTMmaWarp = kTTmaWarp + 2;
+constexpr int kTThreads = 640;
+constexpr int kTStages = kTGroups;
+constexpr int kTAccCol = 0, kTACol = 256, kTAStageCols = 64;      // TMEM column map
+constexpr int kTSmemBudget = 214 * 1024;
+
+struct DeformTmemParams {
+    ConvParams p;
+    int HH, HWd, lines, slot_bytes;    // halo box (rows, pixels per row), lines = HH * HWd, bytes rounded to 1024
+    int margin_y, margin_x, n_cb, prof;   // pixels of offset the halo covers above/below and left/right
+};
+
+struct TItem { int grp, nt, b, ty, tx; };
+
+__device__ __forceinline__ TItem t_item(const ConvParams &p, int t) {
+    TItem it;
+    const int pt = t % p.n_ptiles, gn = t / p.n_ptiles;
+    it.grp = gn / p.n_tiles_n; it.nt = gn - it.grp * p.n_tiles_n;
+    it.b = pt / p.tiles_per_img;
+    const int r = pt - it.b * p.tiles_per_img;
+    it.ty = r / p.tiles_x; it.tx = r - it.ty * p.tiles_x;
+    return it;
+}
+
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// thread t of the warp writes 8 consecutive 32-bit columns of TMEM lane (base lane + t)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                   "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                   "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kTThreads, 1)
+deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_constant__ CUtensorMap tm) {
+    constexpr int S = kTStages;
+    constexpr int kBTile = 2 * BN * 32 * 4;                   // [B_hi | B_lo] of one K block
+    static_assert(2 * BN <= 128, "accumulator stride is 128 columns");
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_halo_full[2], bar_halo_empty[2];
+    __shared__ __align__(8) uint64_t bar_full_a[S], bar_full_b[S], bar_empty[S];
+    __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(16) float s_aff[2][BN];
+    __shared__ int2 s_tapoff[64];                             // per tap: (ki * dil - pad, kj * dil - pad)
+
+    const ConvParams &p = hp.p;
+    const MdcnDims &d = p.d;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t *smem = smem_raw + ((1024 - (umma::smem_u32(smem_raw) & 1023)) & 1023);
+    uint8_t *halo0 = smem + (size_t)S * kBTile;               // two halo slots behind the weight ring
+    if (tid < d.K) s_tapoff[tid] = make_int2((tid / d.kw) * d.dil - d.pad, (tid % d.kw) * d.dil - d.pad);
+    const int T = d.K, n_cb = hp.n_cb, total = p.total_tiles;
+
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            umma::mbar_init(&bar_halo_full[s], 1);            // expect_tx + TMA bytes
+            umma::mbar_init(&bar_halo_empty[s], kTProdWarps); // every producer warp, after its last tap of the slot
+        }
+        for (int s = 0; s < S; ++s) {
+            umma::mbar_init(&bar_full_a[s], 4);               // the four warps of the filling group
+            umma::mbar_init(&bar_full_b[s], 1);
+            umma::mbar_init(&bar_empty[s], 1);                // tcgen05.commit: A stage (TMEM) and B stage (smem) free
+        }
+        for (int a = 0; a < 2; ++a) {
+            umma::mbar_init(&bar_acc_full[a], 1);
+            umma::mbar_init(&bar_acc_empty[a], 4);
+        }
+        umma::fence_mbar_init();
+    }
+    if (warp == kTMmaWarp) umma::tmem_alloc<512>(&s_tmem);
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem_base = s_tmem;
+    pdl_wait();
+    bool triggered = false;
+
+    if (warp < 4) {
+        // ================================ epilogue (channels-last, affine + activation) ===========
+        const int q = warp, row = q * 32 + lane;
+        uint32_t ti = 0;
+        int cur_gn = -1;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
+            if (t + (int)gridDim.x >= total) { pdl_trigger(); triggered = true; }
+            const TItem it = t_item(p, t);
+            const int a = ti & 1;
+            int e_oh = it.ty * kTTH + (row >> 4), e_ow = it.tx * kTTW + (row & 15);
+            const bool p_ok = e_oh < d.Ho && e_ow < d.Wo;
+            e_oh = min(e_oh, d.Ho - 1); e_ow = min(e_ow, d.Wo - 1);
+            const int o_base = it.grp * d.Og + it.nt * BN;
+            const int n_valid = min(BN, d.Og - it.nt * BN);
+            if (it.grp * p.n_tiles_n + it.nt != cur_gn) {
+                cur_gn = it.grp * p.n_tiles_n + it.nt;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (tid < BN) {
+                    float sc = 1.f, sh = 0.f;
+                    if (tid < n_valid) {
+                        const int o = o_base + tid;
+                        if (p.scale) { sc = __ldg(p.scale + o); sh = __ldg(p.shift + o); }
+                        if (p.bias) sh = fmaf(__ldg(p.bias + o), sc, sh);
+                    }
+                    s_aff[0][tid] = sc; s_aff[1][tid] = sh;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            float *dst_px = p.out + ((long)it.b * d.P + (long)e_oh * d.Wo + e_ow) * d.Cout + o_base;
+            umma::mbar_wait_sleep(&bar_acc_full[a], (ti >> 1) & 1);
+            umma::tc_fence_after();
+#pragma unroll 1
+            for (int n0 = 0; n0 < BN; n0 += 16) {
+                float acc[16], acc2[16];
+                umma::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + kTAccCol + a * 128 + n0, acc);
+                umma::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + kTAccCol + a * 128 + BN + n0, acc2);
+                if (!p_ok || n0 >= n_valid) continue;
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 sc = *reinterpret_cast<const float4 *>(&s_aff[0][n0 + i]);
+                    const float4 sh = *reinterpret_cast<const float4 *>(&s_aff[1][n0 + i]);
+                    acc[i] = fmaf(acc[i] + acc2[i], sc.x, sh.x); acc[i + 1] = fmaf(acc[i + 1] + acc2[i + 1], sc.y, sh.y);
+                    acc[i + 2] = fmaf(acc[i + 2] + acc2[i + 2], sc.z, sh.z); acc[i + 3] = fmaf(acc[i + 3] + acc2[i + 3], sc.w, sh.w);
+                }
+                if (p.act == ACT_RELU) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[i] = fmaxf(acc[i], 0.f);
+                } else if (p.act == ACT_LEAKY) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[i] = acc[i] > 0.f ? acc[i] : acc[i] * p.slope;
+                }
+                float4 *dst = reinterpret_cast<float4 *>(dst_px + n0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+            }
+            umma::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(&bar_acc_empty[a]);
+        }
+    } else if (warp < kTProdWarp0 + kTProdWarps) {
+        // ================================ A producers: thread = pixel = TMEM lane =================
+        const int pw = warp - kTProdWarp0;
+        const int grpi = pw >> 2, q = pw & 3;                 // producer group; TMEM lane quarter (== warp % 4)
+        const int row = q * 32 + lane;                        // row of the tile this thread produces
+        long long c_wait_halo = 0, c_wait_stage = 0;
+        const long long pt0 = clock64();
+
+        // Walk state of this group's K blocks (every kTGroups-th of the CTA's (tile, channel block, tap) sequence).
+        // Everything that only changes with the tile or the channel block is decoded when it changes, not per K
+        // block (the first version spent 450 of its 730 instructions per K block on index arithmetic).
+        struct St {
+            int t, cb, tap; uint32_t it, hs;
+            int b, grp, oh, ow, hy0, hx0; bool ok;
+            const float *off, *msk;          // offset / mask pointers of my pixel, channel 0
+            long ch0;                        // first offset channel of the deformable group of (grp, cb)
+        };
+        auto decode_tile = [&](St &c) {
+            const TItem item = t_item(p, c.t);
+            c.b = item.b; c.grp = item.grp;
+            c.oh = item.ty * kTTH + (row >> 4); c.ow = item.tx * kTTW + (row & 15);
+            c.ok = c.oh < d.Ho && c.ow < d.Wo;
+            c.oh = min(c.oh, d.Ho - 1); c.ow = min(c.ow, d.Wo - 1);
+            c.hy0 = item.ty * kTTH - d.pad - hp.margin_y; c.hx0 = item.tx * kTTW - d.pad - hp.margin_x;
+            const long pc = (long)c.oh * d.Wo + c.ow;
+            c.off = p.offset + (long)item.b * p.off_bs + pc * p.off_ps;
+            c.msk = p.mask ? p.mask + (long)item.b * p.mask_bs + pc * p.mask_ps : nullptr;
+        };
+        auto decode_cb = [&](St &c) { c.ch0 = (long)((c.grp * d.Cg + c.cb * 32) / d.Cd) * d.K; };
+        auto advance = [&](St &c, int n) {
+            c.it += n; c.tap += n;
+            if (c.tap < T) return;
+            bool new_tile = false;
+            while (c.tap >= T) {
+                c.tap -= T; ++c.cb; ++c.hs;
+                if (c.cb == n_cb) { c.cb = 0; c.t += gridDim.x; new_tile = true; }
+            }
+            if (c.t < total) {
+                if (new_tile) decode_tile(c);
+                decode_cb(c);
+            }
+        };
+        auto load_geom = [&](const St &c, float &gh, float &gw, float &gm) {
+            const long ch = c.ch0 + c.tap;
+            gh = __ldg(c.off + (ch * 2) * p.off_cs);
+            gw = __ldg(c.off + (ch * 2 + 1) * p.off_cs);
+            gm = c.msk ? __ldg(c.msk + ch * p.mask_cs) : 1.f;
+        };
+
+        St cur;
+        cur.t = (int)blockIdx.x; cur.cb = 0; cur.tap = 0; cur.it = 0u; cur.hs = 0u;
+        if (cur.t < total) { decode_tile(cur); decode_cb(cur); }
+        advance(cur, grpi);
+        float gh = 0.f, gw = 0.f, gm = 0.f;
+        if (cur.t < total) load_geom(cur, gh, gw, gm);
+        int2 tapo = s_tapoff[cur.tap];
+        uint32_t ready_hs = 0xffffffffu;
+        while (cur.t < total) {
+            // offsets / mask of my NEXT K block: each (tap, deformable group) plane is touched once per tile, so
+            // these loads are DRAM misses and must be in flight while the current K block is produced
+            St nxt = cur;
+            advance(nxt, kTGroups);
+            float ngh = 0.f, ngw = 0.f, ngm = 0.f;
+            if (nxt.t < total) load_geom(nxt, ngh, ngw, ngm);
+            const int2 ntapo = s_tapoff[nxt.tap];                                // (ki * dil - pad, kj * dil - pad)
+            const int s = cur.it % S;
+            const uint32_t ph = (cur.it / S) & 1;
+            const int hslot = cur.hs & 1;
+            const uint32_t halo = umma::smem_u32(halo0 + (size_t)hslot * hp.slot_bytes);
+            // ---- my bilinear sample for this (tap, deformable group)
+            const float py = (float)(cur.oh + tapo.x) + gh;
+            const float px = (float)(cur.ow + tapo.y) + gw;
+            const float fy = floorf(py), fx = floorf(px);
+            const float lh = py - fy, lw = px - fx;
+            const float m = cur.ok ? gm : 0.f;
+            const float ry = fy - (float)cur.hy0, rx = fx - (float)cur.hx0;      // top-left corner inside the halo?
+            const bool inside = ry >= 0.f && rx >= 0.f && ry <= (float)(hp.HH - 2) && rx <= (float)(hp.HWd - 2);
+            float w0 = (1.f - lh) * (1.f - lw) * m, w1 = (1.f - lh) * lw * m, w2 = lh * (1.f - lw) * m, w3 = lh * lw * m;
+
+            if (ready_hs != cur.hs) {
+                const long long t0 = clock64();
+                umma::mbar_wait(&bar_halo_full[hslot], (cur.hs >> 1) & 1);
+                c_wait_halo += clock64() - t0;
+                ready_hs = cur.hs;
+            }
+            {
+                const long long t0 = clock64();
+                umma::mbar_wait(&bar_empty[s], ph ^ 1);       // the MMAs that read this A stage have retired
+                c_wait_stage += clock64() - t0;
+            }
+            umma::tc_fence_after();
+            const uint32_t a_col = tmem_base + ((uint32_t)(q * 32) << 16) + kTACol + s * kTAStageCols;
+
+            // Fast path: corner line L sits at L * 128 bytes of the slot; its 16-byte chunk c at (c ^ (L & 7)) * 16
+            // (SWIZZLE_128B).  With P = line address | ((L & 7) << 4) the chunk address is P ^ (c << 4).
+            // Slow path (footprint leaves the staged patch): global gather with the reference's validity rules.
+            // tcgen05.st is warp-collective (.sync.aligned): only the LOADS may diverge, the stores are issued by the
+            // whole warp after reconvergence.
+            uint32_t P0 = 0, P1 = 0, P2 = 0, P3 = 0;
+            const float4 *g0 = nullptr, *g1 = nullptr, *g2 = nullptr, *g3 = nullptr;
+            if (inside) {
+                const int l0 = (int)ry * hp.HWd + (int)rx, l2 = l0 + hp.HWd;
+                const uint32_t p0 = halo + (uint32_t)l0 * 128, p2 = halo + (uint32_t)l2 * 128;
+                P0 = p0 | ((uint32_t)(l0 & 7) << 4); P1 = (p0 + 128) | ((uint32_t)((l0 + 1) & 7) << 4);
+                P2 = p2 | ((uint32_t)(l2 & 7) << 4); P3 = (p2 + 128) | ((uint32_t)((l2 + 1) & 7) << 4);
+            } else {
+                const Sample sm = make_sample(py, px, d.H, d.W);
+                w0 = sm.w[0] * m; w1 = sm.w[1] * m; w2 = sm.w[2] * m; w3 = sm.w[3] * m;
+                const float *x_b = p.x + (long)cur.b * d.HW * d.Cin + cur.grp * d.Cg + cur.cb * 32;
+                g0 = reinterpret_cast<const float4 *>(x_b + (long)sm.i[0] * d.Cin);
+                g1 = reinterpret_cast<const float4 *>(x_b + (long)sm.i[1] * d.Cin);
+                g2 = reinterpret_cast<const float4 *>(x_b + (long)sm.i[2] * d.Cin);
+                g3 = reinterpret_cast<const float4 *>(x_b + (long)sm.i[3] * d.Cin);
+            }
+            auto combine_store = [&](int c8, const float4 (&qa)[2][4]) {
+                float hi[8], lo[8];
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const float v0 = w0 * qa[cc][0].x + w1 * qa[cc][1].x + w2 * qa[cc][2].x + w3 * qa[cc][3].x;
+                    const float v1 = w0 * qa[cc][0].y + w1 * qa[cc][1].y + w2 * qa[cc][2].y + w3 * qa[cc][3].y;
+                    const float v2 = w0 * qa[cc][0].z + w1 * qa[cc][1].z + w2 * qa[cc][2].z + w3 * qa[cc][3].z;
+                    const float v3 = w0 * qa[cc][0].w + w1 * qa[cc][1].w + w2 * qa[cc][2].w + w3 * qa[cc][3].w;
+                    umma::split_tf32(v0, hi[cc * 4 + 0], lo[cc * 4 + 0]); umma::split_tf32(v1, hi[cc * 4 + 1], lo[cc * 4 + 1]);
+                    umma::split_tf32(v2, hi[cc * 4 + 2], lo[cc * 4 + 2]); umma::split_tf32(v3, hi[cc * 4 + 3], lo[cc * 4 + 3]);
+                }
+                tmem_st8(a_col + c8 * 8, hi);
+                tmem_st8(a_col + 32 + c8 * 8, lo);
+            };
+            if (__all_sync(0xffffffffu, inside)) {
+                // the whole warp reads from the staged patch (the common case): no branches in the loop; the four
+                // corner chunks of chunk c+1 are requested before chunk c is combined (LDS latency under load is
+                // ~100 cycles and only three producer warps share a scheduler)
+                float4 qb[2][4];
+                qb[0][0] = lds128(P0); qb[0][1] = lds128(P1); qb[0][2] = lds128(P2); qb[0][3] = lds128(P3);
+                float hi[8], lo[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int b = c & 1;
+                    if (c + 1 < 8) {
+                        const uint32_t x = (uint32_t)((c + 1) << 4);
+                        qb[b ^ 1][0] = lds128(P0 ^ x); qb[b ^ 1][1] = lds128(P1 ^ x);
+                        qb[b ^ 1][2] = lds128(P2 ^ x); qb[b ^ 1][3] = lds128(P3 ^ x);
+                    }
+                    const float v0 = w0 * qb[b][0].x + w1 * qb[b][1].x + w2 * qb[b][2].x + w3 * qb[b][3].x;
+                    const float v1 = w0 * qb[b][0].y + w1 * qb[b][1].y + w2 * qb[b][2].y + w3 * qb[b][3].y;
+                    const float v2 = w0 * qb[b][0].z + w1 * qb[b][1].z + w2 * qb[b][2].z + w3 * qb[b][3].z;
+                    const float v3 = w0 * qb[b][0].w + w1 * qb[b][1].w + w2 * qb[b][2].w + w3 * qb[b][3].w;
+                    umma::split_tf32(v0, hi[b * 4 + 0], lo[b * 4 + 0]); umma::split_tf32(v1, hi[b * 4 + 1], lo[b * 4 + 1]);
+                    umma::split_tf32(v2, hi[b * 4 + 2], lo[b * 4 + 2]); umma::split_tf32(v3, hi[b * 4 + 3], lo[b * 4 + 3]);
+                    if (b) {
+                        tmem_st8(a_col + (c >> 1) * 8, hi);
+                        tmem_st8(a_col + 32 + (c >> 1) * 8, lo);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    float4 qa[2][4];
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int c = c8 * 2 + cc;
+                        if (inside) {
+                            const uint32_t x = (uint32_t)(c << 4);
+                            qa[cc][0] = lds128(P0 ^ x); qa[cc][1] = lds128(P1 ^ x); qa[cc][2] = lds128(P2 ^ x); qa[cc][3] = lds128(P3 ^ x);
+                        } else {
+                            qa[cc][0] = __ldg(g0 + c); qa[cc][1] = __ldg(g1 + c); qa[cc][2] = __ldg(g2 + c); qa[cc][3] = __ldg(g3 + c);
+                        }
+                    }
+                    __syncwarp();
+                    combine_store(c8, qa);
+                }
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            umma::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                umma::mbar_arrive(&bar_full_a[s]);
+                // last K block of this group inside the halo slot: this warp has read everything it needs from it
+                if (nxt.hs != cur.hs) umma::mbar_arrive(&bar_halo_empty[hslot]);
+            }
+            cur = nxt; gh = ngh; gw = ngw; gm = ngm; tapo = ntapo;
+        }
+        if (hp.prof && blockIdx.x == 0 && lane == 0 && q == 0)
+            printf("deform tmem producer group %d: total %lld cycles, wait halo %lld, wait stage %lld\n", grpi,
+                   clock64() - pt0, c_wait_halo, c_wait_stage);
+    } else if (warp == kTTmaWarp) {
+        if (lane == 0) {
+            // ================================ halo loader (tensor-map TMA) ========================
+            uint32_t hs = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const TItem it = t_item(p, t);
+                for (int cb = 0; cb < n_cb; ++cb, ++hs) {
+                    const int s = hs & 1;
+                    umma::mbar_wait_sleep(&bar_halo_empty[s], ((hs >> 1) & 1) ^ 1);
+                    umma::mbar_expect_tx(&bar_halo_full[s], hp.lines * 128);
+                    umma::tma_load_4d(halo0 + (size_t)s * hp.slot_bytes, &tm, it.grp * d.Cg + cb * 32,
+                                      it.tx * kTTW - d.pad - hp.margin_x, it.ty * kTTH - d.pad - hp.margin_y, it.b,
+                                      &bar_halo_full[s]);
+                }
+            }
+        }
+    } else if (warp == kTLoadWarp) {
+        if (lane == 0) {
+            // ================================ weight loader ========================================
+            uint32_t itc = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const TItem it = t_item(p, t);
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(p.wpack) +
+                                     (size_t)(it.grp * p.n_tiles_n + it.nt) * p.KB * kBTile;
+                for (int cb = 0; cb < n_cb; ++cb)
+                    for (int tap = 0; tap < T; ++tap, ++itc) {
+                        const int s = itc % S;
+                        umma::mbar_wait_sleep(&bar_empty[s], ((itc / S) & 1) ^ 1);
+                        umma::mbar_expect_tx(&bar_full_b[s], kBTile);
+                        umma::bulk_g2s(smem + (size_t)s * kBTile, src + (size_t)(tap * n_cb + cb) * kBTile, kBTile,
+                                       &bar_full_b[s]);
+                    }
+            }
+        }
+    } else if (warp == kTMmaWarp) {
+        if (lane == 0) {
+            // ================================ MMA issuer (A from tensor memory) ====================
+            constexpr uint32_t idesc = umma::make_idesc_tf32(kTM, BN);
+            constexpr uint32_t idesc2 = umma::make_idesc_tf32(kTM, 2 * BN);
+            uint32_t itc = 0, ti = 0;
+            long long c_acc = 0, c_a = 0, c_b = 0, c_issue = 0, t0 = clock64();
+            const long long t_start = t0;
+#define TPROF(acc_) do { const long long t1 = clock64(); acc_ += t1 - t0; t0 = t1; } while (0)
+            const int nkb = n_cb * T;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
+                const int a = ti & 1;
+                umma::mbar_wait_sleep(&bar_acc_empty[a], ((ti >> 1) & 1) ^ 1);
+                umma::tc_fence_after();
+                TPROF(c_acc);
+                const uint32_t d_tmem = tmem_base + kTAccCol + a * 128;
+                for (int kb = 0; kb < nkb; ++kb, ++itc) {
+                    const int s = itc % S;
+                    const uint32_t ph = (itc / S) & 1;
+                    umma::mbar_wait_sleep(&bar_full_a[s], ph);
+                    TPROF(c_a);
+                    umma::mbar_wait_sleep(&bar_full_b[s], ph);
+                    umma::tc_fence_after();
+                    TPROF(c_b);
+                    const uint32_t a_col = tmem_base + kTACol + s * kTAStageCols;
+                    const uint64_t b_hi = umma::make_desc_sw128(umma::smem_u32(smem + (size_t)s * kBTile));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        mma_tf32_ts(d_tmem, a_col + k * 8, umma::desc_advance(b_hi, k * 32), idesc2, (kb | k) != 0);
+                        mma_tf32_ts(d_tmem, a_col + 32 + k * 8, umma::desc_advance(b_hi, k * 32), idesc, 1);
+                    }
+                    umma::tc_commit(&bar_empty[s]);
+                    TPROF(c_issue);
+                }
+                umma::tc_commit(&bar_acc_full[a]);
+            }
+            if (hp.prof && blockIdx.x == 0)
+                printf("deform tmem MMA thread: %u tiles, total %lld cycles; wait acc %lld, wait A %lld, wait B %lld, issue %lld\n",
+                       ti, clock64() - t_start, c_acc, c_a, c_b, c_issue);
+        }
+    }
+    if (!triggered) pdl_trigger();
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == kTMmaWarp) {
+        umma::tc_fence_after();
+        umma::tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// --------------------------------------------------------------------------------------------- host side
+template <int BN>
+static int deform_tmem_launch_bn(const DeformTmemParams &hp, const CUtensorMap &tm, cudaStream_t stream) {
+    const size_t smem = (size_t)kTStages * 2 * BN * 32 * 4 + 2 * (size_t)hp.slot_bytes + 1024;
+    cudaFuncSetAttribute(deform_tmem_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int rounds = ceil_div(hp.p.total_tiles, num_sms());
+    const int grid = ceil_div(hp.p.total_tiles, rounds);
+    return launch_pdl(deform_tmem_kernel<BN>, dim3(grid), dim3(kTThreads), smem, stream, hp, tm);
+}
+
+// Returns AANET_ERR_UNSUPPORTED when the problem should take another kernel.
+int deform_tmem_launch(const ConvParams &src, int BN, cudaStream_t stream) {
+    { const char *e = getenv("AANET_DEFORM_TMEM"); if (e && e[0] == '0') return AANET_ERR_UNSUPPORTED; }   // A/B switch
+    const MdcnDims &d = src.d;
+    if (d.stride != 1 || d.Cg % 32 || d.Cd % 32 || !aligned16(src.x)) return AANET_ERR_UNSUPPORTED;
+    if (src.out_nchw || src.residual || d.Og % 16 || (d.Cout & 3) || src.act == ACT_OFFSET_MASK) return AANET_ERR_UNSUPPORTED;
+    if (BN != 32 && BN != 64) return AANET_ERR_UNSUPPORTED;
+    if (d.K < kTGroups) return AANET_ERR_UNSUPPORTED;       // every producer group must own a tap in every halo slot
+    DeformTmemParams hp;
+    hp.p = src;
+    const size_t ring = (size_t)kTStages * 2 * BN * 32 * 4;
+    // Halo plan.  The pitch (pixels per halo row) is rounded up to a multiple of 8 lines: a sample whose row index
+    // jitters by one (sub-pixel offsets of either sign) then keeps its swizzle key (line & 7), so neighbouring
+    // threads keep hitting different bank groups; the extra columns widen the horizontal margin.  Vertical margin:
+    // the largest (<= AANET_DEFORM_MARGIN, default 4) for which two slots fit next to the weight ring.
+    const char *em = getenv("AANET_DEFORM_MARGIN");
+    int margin = em ? atoi(em) : 4;
+    const char *ep8 = getenv("AANET_DEFORM_PITCH8");
+    const bool pitch8 = !(ep8 && ep8[0] == '0');
+    int mx = 0;
+    for (; margin >= 0; --margin) {
+        hp.HH = kTTH + (d.kh - 1) * d.dil + 2 * margin + 1;
+        const int wmin = kTTW + (d.kw - 1) * d.dil + 2 * margin + 1;
+        hp.HWd = pitch8 ? (wmin + 7) / 8 * 8 : wmin;
+        mx = margin + (hp.HWd - wmin) / 2;
+        hp.lines = hp.HH * hp.HWd;
+        hp.slot_bytes = (hp.lines * 128 + 1023) & ~1023;
+        if (hp.HH <= 256 && hp.HWd <= 256 && ring + 2 * (size_t)hp.slot_bytes <= (size_t)kTSmemBudget) break;
+    }
+    if (margin < 0) return AANET_ERR_UNSUPPORTED;
+    hp.margin_y = margin;
+    hp.margin_x = mx;
+    hp.n_cb = d.Cg / 32;
+    { const char *ep = getenv("AANET_HALO_PROF"); hp.prof = ep && ep[0] == '1'; }
+    ConvParams &p = hp.p;
+    p.n_tiles_n = ceil_div(d.Og, BN);
+    p.K = d.K * d.Cg;
+    p.KB = p.K / 32;
+    p.tiles_x = ceil_div(d.Wo, kTTW);
+    p.tiles_per_img = p.tiles_x * ceil_div(d.Ho, kTTH);
+    p.n_ptiles = d.B * p.tiles_per_img;
+    const long total = (long)d.groups * p.n_tiles_n * p.n_ptiles;
+    if (total > 0x3fffffffL) return AANET_ERR_UNSUPPORTED;
+    p.total_tiles = (int)total;
+    CUtensorMap tm;
+    const uint64_t dims[4] = {(uint64_t)d.Cin, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.B};
+    const uint64_t strides[3] = {(uint64_t)d.Cin * 4, (uint64_t)d.W * d.Cin * 4, (uint64_t)d.HW * d.Cin * 4};
+    const uint32_t box[4] = {32, (uint32_t)hp.HWd, (uint32_t)hp.HH, 1};
+    const int rc = make_tensor_map_f32(&tm, src.x, 4, dims, strides, box, true);
+    if (rc) return rc;
+    return BN == 64 ? deform_tmem_launch_bn<64>(hp, tm, stream) : deform_tmem_launch_bn<32>(hp, tm, stream);
+}
+
+}  // namespace aanet

@@ -17,6 +17,7 @@
 //   K order            (channel block, tap): a halo slot is released as soon as its taps are done, so the next
 //                      block's / tile's halo streams in underneath the MMAs (2-4 slots).
 //   Precision          3xTF32 exactly as the gather engine (conv_umma_kernel.cuh): A_raw x [B_hi | B_lo] + A_lo x B_hi.
+#include <stdio.h>
 #include <stdlib.h>
 #include "conv_engine.cuh"
 #include "tma.cuh"
@@ -28,7 +29,7 @@ constexpr int kHM = 128;                   // pixels per tile (UMMA M)
 constexpr int kHTW = 8, kHTH = 16;         // output tile: 8 wide (one 8-row descriptor group) x 16 tall
 constexpr int kHThreads = 384;
 constexpr int kHConvWarp0 = 4, kHTmaWarp = 8, kHLoadWarp = 9, kHMmaWarp = 10;
-constexpr int kHMaxSlots = 4, kHMaxBStages = 4;
+constexpr int kHMaxSlots = 4, kHMaxBStages = 8;
 constexpr int kHSmemBudget = 216 * 1024;
 
 struct HaloParams {
@@ -37,6 +38,8 @@ struct HaloParams {
     int slot_bytes;        // lines * 128 rounded up to 1024 (raw; the lo copy follows at + slot_bytes)
     int n_cb;              // 32-channel blocks per convolution group
     int n_slots, n_bst;
+    int rot;               // per-CTA tap rotation (AANET_HALO_ROT=0 turns it off)
+    int prof;              // debug: block 0 prints per-role cycle counters (AANET_HALO_PROF=1)
 };
 
 struct HaloItem { int grp, nt, b, ty, tx; };
@@ -70,6 +73,9 @@ halo_conv_kernel(const __grid_constant__ HaloParams hp, const __grid_constant__ 
     uint8_t *bstage0 = smem + (size_t)S * 2 * hp.slot_bytes;
     constexpr int kBStageBytes = 2 * BN * 32 * 4;
     const int T = d.K, n_cb = hp.n_cb, total = p.total_tiles;
+    // Every CTA streams the SAME weight blocks; walking the taps from a per-CTA start spreads the CTAs over the
+    // whole packed weight array instead of having all of them ask the same L2 lines at the same time.
+    const int rot = hp.rot ? (int)((blockIdx.x * 4u) % (unsigned)T) : 0;
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
@@ -100,6 +106,7 @@ halo_conv_kernel(const __grid_constant__ HaloParams hp, const __grid_constant__ 
         const int q = warp, row = q * 32 + lane;
         uint32_t ti = 0;
         int cur_gn = -1;
+        long long e_wait = 0, e_work = 0, et0 = clock64();
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
             if (t + (int)gridDim.x >= total) { pdl_trigger(); triggered = true; }
             const HaloItem it = halo_item(p, t);
@@ -126,8 +133,10 @@ halo_conv_kernel(const __grid_constant__ HaloParams hp, const __grid_constant__ 
             }
             const long pix_g = (long)it.b * d.P + pix;
             const bool vec_ok = !p.out_nchw && ((d.Cout | o_base) & 3) == 0;
+            { const long long t1 = clock64(); e_work += t1 - et0; et0 = t1; }
             umma::mbar_wait_sleep(&bar_acc_full[a], (ti >> 1) & 1);
             umma::tc_fence_after();
+            { const long long t1 = clock64(); e_wait += t1 - et0; et0 = t1; }
 #pragma unroll 1
             for (int n0 = 0; n0 < BN; n0 += 16) {
                 const bool live = p_ok && n0 < n_valid;
@@ -203,6 +212,8 @@ halo_conv_kernel(const __grid_constant__ HaloParams hp, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(&bar_acc_empty[a]);
         }
+        if (hp.prof && blockIdx.x == 0 && tid == 0)
+            printf("halo epilogue warp 0: wait acc_full %lld, work %lld cycles\n", e_wait, e_work + (clock64() - et0));
     } else if (warp < kHTmaWarp) {
         // ================================ converters: lo = x - trunc_tf32(x) over the halo ========
         const int ct = tid - kHConvWarp0 * 32;            // 0..127
@@ -254,7 +265,8 @@ halo_conv_kernel(const __grid_constant__ HaloParams hp, const __grid_constant__ 
                 const uint8_t *src = reinterpret_cast<const uint8_t *>(p.wpack) +
                                      (size_t)(it.grp * p.n_tiles_n + it.nt) * p.KB * kBStageBytes;
                 for (int cb = 0; cb < n_cb; ++cb)
-                    for (int tap = 0; tap < T; ++tap, ++itc) {
+                    for (int tq = 0; tq < T; ++tq, ++itc) {
+                        const int tap = tq + rot < T ? tq + rot : tq + rot - T;
                         const int s = itc % SB;
                         const uint32_t ph = (itc / SB) & 1;
                         umma::mbar_wait_sleep(&bar_b_empty[s], ph ^ 1);
@@ -272,21 +284,28 @@ halo_conv_kernel(const __grid_constant__ HaloParams hp, const __grid_constant__ 
             constexpr uint32_t idesc2 = umma::make_idesc_tf32(kHM, 2 * BN);
             const uint32_t sbo = (uint32_t)hp.HWd * 128;
             uint32_t itc = 0, hs = 0, ti = 0;
+            long long c_acc = 0, c_halo = 0, c_b = 0, c_issue = 0, t0 = clock64();
+            const long long t_start = t0;
+#define HPROF(acc) do { const long long t1 = clock64(); acc += t1 - t0; t0 = t1; } while (0)
             for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
                 const int a = ti & 1;
                 umma::mbar_wait_sleep(&bar_acc_empty[a], ((ti >> 1) & 1) ^ 1);
                 umma::tc_fence_after();
+                HPROF(c_acc);
                 const uint32_t d_tmem = tmem_base + a * Cfg::kAccStride;
                 bool first = true;
                 for (int cb = 0; cb < n_cb; ++cb, ++hs) {
                     const int s = hs % S;
                     umma::mbar_wait_sleep(&bar_halo_lo[s], (hs / S) & 1);      // raw landed and lo written
                     umma::tc_fence_after();
+                    HPROF(c_halo);
                     const uint32_t slot = umma::smem_u32(smem + (size_t)s * 2 * hp.slot_bytes);
-                    for (int tap = 0; tap < T; ++tap, ++itc) {
+                    for (int tq = 0; tq < T; ++tq, ++itc) {
+                        const int tap = tq + rot < T ? tq + rot : tq + rot - T;
                         const int sb = itc % SB;
                         umma::mbar_wait_sleep(&bar_b_full[sb], (itc / SB) & 1);
                         umma::tc_fence_after();
+                        HPROF(c_b);
                         const int ki = tap / d.kw, kj = tap - ki * d.kw;
                         const uint32_t win = slot + (uint32_t)(ki * d.dil * hp.HWd + kj * d.dil) * 128;
                         const uint64_t a_hi = umma::make_desc_sw128_sbo(win, sbo);
@@ -301,11 +320,15 @@ halo_conv_kernel(const __grid_constant__ HaloParams hp, const __grid_constant__ 
                         }
                         first = false;
                         umma::tc_commit(&bar_b_empty[sb]);
+                        HPROF(c_issue);
                     }
                     umma::tc_commit(&bar_halo_empty[s]);
                 }
                 umma::tc_commit(&bar_acc_full[a]);
             }
+            if (hp.prof && blockIdx.x == 0)
+                printf("halo MMA thread: %u tiles, total %lld cycles; wait acc %lld, wait halo %lld, wait B %lld, issue %lld\n",
+                       ti, clock64() - t_start, c_acc, c_halo, c_b, c_issue);
         }
     }
     if (!triggered) pdl_trigger();
@@ -319,8 +342,8 @@ halo_conv_kernel(const __grid_constant__ HaloParams hp, const __grid_constant__ 
 
 // --------------------------------------------------------------------------------------------- host side
 static bool halo_enabled() {
-    static const bool on = [] { const char *e = getenv("AANET_HALO"); return e && e[0] == '1'; }();   // opt-in until validated
-    return on;
+    const char *e = getenv("AANET_HALO");       // read per call: tests and A/B runs flip it at run time
+    return e && e[0] == '1';                   // opt-in until validated
 }
 
 // Fills the halo geometry; false when the problem is outside what the kernel covers.
@@ -336,11 +359,21 @@ static bool halo_plan(const ConvParams &src, int BN, HaloParams &hp) {
     hp.slot_bytes = (hp.lines * 128 + 1023) & ~1023;
     hp.n_cb = d.Cg / 32;
     const int bstage = 2 * BN * 32 * 4;
-    hp.n_bst = 3;
-    int slots = (kHSmemBudget - hp.n_bst * bstage) / (2 * hp.slot_bytes);
-    if (slots < 2) { hp.n_bst = 2; slots = (kHSmemBudget - hp.n_bst * bstage) / (2 * hp.slot_bytes); }
-    if (slots < 2) return false;
-    hp.n_slots = slots > kHMaxSlots ? kHMaxSlots : slots;
+    // shared-memory plan: halo slots first (2 hide a halo load behind the other slot's taps; 3 when one slot is a
+    // whole tile), the rest of the budget goes to the weight ring, whose depth hides the L2 latency of the
+    // per-K-block weight blocks
+    const char *es = getenv("AANET_HALO_SLOTS"), *eb = getenv("AANET_HALO_BST");
+    int slots = es ? atoi(es) : (hp.n_cb == 1 ? 3 : 2);
+    if (slots < 2) slots = 2;
+    if (slots > kHMaxSlots) slots = kHMaxSlots;
+    while (slots > 2 && kHSmemBudget - slots * 2 * hp.slot_bytes < 2 * bstage) --slots;
+    int bst = (kHSmemBudget - slots * 2 * hp.slot_bytes) / bstage;
+    if (bst < 2) return false;
+    if (eb && atoi(eb) >= 2 && atoi(eb) < bst) bst = atoi(eb);
+    hp.n_bst = bst > kHMaxBStages ? kHMaxBStages : bst;
+    hp.n_slots = slots;
+    { const char *ep = getenv("AANET_HALO_PROF"); hp.prof = ep && ep[0] == '1'; }
+    { const char *er = getenv("AANET_HALO_ROT"); hp.rot = !(er && er[0] == '0'); }
     ConvParams &p = hp.p;
     p.n_tiles_n = ceil_div(d.Og, BN);
     p.K = d.K * d.Cg;

@@ -55,6 +55,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
+    // fast path: one plain try_wait, no timer read (SR_GLOBALTIMER costs ~100 cycles and the MMA issuer passes
+    // through three waits per K block, most of them already satisfied)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
     const unsigned long long t0 = globaltimer_ns();
     for (uint32_t spin = 0; !done; ++spin) {
         asm volatile(

@@ -1,0 +1,89 @@
+"""Halo engine (aanet_b200/csrc/halo_engine.cu): stride-1 dense convolutions whose tcgen05 A operand is a window
+into a TMA-loaded, swizzled input halo -- against float64 torch convolutions, and against the gather engine."""
+import os
+
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def halo():
+    old = os.environ.get("AANET_HALO")
+    os.environ["AANET_HALO"] = "1"
+    yield
+    if old is None:
+        del os.environ["AANET_HALO"]
+    else:
+        os.environ["AANET_HALO"] = old
+
+
+def npy(t):
+    return t.detach().float().cpu().numpy()
+
+
+@pytest.mark.parametrize("cfg", [
+    # B, Cin, Cout, H, W, k, pad, dil, groups
+    (1, 64, 64, 128, 416, 3, 1, 1, 1),     # SimpleBottleneck conv2 at the 1/3 scale (config 2)
+    (1, 64, 64, 128, 416, 1, 0, 1, 1),     # conv1 / conv3
+    (1, 64, 54, 128, 416, 3, 2, 2, 2),     # offset head: grouped, dilated, 27 outputs per group
+    (2, 32, 32, 33, 47, 3, 1, 1, 1),       # one channel block, ragged tiles, batch 2
+    (1, 96, 96, 21, 30, 3, 2, 2, 1),       # three channel blocks, two N tiles (config 5 widths)
+    (1, 128, 128, 17, 9, 3, 1, 1, 1),      # four channel blocks, two N tiles
+    (1, 32, 16, 5, 7, 1, 0, 1, 1),         # image smaller than one tile
+    (1, 64, 64, 20, 24, 3, 3, 1, 1),       # pad > (k-1)/2: output larger than the input
+    (1, 64, 64, 20, 24, 3, 0, 1, 1),       # pad 0: output smaller than the input
+])
+def test_halo_conv_matches_float64(halo, cfg):
+    import aanet_b200.ops as ops
+    B, Ci, Co, H, W, k, pad, dil, grp = cfg
+    torch.manual_seed(17)
+    x = torch.randn(B, Ci, H, W, device="cuda")
+    w = torch.randn(Co, Ci // grp, k, k, device="cuda") / (Ci * k * k / grp) ** 0.5
+    bias = torch.randn(Co, device="cuda")
+    scale, shift = torch.rand(Co, device="cuda") + 0.5, torch.randn(Co, device="cuda")
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), bias.double(), 1, pad, dil, grp)
+    res = torch.randn_like(ref).float()
+    xt, wp = ops.nchw_to_nhwc(x), ops.pack_conv_weight(w, grp)
+    # residual + LeakyReLU, channels-last output (LEAN when Cout/groups % 16 == 0)
+    out = ops.conv2d_nhwc(xt, wp, Co, k, k, bias, scale, shift, ops.nchw_to_nhwc(res), ops.ACT_LEAKY, 0.2, 1, pad, dil, grp)
+    ref2 = torch.nn.functional.leaky_relu(ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) + res, 0.2)
+    assert rel_err(npy(out.permute(0, 3, 1, 2)), npy(ref2)) < 1e-5
+    # NCHW output, ReLU, no affine
+    out_nchw = ops.conv2d_nhwc(xt, wp, Co, k, k, bias, None, None, None, ops.ACT_RELU, 0.0, 1, pad, dil, grp, out_nchw=True)
+    assert rel_err(npy(out_nchw), npy(torch.relu(ref))) < 1e-5
+    # offset/mask head epilogue
+    n_off = (Co * 2) // 3
+    om = ops.conv2d_nhwc(xt, wp, Co, k, k, bias, None, None, None, ops.ACT_OFFSET_MASK, 0.0, 1, pad, dil, grp,
+                         out_nchw=True, n_offset_ch=n_off, mask_scale=2.0)
+    want = ref.clone()
+    want[:, n_off:] = 2 * torch.sigmoid(ref[:, n_off:])
+    assert rel_err(npy(om), npy(want)) < 1e-5
+    # and the gather engine gives the same numbers up to the summation order of the K blocks
+    os.environ["AANET_HALO"] = "0"
+    old = ops.conv2d_nhwc(xt, wp, Co, k, k, bias, scale, shift, ops.nchw_to_nhwc(res), ops.ACT_LEAKY, 0.2, 1, pad, dil, grp)
+    os.environ["AANET_HALO"] = "1"
+    assert rel_err(npy(out), npy(old)) < 1e-5
+
+
+def test_halo_fused_executor_matches_gather_engine(halo):
+    """The whole aggregation on the halo kernels where they apply vs the gather engine only."""
+    import aanet_b200.nets as n
+    torch.manual_seed(326)
+    D0, H, W, B = 64, 48, 104, 2
+    agg = n.AdaptiveAggregation(D0, num_deform_blocks=3, intermediate_supervision=False).cuda().eval()
+    for name, m in agg.named_modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.8, 1.2)
+        if name.endswith("offset_conv"):
+            torch.nn.init.normal_(m.weight, std=0.05); torch.nn.init.normal_(m.bias, std=0.5)
+    costs = [torch.randn(B, D0 >> s, H >> s, W >> s, device="cuda") for s in range(3)]
+    with torch.no_grad():
+        new = agg([c.clone() for c in costs])[0]
+        os.environ["AANET_HALO"] = "0"
+        old = agg([c.clone() for c in costs])[0]
+        os.environ["AANET_HALO"] = "1"
+    assert rel_err(npy(new), npy(old)) < 1e-5
