@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libaanet_b200.so")
-SOURCES = ["capi.cu", "softargmin.cu", "correlation.cu", "correlation_umma.cu", "cost5d.cu", "csa_fuse.cu", "refine.cu", "mdcn_fwd.cu", "mdcn_bwd.cu", "mdcn_bwd_umma.cu",
+SOURCES = ["capi.cu", "softargmin.cu", "correlation.cu", "correlation_umma.cu", "correlation_tma.cu", "cost5d.cu", "csa_fuse.cu", "refine.cu", "mdcn_fwd.cu", "mdcn_bwd.cu", "mdcn_bwd_umma.cu",
            "mdcn_api.cu", "conv_umma.cu", "halo_engine.cu", "deform_halo.cu", "deform_tmem.cu", "conv_umma_m0.cu", "conv_umma_m1.cu", "conv_umma_m2.cu", "conv_umma_m3.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]

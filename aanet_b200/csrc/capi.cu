@@ -26,7 +26,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int make_tensor_map_f32(CUtensorMap *tm, const void *base, int rank, const uint64_t *dims,
-                        const uint64_t *strides_bytes, const uint32_t *box, bool swizzle128) {
+                        const uint64_t *strides_bytes, const uint32_t *box, int swizzle) {
     static EncodeTiledFn encode = nullptr;      // benign race: every thread resolves the same entry point
     if (!encode) {
         void *fn = nullptr;
@@ -43,7 +43,7 @@ int make_tensor_map_f32(CUtensorMap *tm, const void *base, int rank, const uint6
     for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
     const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), d, s, b,
                               e, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                              swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_last_cuda_error("cuTensorMapEncodeTiled failed");

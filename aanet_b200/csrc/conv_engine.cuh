@@ -52,6 +52,7 @@ int conv_halo_launch(const ConvParams &p, int BN, cudaStream_t stream);
 int deform_halo_launch(const ConvParams &p, int BN, cudaStream_t stream);
 // deform_tmem.cu: the same with the sampled operand written straight into tensor memory (tcgen05.st, TMEM-A MMA)
 int deform_tmem_launch(const ConvParams &p, int BN, cudaStream_t stream);
+int dense_tmem_launch(const ConvParams &p, int BN, cudaStream_t stream);
 
 bool conv_umma_supported(const MdcnDims &d, bool deform);
 int conv_umma_pick_bn(int Og);

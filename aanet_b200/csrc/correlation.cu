@@ -355,6 +355,9 @@ namespace aanet {
 bool corr_umma_supported(int B, int C, int H, int W, int D);
 int corr_umma_launch(const float *L, const float *R, float *cost, int B, int C, int H, int W, int D, bool nhwc,
                      cudaStream_t stream);
+// correlation_tma.cu (AANET_ERR_UNSUPPORTED = take correlation_umma.cu)
+int corr_tma_launch(const float *L, const float *R, float *cost, int B, int C, int H, int W, int D, bool nhwc,
+                    cudaStream_t stream);
 }  // namespace aanet
 
 using namespace aanet;
@@ -364,8 +367,13 @@ extern "C" int aanet_corr_fwd(const float *L, const float *R, float *cost, int B
     if (!L || !R || !cost) return AANET_ERR_NULL;
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || D <= 0) return AANET_ERR_SHAPE;
     if (H > 65535 || B > 65535) return AANET_ERR_UNSUPPORTED;
-    // tensor-core path (D <= 128); the FFMA kernels below remain for wider searches
-    if (corr_umma_supported(B, C, H, W, D)) return corr_umma_launch(L, R, cost, B, C, H, W, D, false, as_stream(stream));
+    // tensor-core paths (D <= 128): TMA-staged tiles where the shape allows, else the register-staged kernel; the
+    // FFMA kernels below remain for wider searches
+    if (corr_umma_supported(B, C, H, W, D)) {
+        const int rc = corr_tma_launch(L, R, cost, B, C, H, W, D, false, as_stream(stream));
+        if (rc != AANET_ERR_UNSUPPORTED) return rc;
+        return corr_umma_launch(L, R, cost, B, C, H, W, D, false, as_stream(stream));
+    }
     const int n_wtiles = ceil_div(W, kTW), n_dtiles = ceil_div(D, kTD);
     const dim3 grid(n_wtiles * n_dtiles, H, B);
     if (W % 4 == 0 && aligned16(L) && aligned16(R) && aligned16(cost))
@@ -380,6 +388,10 @@ extern "C" int aanet_corr_fwd_nhwc(const float *L, const float *R, float *cost, 
     if (!L || !R || !cost) return AANET_ERR_NULL;
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || D <= 0) return AANET_ERR_SHAPE;
     if (!corr_umma_supported(B, C, H, W, D)) return AANET_ERR_UNSUPPORTED;
+    if (D % 4 == 0) {
+        const int rc = corr_tma_launch(L, R, cost, B, C, H, W, D, true, as_stream(stream));
+        if (rc != AANET_ERR_UNSUPPORTED) return rc;
+    }
     return corr_umma_launch(L, R, cost, B, C, H, W, D, true, as_stream(stream));
 }
 

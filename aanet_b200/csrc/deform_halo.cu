@@ -509,7 +509,7 @@ int deform_halo_launch(const ConvParams &src, int BN, cudaStream_t stream) {
     const uint64_t dims[4] = {(uint64_t)d.Cin, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.B};
     const uint64_t strides[3] = {(uint64_t)d.Cin * 4, (uint64_t)d.W * d.Cin * 4, (uint64_t)d.HW * d.Cin * 4};
     const uint32_t box[4] = {32, (uint32_t)hp.HWd, (uint32_t)hp.HH, 1};
-    const int rc = make_tensor_map_f32(&tm, src.x, 4, dims, strides, box, false);
+    const int rc = make_tensor_map_f32(&tm, src.x, 4, dims, strides, box, 0);
     if (rc) return rc;
     return BN == 64 ? deform_halo_launch_bn<64>(hp, tm, stream) : deform_halo_launch_bn<32>(hp, tm, stream);
 }

@@ -36,11 +36,17 @@
 namespace aanet {
 
 constexpr int kTM = 128, kTTW = 16, kTTH = 8;          // 16 x 8 output pixels per tile
-constexpr int kTGroups = 3, kTProdWarp0 = 4, kTProdWarps = 4 * kTGroups;
-constexpr int kTTmaWarp = kTProdWarp0 + kTProdWarps, kTLoadWarp = kTTmaWarp + 1, kTMmaWarp = kTTmaWarp + 2;
-constexpr int kTThreads = 640;
-constexpr int kTStages = kTGroups;
+constexpr int kTProdWarp0 = 4;
 constexpr int kTAccCol = 0, kTACol = 256, kTAStageCols = 64;      // TMEM column map
+// G producer groups of 4 warps, one A stage (64 TMEM columns) and one weight stage each.  The per-K-block chain
+// "stage free -> gather -> tcgen05.st -> wait::st -> arrive -> MMA -> commit" is latency-bound, so the number of
+// stages in rotation sets the K-block rate: G = 3 (640 threads, 96 registers) or G = 4 (768 threads, 80 registers).
+template <int G> struct TCfg {
+    static constexpr int kProdWarps = 4 * G;
+    static constexpr int kTmaWarp = kTProdWarp0 + kProdWarps, kLoadWarp = kTmaWarp + 1, kMmaWarp = kTmaWarp + 2;
+    static constexpr int kThreads = ((kMmaWarp + 1 + 3) / 4) * 4 * 32;
+    static_assert(kTACol + G * kTAStageCols <= 512, "TMEM: two accumulators + G operand stages");
+};
 constexpr int kTSmemBudget = 214 * 1024;
 
 struct DeformTmemParams {
@@ -84,10 +90,15 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     return v;
 }
 
-template <int BN>
-__global__ void __launch_bounds__(kTThreads, 1)
+// DENSE = false: DCNv2 (bilinear gather, offsets + mask).  DENSE = true: an ordinary stride-1 convolution through the
+// same pipeline -- the "sample" of tap (ki, kj) is the input pixel itself, one line per K block and thread (the
+// offset/mask head of nets/deform.py:70-72 and the 3x3 of SimpleBottleneck, nets/deform.py:164-184).
+// LEAN = true: channels-last output in whole 16-channel chunks, no offset/mask head epilogue (see conv_umma_kernel.cuh).
+template <int BN, bool DENSE, bool LEAN, int G>
+__global__ void __launch_bounds__(TCfg<G>::kThreads, 1)
 deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_constant__ CUtensorMap tm) {
-    constexpr int S = kTStages;
+    constexpr int S = G, kTGroups = G, kTProdWarps = TCfg<G>::kProdWarps, kTTmaWarp = TCfg<G>::kTmaWarp,
+                  kTLoadWarp = TCfg<G>::kLoadWarp, kTMmaWarp = TCfg<G>::kMmaWarp;
     constexpr int kBTile = 2 * BN * 32 * 4;                   // [B_hi | B_lo] of one K block
     static_assert(2 * BN <= 128, "accumulator stride is 128 columns");
     extern __shared__ uint8_t smem_raw[];
@@ -158,7 +169,9 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
-            float *dst_px = p.out + ((long)it.b * d.P + (long)e_oh * d.Wo + e_ow) * d.Cout + o_base;
+            const int pix = e_oh * d.Wo + e_ow;
+            const long pix_g = (long)it.b * d.P + pix;
+            const bool vec_ok = !p.out_nchw && ((d.Cout | o_base) & 3) == 0;
             umma::mbar_wait_sleep(&bar_acc_full[a], (ti >> 1) & 1);
             umma::tc_fence_after();
 #pragma unroll 1
@@ -167,6 +180,7 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                 umma::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + kTAccCol + a * 128 + n0, acc);
                 umma::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + kTAccCol + a * 128 + BN + n0, acc2);
                 if (!p_ok || n0 >= n_valid) continue;
+                const bool full = LEAN || (vec_ok && n0 + 16 <= n_valid);
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) {
                     const float4 sc = *reinterpret_cast<const float4 *>(&s_aff[0][n0 + i]);
@@ -180,10 +194,25 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                 } else if (p.act == ACT_LEAKY) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) acc[i] = acc[i] > 0.f ? acc[i] : acc[i] * p.slope;
-                }
-                float4 *dst = reinterpret_cast<float4 *>(dst_px + n0);
+                } else if (!LEAN && p.act == ACT_OFFSET_MASK) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+                    for (int i = 0; i < 16; ++i)
+                        if (o_base + n0 + i >= p.n_offset_ch) acc[i] = __fdividef(p.mask_scale, 1.f + __expf(-acc[i]));
+                }
+                if (full) {
+                    float4 *dst = reinterpret_cast<float4 *>(p.out + pix_g * d.Cout + o_base + n0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+                } else if (!LEAN && p.out_nchw) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (n0 + i < n_valid) p.out[((long)it.b * d.Cout + o_base + n0 + i) * d.P + pix] = acc[i];
+                } else if (!LEAN) {
+                    float *dst = p.out + pix_g * d.Cout + o_base + n0;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (n0 + i < n_valid) dst[i] = acc[i];
+                }
             }
             umma::tc_fence_before();
             __syncwarp();
@@ -214,10 +243,10 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
             c.oh = min(c.oh, d.Ho - 1); c.ow = min(c.ow, d.Wo - 1);
             c.hy0 = item.ty * kTTH - d.pad - hp.margin_y; c.hx0 = item.tx * kTTW - d.pad - hp.margin_x;
             const long pc = (long)c.oh * d.Wo + c.ow;
-            c.off = p.offset + (long)item.b * p.off_bs + pc * p.off_ps;
-            c.msk = p.mask ? p.mask + (long)item.b * p.mask_bs + pc * p.mask_ps : nullptr;
+            c.off = DENSE ? nullptr : p.offset + (long)item.b * p.off_bs + pc * p.off_ps;
+            c.msk = (!DENSE && p.mask) ? p.mask + (long)item.b * p.mask_bs + pc * p.mask_ps : nullptr;
         };
-        auto decode_cb = [&](St &c) { c.ch0 = (long)((c.grp * d.Cg + c.cb * 32) / d.Cd) * d.K; };
+        auto decode_cb = [&](St &c) { c.ch0 = DENSE ? 0 : (long)((c.grp * d.Cg + c.cb * 32) / d.Cd) * d.K; };
         auto advance = [&](St &c, int n) {
             c.it += n; c.tap += n;
             if (c.tap < T) return;
@@ -232,6 +261,7 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
             }
         };
         auto load_geom = [&](const St &c, float &gh, float &gw, float &gm) {
+            if (DENSE) return;
             const long ch = c.ch0 + c.tap;
             gh = __ldg(c.off + (ch * 2) * p.off_cs);
             gw = __ldg(c.off + (ch * 2 + 1) * p.off_cs);
@@ -258,6 +288,41 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
             const uint32_t ph = (cur.it / S) & 1;
             const int hslot = cur.hs & 1;
             const uint32_t halo = umma::smem_u32(halo0 + (size_t)hslot * hp.slot_bytes);
+            if (DENSE) {
+                // the tap's input pixel of my output pixel: always inside the staged patch (margin 0); out-of-image
+                // pixels were zero-filled by the TMA unit (= the convolution's zero padding)
+                if (ready_hs != cur.hs) {
+                    umma::mbar_wait(&bar_halo_full[hslot], (cur.hs >> 1) & 1);
+                    ready_hs = cur.hs;
+                }
+                umma::mbar_wait(&bar_empty[s], ph ^ 1);
+                umma::tc_fence_after();
+                const uint32_t a_col = tmem_base + ((uint32_t)(q * 32) << 16) + kTACol + s * kTAStageCols;
+                const int l0 = (cur.oh + tapo.x - cur.hy0) * hp.HWd + (cur.ow + tapo.y - cur.hx0);
+                const uint32_t P0 = (halo + (uint32_t)l0 * 128) | ((uint32_t)(l0 & 7) << 4);
+                float4 qd[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) qd[c] = lds128(P0 ^ (uint32_t)(c << 4));
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    float hi[8], lo[8];
+                    umma::split_tf32(qd[2 * c8].x, hi[0], lo[0]); umma::split_tf32(qd[2 * c8].y, hi[1], lo[1]);
+                    umma::split_tf32(qd[2 * c8].z, hi[2], lo[2]); umma::split_tf32(qd[2 * c8].w, hi[3], lo[3]);
+                    umma::split_tf32(qd[2 * c8 + 1].x, hi[4], lo[4]); umma::split_tf32(qd[2 * c8 + 1].y, hi[5], lo[5]);
+                    umma::split_tf32(qd[2 * c8 + 1].z, hi[6], lo[6]); umma::split_tf32(qd[2 * c8 + 1].w, hi[7], lo[7]);
+                    tmem_st8(a_col + c8 * 8, hi);
+                    tmem_st8(a_col + 32 + c8 * 8, lo);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                umma::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    umma::mbar_arrive(&bar_full_a[s]);
+                    if (nxt.hs != cur.hs) umma::mbar_arrive(&bar_halo_empty[hslot]);
+                }
+                cur = nxt; tapo = ntapo;
+                continue;
+            }
             // ---- my bilinear sample for this (tap, deformable group)
             const float py = (float)(cur.oh + tapo.x) + gh;
             const float px = (float)(cur.ow + tapo.y) + gw;
@@ -459,38 +524,42 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
 }
 
 // --------------------------------------------------------------------------------------------- host side
-template <int BN>
-static int deform_tmem_launch_bn(const DeformTmemParams &hp, const CUtensorMap &tm, cudaStream_t stream) {
-    const size_t smem = (size_t)kTStages * 2 * BN * 32 * 4 + 2 * (size_t)hp.slot_bytes + 1024;
-    cudaFuncSetAttribute(deform_tmem_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int BN, bool DENSE, bool LEAN, int G>
+static int tmem_launch_g(const DeformTmemParams &hp, const CUtensorMap &tm, cudaStream_t stream) {
+    const size_t smem = (size_t)G * 2 * BN * 32 * 4 + 2 * (size_t)hp.slot_bytes + 1024;
+    cudaFuncSetAttribute(deform_tmem_kernel<BN, DENSE, LEAN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int rounds = ceil_div(hp.p.total_tiles, num_sms());
     const int grid = ceil_div(hp.p.total_tiles, rounds);
-    return launch_pdl(deform_tmem_kernel<BN>, dim3(grid), dim3(kTThreads), smem, stream, hp, tm);
+    return launch_pdl(deform_tmem_kernel<BN, DENSE, LEAN, G>, dim3(grid), dim3(TCfg<G>::kThreads), smem, stream, hp, tm);
 }
 
-// Returns AANET_ERR_UNSUPPORTED when the problem should take another kernel.
-int deform_tmem_launch(const ConvParams &src, int BN, cudaStream_t stream) {
-    { const char *e = getenv("AANET_DEFORM_TMEM"); if (e && e[0] == '0') return AANET_ERR_UNSUPPORTED; }   // A/B switch
+static int tmem_groups(bool dense) {
+    const char *e = getenv(dense ? "AANET_DENSE_GROUPS" : "AANET_DEFORM_GROUPS");
+    const int g = e ? atoi(e) : 3;      // measured: 4 groups buy nothing (dense) or cost spills (deformable)
+    return g == 4 ? 4 : 3;
+}
+
+template <int BN, bool DENSE, bool LEAN>
+static int tmem_launch_inst(const DeformTmemParams &hp, const CUtensorMap &tm, int groups, cudaStream_t stream) {
+    return groups == 4 ? tmem_launch_g<BN, DENSE, LEAN, 4>(hp, tm, stream) : tmem_launch_g<BN, DENSE, LEAN, 3>(hp, tm, stream);
+}
+
+// Shared plan of the two modes; margin = pixels of learned offset the staged patch covers (0 for DENSE).
+static int tmem_plan(const ConvParams &src, int BN, int margin_req, int groups, DeformTmemParams &hp, CUtensorMap &tm) {
     const MdcnDims &d = src.d;
-    if (d.stride != 1 || d.Cg % 32 || d.Cd % 32 || !aligned16(src.x)) return AANET_ERR_UNSUPPORTED;
-    if (src.out_nchw || src.residual || d.Og % 16 || (d.Cout & 3) || src.act == ACT_OFFSET_MASK) return AANET_ERR_UNSUPPORTED;
-    if (BN != 32 && BN != 64) return AANET_ERR_UNSUPPORTED;
-    if (d.K < kTGroups) return AANET_ERR_UNSUPPORTED;       // every producer group must own a tap in every halo slot
-    DeformTmemParams hp;
     hp.p = src;
-    const size_t ring = (size_t)kTStages * 2 * BN * 32 * 4;
+    const size_t ring = (size_t)groups * 2 * BN * 32 * 4;
     // Halo plan.  The pitch (pixels per halo row) is rounded up to a multiple of 8 lines: a sample whose row index
     // jitters by one (sub-pixel offsets of either sign) then keeps its swizzle key (line & 7), so neighbouring
     // threads keep hitting different bank groups; the extra columns widen the horizontal margin.  Vertical margin:
-    // the largest (<= AANET_DEFORM_MARGIN, default 4) for which two slots fit next to the weight ring.
-    const char *em = getenv("AANET_DEFORM_MARGIN");
-    int margin = em ? atoi(em) : 4;
+    // the largest (<= the request) for which two slots fit next to the weight ring.
     const char *ep8 = getenv("AANET_DEFORM_PITCH8");
     const bool pitch8 = !(ep8 && ep8[0] == '0');
-    int mx = 0;
+    const int corner = margin_req > 0 || src.offset ? 1 : 0;      // +1 line / column for the bilinear corner
+    int margin = margin_req, mx = 0;
     for (; margin >= 0; --margin) {
-        hp.HH = kTTH + (d.kh - 1) * d.dil + 2 * margin + 1;
-        const int wmin = kTTW + (d.kw - 1) * d.dil + 2 * margin + 1;
+        hp.HH = kTTH + (d.kh - 1) * d.dil + 2 * margin + corner;
+        const int wmin = kTTW + (d.kw - 1) * d.dil + 2 * margin + corner;
         hp.HWd = pitch8 ? (wmin + 7) / 8 * 8 : wmin;
         mx = margin + (hp.HWd - wmin) / 2;
         hp.lines = hp.HH * hp.HWd;
@@ -499,7 +568,7 @@ int deform_tmem_launch(const ConvParams &src, int BN, cudaStream_t stream) {
     }
     if (margin < 0) return AANET_ERR_UNSUPPORTED;
     hp.margin_y = margin;
-    hp.margin_x = mx;
+    hp.margin_x = src.offset ? mx : 0;
     hp.n_cb = d.Cg / 32;
     { const char *ep = getenv("AANET_HALO_PROF"); hp.prof = ep && ep[0] == '1'; }
     ConvParams &p = hp.p;
@@ -512,13 +581,50 @@ int deform_tmem_launch(const ConvParams &src, int BN, cudaStream_t stream) {
     const long total = (long)d.groups * p.n_tiles_n * p.n_ptiles;
     if (total > 0x3fffffffL) return AANET_ERR_UNSUPPORTED;
     p.total_tiles = (int)total;
-    CUtensorMap tm;
     const uint64_t dims[4] = {(uint64_t)d.Cin, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.B};
     const uint64_t strides[3] = {(uint64_t)d.Cin * 4, (uint64_t)d.W * d.Cin * 4, (uint64_t)d.HW * d.Cin * 4};
     const uint32_t box[4] = {32, (uint32_t)hp.HWd, (uint32_t)hp.HH, 1};
-    const int rc = make_tensor_map_f32(&tm, src.x, 4, dims, strides, box, true);
+    return make_tensor_map_f32(&tm, src.x, 4, dims, strides, box, 1);
+}
+
+// DCNv2.  Returns AANET_ERR_UNSUPPORTED when the problem should take another kernel.
+int deform_tmem_launch(const ConvParams &src, int BN, cudaStream_t stream) {
+    { const char *e = getenv("AANET_DEFORM_TMEM"); if (e && e[0] == '0') return AANET_ERR_UNSUPPORTED; }   // A/B switch
+    const MdcnDims &d = src.d;
+    if (d.stride != 1 || d.Cg % 32 || d.Cd % 32 || !aligned16(src.x)) return AANET_ERR_UNSUPPORTED;
+    if (src.out_nchw || src.residual || d.Og % 16 || (d.Cout & 3) || src.act == ACT_OFFSET_MASK) return AANET_ERR_UNSUPPORTED;
+    if (BN != 32 && BN != 64) return AANET_ERR_UNSUPPORTED;
+    const int groups = tmem_groups(false);
+    if (d.K < groups) return AANET_ERR_UNSUPPORTED;         // every producer group must own a tap in every halo slot
+    const char *em = getenv("AANET_DEFORM_MARGIN");
+    DeformTmemParams hp;
+    CUtensorMap tm;
+    const int rc = tmem_plan(src, BN, em ? atoi(em) : 4, groups, hp, tm);
     if (rc) return rc;
-    return BN == 64 ? deform_tmem_launch_bn<64>(hp, tm, stream) : deform_tmem_launch_bn<32>(hp, tm, stream);
+    return BN == 64 ? tmem_launch_inst<64, false, true>(hp, tm, groups, stream)
+                    : tmem_launch_inst<32, false, true>(hp, tm, groups, stream);
+}
+
+// Stride-1 dense convolution with at least as many taps as producer groups and 32-channel blocks (3x3 layers of the ISA blocks and
+// the offset/mask head).  Returns AANET_ERR_UNSUPPORTED when the problem should take the round-1 engine.
+int dense_tmem_launch(const ConvParams &src, int BN, cudaStream_t stream) {
+    { const char *e = getenv("AANET_DENSE_TMEM"); if (e && e[0] == '0') return AANET_ERR_UNSUPPORTED; }   // A/B switch
+    const MdcnDims &d = src.d;
+    if (d.stride != 1 || d.Cg % 32 || !aligned16(src.x) || src.residual || src.offset) return AANET_ERR_UNSUPPORTED;
+    if (BN != 32 && BN != 48 && BN != 64) return AANET_ERR_UNSUPPORTED;
+    const int groups = tmem_groups(true);
+    if (d.K < groups) return AANET_ERR_UNSUPPORTED;
+    DeformTmemParams hp;
+    CUtensorMap tm;
+    const int rc = tmem_plan(src, BN, 0, groups, hp, tm);
+    if (rc) return rc;
+    const bool lean = !src.out_nchw && src.act != ACT_OFFSET_MASK && d.Og % 16 == 0 && (d.Cout & 3) == 0;
+    switch (BN) {
+        case 32: return lean ? tmem_launch_inst<32, true, true>(hp, tm, groups, stream) : tmem_launch_inst<32, true, false>(hp, tm, groups, stream);
+        case 48: return lean ? tmem_launch_inst<48, true, true>(hp, tm, groups, stream) : tmem_launch_inst<48, true, false>(hp, tm, groups, stream);
+        case 64: return lean ? tmem_launch_inst<64, true, true>(hp, tm, groups, stream) : tmem_launch_inst<64, true, false>(hp, tm, groups, stream);
+    }
+    return AANET_ERR_UNSUPPORTED;
 }
 
 }  // namespace aanet

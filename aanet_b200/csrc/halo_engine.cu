@@ -415,7 +415,7 @@ int conv_halo_launch(const ConvParams &src, int BN, cudaStream_t stream) {
     const uint64_t dims[4] = {(uint64_t)d.Cin, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.B};
     const uint64_t strides[3] = {(uint64_t)d.Cin * 4, (uint64_t)d.W * d.Cin * 4, (uint64_t)d.HW * d.Cin * 4};
     const uint32_t box[4] = {32, (uint32_t)hp.HWd, (uint32_t)hp.HH, 1};
-    const int rc = make_tensor_map_f32(&tm, src.x, 4, dims, strides, box, true);
+    const int rc = make_tensor_map_f32(&tm, src.x, 4, dims, strides, box, 1);
     if (rc) return rc;
     switch (BN) {
         case 16: return halo_launch_bn<16>(hp, tm, stream);

@@ -12,8 +12,10 @@ namespace aanet {
 // innermost stride is the element size).  swizzle128: box rows of 128 bytes are stored with the 128-byte swizzle
 // (16-byte chunk index XOR (line & 7)), the layout tcgen05 descriptors of type SWIZZLE_128B read.  Out-of-bounds
 // elements are filled with zeros.  Returns an aanet_status.
+// swizzle: 0 = none, 1 = SWIZZLE_128B, 2 = SWIZZLE_128B_ATOM_32B (the only layout tcgen05 accepts for MN-major
+// tf32 operands: UMMA layout type SWIZZLE_128B_BASE32B).
 int make_tensor_map_f32(CUtensorMap *tm, const void *base, int rank, const uint64_t *dims,
-                        const uint64_t *strides_bytes, const uint32_t *box, bool swizzle128);
+                        const uint64_t *strides_bytes, const uint32_t *box, int swizzle);
 
 namespace umma {
 
@@ -53,6 +55,19 @@ __device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t smem_addr, uint3
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// MN-major tf32 operand in the SWIZZLE_128B_BASE32B layout (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of
+// 128 bytes hold 32 consecutive M (or N) elements of one k; 4 such rows form the swizzle atom; lbo_bytes = distance
+// between consecutive 32-element groups along M/N, sbo_bytes = distance between consecutive 4-k atoms.
+__device__ __forceinline__ uint64_t make_desc_mn_tf32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;
     return d;
 }
 

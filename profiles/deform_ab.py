@@ -30,11 +30,13 @@ def main():
         ref = call(0)
         os.environ["AANET_DEFORM_TMEM"] = "1"
         line = "offsets %.1f px: gather engine %6.1f us | tmem" % (sigma, old)
-        for margin in (4, 2):
+        for groups, margin in ((3, 4), (4, 4), (4, 2)):
             os.environ["AANET_DEFORM_MARGIN"] = str(margin)
+            os.environ["AANET_DEFORM_GROUPS"] = str(groups)
             t = bench._timed(call, n, 24, dev) * 1e3
             err = float((call(0) - ref).abs().max())
-            line += "  margin %d: %6.1f us (max|diff| %.1e)" % (margin, t, err)
+            line += "  G%d margin<=%d: %6.1f us (max|diff| %.1e)" % (groups, margin, t, err)
+        os.environ.pop("AANET_DEFORM_GROUPS", None)
         os.environ["AANET_DEFORM_TMEM"] = "0"
         os.environ["AANET_DEFORM_HALO"] = "1"
         line += " | smem-halo"

@@ -35,6 +35,13 @@ def main():
         for flag in ("0", "1"):
             os.environ["AANET_HALO"] = flag
             res[flag] = bench._timed(call, n, 24, dev) * 1e3
+        os.environ["AANET_HALO"] = "0"
+        os.environ["AANET_DENSE_TMEM"] = "1"
+        for g in ("3", "4"):
+            os.environ["AANET_DENSE_GROUPS"] = g
+            print("   TMEM-A dense kernel, %s producer groups: %.1f us" % (g, bench._timed(call, n, 24, dev) * 1e3))
+        del os.environ["AANET_DENSE_GROUPS"]
+        os.environ["AANET_DENSE_TMEM"] = "0"
         os.environ["AANET_HALO"] = "1"
         os.environ["AANET_HALO_ROT"] = "0"
         norot = bench._timed(call, n, 24, dev) * 1e3

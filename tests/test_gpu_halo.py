@@ -10,15 +10,28 @@ from conftest import rel_err
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture
-def halo():
-    old = os.environ.get("AANET_HALO")
-    os.environ["AANET_HALO"] = "1"
-    yield
-    if old is None:
-        del os.environ["AANET_HALO"]
-    else:
-        os.environ["AANET_HALO"] = old
+FLAGS = {"window": "AANET_HALO", "tmem": "AANET_DENSE_TMEM"}
+
+
+def _select(variant):
+    for k in FLAGS.values():
+        os.environ[k] = "0"
+    if variant is not None:
+        os.environ[FLAGS[variant]] = "1"
+
+
+@pytest.fixture(params=["window", "tmem"])
+def halo(request):
+    """window: A operand = descriptor windows into the swizzled halo (halo_engine.cu); tmem: thread-per-pixel copy of
+    the halo lines into tensor memory (deform_tmem.cu, DENSE mode; layers with >= 3 taps)."""
+    old = {k: os.environ.get(k) for k in FLAGS.values()}
+    _select(request.param)
+    yield request.param
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
 
 
 def npy(t):
@@ -63,9 +76,9 @@ def test_halo_conv_matches_float64(halo, cfg):
     want[:, n_off:] = 2 * torch.sigmoid(ref[:, n_off:])
     assert rel_err(npy(om), npy(want)) < 1e-5
     # and the gather engine gives the same numbers up to the summation order of the K blocks
-    os.environ["AANET_HALO"] = "0"
+    _select(None)
     old = ops.conv2d_nhwc(xt, wp, Co, k, k, bias, scale, shift, ops.nchw_to_nhwc(res), ops.ACT_LEAKY, 0.2, 1, pad, dil, grp)
-    os.environ["AANET_HALO"] = "1"
+    _select(halo)
     assert rel_err(npy(out), npy(old)) < 1e-5
 
 
@@ -83,7 +96,7 @@ def test_halo_fused_executor_matches_gather_engine(halo):
     costs = [torch.randn(B, D0 >> s, H >> s, W >> s, device="cuda") for s in range(3)]
     with torch.no_grad():
         new = agg([c.clone() for c in costs])[0]
-        os.environ["AANET_HALO"] = "0"
+        _select(None)
         old = agg([c.clone() for c in costs])[0]
-        os.environ["AANET_HALO"] = "1"
+        _select(halo)
     assert rel_err(npy(new), npy(old)) < 1e-5
