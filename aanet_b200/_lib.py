@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # AANET_B200_LIB: load another build of the same library (A/B timing of kernel variants in one process tree)
 LIB_PATH = os.environ.get("AANET_B200_LIB") or os.path.join(_HERE, "lib", "libaanet_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _vp, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
 
@@ -38,6 +38,7 @@ SIGNATURES = {
     "aanet_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "aanet_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "aanet_conv_batch_nhwc": (_i, [_vp, _i, _i, _i, _vp]),
+    "aanet_conv_tail_supported": (_i, [_vp, _i]),
     "aanet_csa_fuse_nhwc": (_i, [_vp, _vp, _vp, _i, _vp] + [_i] * 4 + [_f, _vp]),
     "aanet_csa_fuse_fwd": (_i, [_vp, _vp, _vp, _i, _vp] + [_i] * 4 + [_f, _vp]),
     "aanet_csa_fuse_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i] + [_i] * 4 + [_f, _vp]),
@@ -52,7 +53,9 @@ class ConvDesc(ctypes.Structure):
                 ("B", _i), ("Cin", _i), ("H", _i), ("W", _i), ("Cout", _i), ("kh", _i), ("kw", _i),
                 ("stride", _i), ("pad", _i), ("dil", _i), ("groups", _i), ("dg", _i),
                 ("act", _i), ("slope", _f), ("n_offset_ch", _i), ("mask_scale", _f), ("out_nchw", _i),
-                ("om_nchw", _i)]
+                ("om_nchw", _i),
+                ("tail_wpack", _vp), ("tail_scale", _vp), ("tail_shift", _vp), ("tail_residual", _vp),
+                ("tail_cout", _i), ("tail_act", _i)]
 
 
 _lib = None

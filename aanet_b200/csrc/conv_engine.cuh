@@ -22,6 +22,10 @@ struct ConvParams {
     const float *bias, *scale, *shift;  // per output channel, optional
     const float *residual;              // same layout as out, optional
     int act; float slope; int n_offset_ch; float mask_scale;
+    // Optional fused tail (TMEM kernels only): out = act_t(conv1x1(act(main)) * tail_scale + tail_shift + tail_residual),
+    // `out` / `tail_residual` then are [B][P][tail_cout]; scale/shift/act above apply to the main convolution.
+    const float *tail_wpack, *tail_scale, *tail_shift, *tail_residual;
+    int tail_cout, tail_act;
     MdcnDims d;
     int K, KB;                          // K = kh*kw*Cg, KB = ceil(K / 32)
     int n_tiles_n;                      // ceil(Og / BN)
@@ -53,6 +57,8 @@ int deform_halo_launch(const ConvParams &p, int BN, cudaStream_t stream);
 // deform_tmem.cu: the same with the sampled operand written straight into tensor memory (tcgen05.st, TMEM-A MMA)
 int deform_tmem_launch(const ConvParams &p, int BN, cudaStream_t stream);
 int dense_tmem_launch(const ConvParams &p, int BN, cudaStream_t stream);
+// can the (main + fused 1x1 tail) problem run as one TMEM-kernel launch?
+bool tmem_tail_supported(const ConvParams &p, bool deform);
 
 bool conv_umma_supported(const MdcnDims &d, bool deform);
 int conv_umma_pick_bn(int Og);

@@ -47,7 +47,8 @@ template <int G> struct TCfg {
     static constexpr int kThreads = ((kMmaWarp + 1 + 3) / 4) * 4 * 32;
     static_assert(kTACol + G * kTAStageCols <= 512, "TMEM: two accumulators + G operand stages");
 };
-constexpr int kTSmemBudget = 214 * 1024;
+constexpr int kTSmemBudget = 222 * 1024;
+constexpr int kTAcc3Col = 448;           // TAIL: accumulator of the fused 1x1 convolution (<= 64 columns)
 
 struct DeformTmemParams {
     ConvParams p;
@@ -84,6 +85,16 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
                  : "memory");
 }
 
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -94,7 +105,12 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 // same pipeline -- the "sample" of tap (ki, kj) is the input pixel itself, one line per K block and thread (the
 // offset/mask head of nets/deform.py:70-72 and the 3x3 of SimpleBottleneck, nets/deform.py:164-184).
 // LEAN = true: channels-last output in whole 16-channel chunks, no offset/mask head epilogue (see conv_umma_kernel.cuh).
-template <int BN, bool DENSE, bool LEAN, int G>
+// TAIL = true: the bottleneck's trailing 1x1 convolution (conv3 + bn3 + identity + ReLU, nets/deform.py:177-183,
+// :229-235) is fused: the epilogue warps activate the main accumulator (bn2 + ReLU), split it into tf32 hi + lo and
+// write it back IN PLACE into the accumulator's TMEM columns, where it is the A operand of 3 x (Cm / 8) more MMAs
+// against the resident tail weights; a second epilogue pass adds bn3, the residual and the activation and stores.
+// MMA order D(0) D(1) C(0) D(2) C(1) ... so the activation pass of tile i runs under the main loop of tile i + 1.
+template <int BN, bool DENSE, bool LEAN, int G, bool TAIL = false>
 __global__ void __launch_bounds__(TCfg<G>::kThreads, 1)
 deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_constant__ CUtensorMap tm) {
     constexpr int S = G, kTGroups = G, kTProdWarps = TCfg<G>::kProdWarps, kTTmaWarp = TCfg<G>::kTmaWarp,
@@ -105,8 +121,10 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
     __shared__ __align__(8) uint64_t bar_halo_full[2], bar_halo_empty[2];
     __shared__ __align__(8) uint64_t bar_full_a[S], bar_full_b[S], bar_empty[S];
     __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2];
+    __shared__ __align__(8) uint64_t bar_y2[2], bar_acc3_full, bar_acc3_empty, bar_tailw;      // TAIL only
     __shared__ uint32_t s_tmem;
     __shared__ __align__(16) float s_aff[2][BN];
+    __shared__ __align__(16) float s_aff3[2][64];
     __shared__ int2 s_tapoff[64];                             // per tap: (ki * dil - pad, kj * dil - pad)
 
     const ConvParams &p = hp.p;
@@ -114,6 +132,7 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t *smem = smem_raw + ((1024 - (umma::smem_u32(smem_raw) & 1023)) & 1023);
     uint8_t *halo0 = smem + (size_t)S * kBTile;               // two halo slots behind the weight ring
+    uint8_t *tailw = halo0 + 2 * (size_t)hp.slot_bytes;       // TAIL: resident packed weights of the 1x1 convolution
     if (tid < d.K) s_tapoff[tid] = make_int2((tid / d.kw) * d.dil - d.pad, (tid % d.kw) * d.dil - d.pad);
     const int T = d.K, n_cb = hp.n_cb, total = p.total_tiles;
 
@@ -130,7 +149,11 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
         for (int a = 0; a < 2; ++a) {
             umma::mbar_init(&bar_acc_full[a], 1);
             umma::mbar_init(&bar_acc_empty[a], 4);
+            umma::mbar_init(&bar_y2[a], 4);
         }
+        umma::mbar_init(&bar_acc3_full, 1);
+        umma::mbar_init(&bar_acc3_empty, 4);
+        umma::mbar_init(&bar_tailw, 1);
         umma::fence_mbar_init();
     }
     if (warp == kTMmaWarp) umma::tmem_alloc<512>(&s_tmem);
@@ -141,7 +164,98 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
     pdl_wait();
     bool triggered = false;
 
-    if (warp < 4) {
+    if (warp < 4 && TAIL) {
+        // ================================ epilogue with fused 1x1 tail ==========================
+        // pass 1 (tile j): main accumulator -> bn2 + act -> tf32 hi / lo, written back in place (columns [0, BN) hi,
+        // [BN, 2 BN) lo of the accumulator = the A operand of the tail MMAs); pass 2 (tile j - 1): tail accumulator ->
+        // bn3 + residual + act -> global.  groups == 1 and one N tile: the affine tables are constant.
+        const int q = warp, row = q * 32 + lane;
+        const int Ct = p.tail_cout;
+        if (tid < BN) {
+            float sc = 1.f, sh = 0.f;
+            if (p.scale) { sc = __ldg(p.scale + tid); sh = __ldg(p.shift + tid); }
+            if (p.bias) sh = fmaf(__ldg(p.bias + tid), sc, sh);
+            s_aff[0][tid] = sc; s_aff[1][tid] = sh;
+        }
+        if (tid < 64) {
+            s_aff3[0][tid] = (tid < Ct && p.tail_scale) ? __ldg(p.tail_scale + tid) : 1.f;
+            s_aff3[1][tid] = (tid < Ct && p.tail_shift) ? __ldg(p.tail_shift + tid) : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        int n_my = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) ++n_my;
+        for (int j = 0; j <= n_my; ++j) {
+            if (j < n_my) {
+                const int a = j & 1;
+                umma::mbar_wait_sleep(&bar_acc_full[a], (j >> 1) & 1);
+                umma::tc_fence_after();
+                const uint32_t acc0 = tmem_base + ((uint32_t)(q * 32) << 16) + kTAccCol + a * 128;
+#pragma unroll 1
+                for (int n0 = 0; n0 < BN; n0 += 16) {
+                    float acc[16], acc2[16];
+                    umma::tmem_ld16(acc0 + n0, acc);
+                    umma::tmem_ld16(acc0 + BN + n0, acc2);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float v = fmaf(acc[i] + acc2[i], s_aff[0][n0 + i], s_aff[1][n0 + i]);
+                        if (p.act == ACT_RELU) v = fmaxf(v, 0.f);
+                        else if (p.act == ACT_LEAKY) v = v > 0.f ? v : v * p.slope;
+                        umma::split_tf32(v, acc[i], acc2[i]);
+                    }
+                    tmem_st16(acc0 + n0, acc);
+                    tmem_st16(acc0 + BN + n0, acc2);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                umma::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&bar_y2[a]);
+            }
+            if (j >= 1) {
+                const int jj = j - 1;
+                const int t = blockIdx.x + jj * gridDim.x;
+                if (jj == n_my - 1) { pdl_trigger(); triggered = true; }
+                const TItem it = t_item(p, t);
+                int e_oh = it.ty * kTTH + (row >> 4), e_ow = it.tx * kTTW + (row & 15);
+                const bool p_ok = e_oh < d.Ho && e_ow < d.Wo;
+                e_oh = min(e_oh, d.Ho - 1); e_ow = min(e_ow, d.Wo - 1);
+                const long pix_g = (long)it.b * d.P + (long)e_oh * d.Wo + e_ow;
+                umma::mbar_wait_sleep(&bar_acc3_full, jj & 1);
+                umma::tc_fence_after();
+#pragma unroll 1
+                for (int n0 = 0; n0 < 64; n0 += 16) {
+                    if (n0 >= Ct) break;                    // uniform
+                    float res[16];
+                    if (p.tail_residual && p_ok) {
+                        const float4 *rp = reinterpret_cast<const float4 *>(p.tail_residual + pix_g * Ct + n0);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 r4 = __ldg(rp + i);
+                            res[4 * i] = r4.x; res[4 * i + 1] = r4.y; res[4 * i + 2] = r4.z; res[4 * i + 3] = r4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) res[i] = 0.f;
+                    }
+                    float acc[16];
+                    umma::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + kTAcc3Col + n0, acc);
+                    if (!p_ok) continue;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float v = fmaf(acc[i], s_aff3[0][n0 + i], s_aff3[1][n0 + i]) + res[i];
+                        if (p.tail_act == ACT_RELU) v = fmaxf(v, 0.f);
+                        else if (p.tail_act == ACT_LEAKY) v = v > 0.f ? v : v * p.slope;
+                        acc[i] = v;
+                    }
+                    float4 *dst = reinterpret_cast<float4 *>(p.out + pix_g * Ct + n0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dst[i] = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+                }
+                umma::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&bar_acc3_empty);
+            }
+        }
+    } else if (warp < 4) {
         // ================================ epilogue (channels-last, affine + activation) ===========
         const int q = warp, row = q * 32 + lane;
         uint32_t ti = 0;
@@ -458,6 +572,11 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
     } else if (warp == kTLoadWarp) {
         if (lane == 0) {
             // ================================ weight loader ========================================
+            if (TAIL) {                                  // the 1x1 tail's packed weights stay resident
+                const uint32_t bytes = (uint32_t)(BN / 32) * 2u * (uint32_t)p.tail_cout * 128u;
+                umma::mbar_expect_tx(&bar_tailw, bytes);
+                umma::bulk_g2s(tailw, p.tail_wpack, bytes, &bar_tailw);
+            }
             uint32_t itc = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 const TItem it = t_item(p, t);
@@ -483,10 +602,37 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
             const long long t_start = t0;
 #define TPROF(acc_) do { const long long t1 = clock64(); acc_ += t1 - t0; t0 = t1; } while (0)
             const int nkb = n_cb * T;
+            // TAIL: the 1x1 convolution of tile j: A = activated tile in TMEM (hi at the accumulator's columns
+            // [0, BN), lo at [BN, 2 BN)), B = resident tail weights ([B_hi | B_lo] blocks of 32 input channels)
+            auto issue_tail = [&](uint32_t j) {
+                const int a = j & 1;
+                const int Ct = p.tail_cout;
+                const uint32_t idesc_t = umma::make_idesc_tf32(kTM, Ct);
+                if (j == 0) umma::mbar_wait_sleep(&bar_tailw, 0);
+                umma::mbar_wait_sleep(&bar_y2[a], (j >> 1) & 1);
+                umma::mbar_wait_sleep(&bar_acc3_empty, (j & 1) ^ 1);
+                umma::tc_fence_after();
+                const uint32_t a0 = tmem_base + kTAccCol + a * 128, d3 = tmem_base + kTAcc3Col;
+#pragma unroll 1
+                for (int kb = 0; kb < BN / 32; ++kb) {
+                    const uint32_t wb = umma::smem_u32(tailw) + (uint32_t)kb * 2u * (uint32_t)Ct * 128u;
+                    const uint64_t b_hi = umma::make_desc_sw128(wb), b_lo = umma::make_desc_sw128(wb + (uint32_t)Ct * 128u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t ah = a0 + kb * 32 + k * 8, al = a0 + BN + kb * 32 + k * 8;
+                        mma_tf32_ts(d3, ah, umma::desc_advance(b_hi, k * 32), idesc_t, (kb | k) != 0);
+                        mma_tf32_ts(d3, ah, umma::desc_advance(b_lo, k * 32), idesc_t, 1);
+                        mma_tf32_ts(d3, al, umma::desc_advance(b_hi, k * 32), idesc_t, 1);
+                    }
+                }
+                umma::tc_commit(&bar_acc3_full);
+            };
             for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
                 const int a = ti & 1;
-                umma::mbar_wait_sleep(&bar_acc_empty[a], ((ti >> 1) & 1) ^ 1);
-                umma::tc_fence_after();
+                if (!TAIL) {    // TAIL: tile i-2's tail MMAs (which follow its activation pass) precede this tile in the pipe
+                    umma::mbar_wait_sleep(&bar_acc_empty[a], ((ti >> 1) & 1) ^ 1);
+                    umma::tc_fence_after();
+                }
                 TPROF(c_acc);
                 const uint32_t d_tmem = tmem_base + kTAccCol + a * 128;
                 for (int kb = 0; kb < nkb; ++kb, ++itc) {
@@ -508,7 +654,9 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                     TPROF(c_issue);
                 }
                 umma::tc_commit(&bar_acc_full[a]);
+                if (TAIL && ti >= 1) issue_tail(ti - 1);
             }
+            if (TAIL && ti >= 1) issue_tail(ti - 1);
             if (hp.prof && blockIdx.x == 0)
                 printf("deform tmem MMA thread: %u tiles, total %lld cycles; wait acc %lld, wait A %lld, wait B %lld, issue %lld\n",
                        ti, clock64() - t_start, c_acc, c_a, c_b, c_issue);
@@ -524,13 +672,24 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
 }
 
 // --------------------------------------------------------------------------------------------- host side
-template <int BN, bool DENSE, bool LEAN, int G>
+static size_t tail_bytes(const ConvParams &p, int BN) {
+    return p.tail_wpack ? (size_t)(BN / 32) * 2 * p.tail_cout * 128 : 0;
+}
+
+template <int BN, bool DENSE, bool LEAN, int G, bool TAIL = false>
 static int tmem_launch_g(const DeformTmemParams &hp, const CUtensorMap &tm, cudaStream_t stream) {
-    const size_t smem = (size_t)G * 2 * BN * 32 * 4 + 2 * (size_t)hp.slot_bytes + 1024;
-    cudaFuncSetAttribute(deform_tmem_kernel<BN, DENSE, LEAN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = (size_t)G * 2 * BN * 32 * 4 + 2 * (size_t)hp.slot_bytes + tail_bytes(hp.p, BN) + 1024;
+    cudaFuncSetAttribute(deform_tmem_kernel<BN, DENSE, LEAN, G, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int rounds = ceil_div(hp.p.total_tiles, num_sms());
     const int grid = ceil_div(hp.p.total_tiles, rounds);
-    return launch_pdl(deform_tmem_kernel<BN, DENSE, LEAN, G>, dim3(grid), dim3(TCfg<G>::kThreads), smem, stream, hp, tm);
+    return launch_pdl(deform_tmem_kernel<BN, DENSE, LEAN, G, TAIL>, dim3(grid), dim3(TCfg<G>::kThreads), smem, stream, hp, tm);
+}
+
+// the fused-tail instantiations exist for the 3-group pipeline, lean epilogue, BN = 32 / 64
+template <bool DENSE>
+static int tmem_launch_tail(const DeformTmemParams &hp, const CUtensorMap &tm, int BN, cudaStream_t stream) {
+    return BN == 64 ? tmem_launch_g<64, DENSE, true, 3, true>(hp, tm, stream)
+                    : tmem_launch_g<32, DENSE, true, 3, true>(hp, tm, stream);
 }
 
 static int tmem_groups(bool dense) {
@@ -544,11 +703,20 @@ static int tmem_launch_inst(const DeformTmemParams &hp, const CUtensorMap &tm, i
     return groups == 4 ? tmem_launch_g<BN, DENSE, LEAN, 4>(hp, tm, stream) : tmem_launch_g<BN, DENSE, LEAN, 3>(hp, tm, stream);
 }
 
+// Fused 1x1 tail: one conv group, the main output is exactly one N tile of 32 / 64 channels (it becomes the tail's
+// K = 1 or 2 blocks), lean main epilogue (no NCHW output / residual / offset-mask head), tail width a multiple of 16.
+static bool tmem_tail_ok(const ConvParams &p, int BN) {
+    const MdcnDims &d = p.d;
+    return d.groups == 1 && d.Cout == BN && (BN == 32 || BN == 64) && !p.out_nchw && !p.residual &&
+           p.act != ACT_OFFSET_MASK && p.tail_cout >= 16 && p.tail_cout <= 64 && p.tail_cout % 16 == 0 &&
+           aligned16(p.tail_wpack) && (p.tail_act == ACT_NONE || p.tail_act == ACT_RELU || p.tail_act == ACT_LEAKY);
+}
+
 // Shared plan of the two modes; margin = pixels of learned offset the staged patch covers (0 for DENSE).
 static int tmem_plan(const ConvParams &src, int BN, int margin_req, int groups, DeformTmemParams &hp, CUtensorMap &tm) {
     const MdcnDims &d = src.d;
     hp.p = src;
-    const size_t ring = (size_t)groups * 2 * BN * 32 * 4;
+    const size_t ring = (size_t)groups * 2 * BN * 32 * 4 + tail_bytes(src, BN);
     // Halo plan.  The pitch (pixels per halo row) is rounded up to a multiple of 8 lines: a sample whose row index
     // jitters by one (sub-pixel offsets of either sign) then keeps its swizzle key (line & 7), so neighbouring
     // threads keep hitting different bank groups; the extra columns widen the horizontal margin.  Vertical margin:
@@ -594,13 +762,16 @@ int deform_tmem_launch(const ConvParams &src, int BN, cudaStream_t stream) {
     if (d.stride != 1 || d.Cg % 32 || d.Cd % 32 || !aligned16(src.x)) return AANET_ERR_UNSUPPORTED;
     if (src.out_nchw || src.residual || d.Og % 16 || (d.Cout & 3) || src.act == ACT_OFFSET_MASK) return AANET_ERR_UNSUPPORTED;
     if (BN != 32 && BN != 64) return AANET_ERR_UNSUPPORTED;
-    const int groups = tmem_groups(false);
+    const bool tail = src.tail_wpack != nullptr;
+    if (tail && !tmem_tail_ok(src, BN)) return AANET_ERR_UNSUPPORTED;
+    const int groups = tail ? 3 : tmem_groups(false);
     if (d.K < groups) return AANET_ERR_UNSUPPORTED;         // every producer group must own a tap in every halo slot
     const char *em = getenv("AANET_DEFORM_MARGIN");
     DeformTmemParams hp;
     CUtensorMap tm;
     const int rc = tmem_plan(src, BN, em ? atoi(em) : 4, groups, hp, tm);
     if (rc) return rc;
+    if (tail) return tmem_launch_tail<false>(hp, tm, BN, stream);
     return BN == 64 ? tmem_launch_inst<64, false, true>(hp, tm, groups, stream)
                     : tmem_launch_inst<32, false, true>(hp, tm, groups, stream);
 }
@@ -612,12 +783,15 @@ int dense_tmem_launch(const ConvParams &src, int BN, cudaStream_t stream) {
     const MdcnDims &d = src.d;
     if (d.stride != 1 || d.Cg % 32 || !aligned16(src.x) || src.residual || src.offset) return AANET_ERR_UNSUPPORTED;
     if (BN != 32 && BN != 48 && BN != 64) return AANET_ERR_UNSUPPORTED;
-    const int groups = tmem_groups(true);
+    const bool tail = src.tail_wpack != nullptr;
+    if (tail && !tmem_tail_ok(src, BN)) return AANET_ERR_UNSUPPORTED;
+    const int groups = tail ? 3 : tmem_groups(true);
     if (d.K < groups) return AANET_ERR_UNSUPPORTED;
     DeformTmemParams hp;
     CUtensorMap tm;
     const int rc = tmem_plan(src, BN, 0, groups, hp, tm);
     if (rc) return rc;
+    if (tail) return tmem_launch_tail<true>(hp, tm, BN, stream);
     const bool lean = !src.out_nchw && src.act != ACT_OFFSET_MASK && d.Og % 16 == 0 && (d.Cout & 3) == 0;
     switch (BN) {
         case 32: return lean ? tmem_launch_inst<32, true, true>(hp, tm, groups, stream) : tmem_launch_inst<32, true, false>(hp, tm, groups, stream);
@@ -625,6 +799,18 @@ int dense_tmem_launch(const ConvParams &src, int BN, cudaStream_t stream) {
         case 64: return lean ? tmem_launch_inst<64, true, true>(hp, tm, groups, stream) : tmem_launch_inst<64, true, false>(hp, tm, groups, stream);
     }
     return AANET_ERR_UNSUPPORTED;
+}
+
+bool tmem_tail_supported(const ConvParams &src, bool deform) {
+    const MdcnDims &d = src.d;
+    const int BN = conv_umma_pick_bn(d.Og);
+    if (!src.tail_wpack || !tmem_tail_ok(src, BN) || d.stride != 1 || d.Cg % 32 || d.K < 3 || !aligned16(src.x)) return false;
+    { const char *e = getenv(deform ? "AANET_DEFORM_TMEM" : "AANET_DENSE_TMEM"); if (e && e[0] == '0') return false; }
+    { const char *e = getenv("AANET_TAIL_FUSION"); if (e && e[0] == '0') return false; }
+    if (deform && d.Cd % 32) return false;
+    DeformTmemParams hp;
+    CUtensorMap tm;
+    return tmem_plan(src, BN, deform ? 4 : 0, 3, hp, tm) == AANET_OK;
 }
 
 }  // namespace aanet

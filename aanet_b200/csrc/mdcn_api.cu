@@ -154,6 +154,11 @@ static int problem_from_desc(const aanet_conv_desc &c, bool deform, ConvParams &
     p.bias = c.bias; p.scale = c.scale; p.shift = c.shift; p.residual = c.residual;
     p.act = c.act; p.slope = c.slope; p.n_offset_ch = c.n_offset_ch; p.mask_scale = c.mask_scale;
     p.d = d;
+    if (c.tail_wpack) {
+        if (c.tail_cout <= 0 || (c.tail_scale == nullptr) != (c.tail_shift == nullptr)) return AANET_ERR_SHAPE;
+        p.tail_wpack = static_cast<const float *>(c.tail_wpack); p.tail_scale = c.tail_scale; p.tail_shift = c.tail_shift;
+        p.tail_residual = c.tail_residual; p.tail_cout = c.tail_cout; p.tail_act = c.tail_act;
+    }
     if (deform) {
         if (!c.offmask) return AANET_ERR_NULL;
         const int n_off = c.dg * 2 * d.K, n_mask = c.dg * d.K;
@@ -171,6 +176,13 @@ static int problem_from_desc(const aanet_conv_desc &c, bool deform, ConvParams &
     return AANET_OK;
 }
 
+extern "C" int aanet_conv_tail_supported(const aanet_conv_desc *desc, int deform) {
+    if (!desc || !desc->tail_wpack) return 0;
+    ConvParams p;
+    if (problem_from_desc(*desc, deform != 0, p) != AANET_OK) return 0;
+    return tmem_tail_supported(p, deform != 0) ? 1 : 0;
+}
+
 extern "C" int aanet_conv_batch_nhwc(const aanet_conv_desc *descs, int n, int deform, int bn, void *stream) {
     if (!descs) return AANET_ERR_NULL;
     if (n < 1 || n > AANET_CONV_MAX_BATCH) return AANET_ERR_SHAPE;
@@ -178,6 +190,8 @@ extern "C" int aanet_conv_batch_nhwc(const aanet_conv_desc *descs, int n, int de
     for (int i = 0; i < n; ++i) {
         const int rc = problem_from_desc(descs[i], deform != 0, probs[i]);
         if (rc) return rc;
+        // a fused tail only exists in the tensor-memory kernels (single problem)
+        if (probs[i].tail_wpack && (n != 1 || !tmem_tail_supported(probs[i], deform != 0))) return AANET_ERR_UNSUPPORTED;
     }
     return conv_umma_launch_batch(probs, n, deform != 0, bn, as_stream(stream));
 }

@@ -68,10 +68,15 @@ class _Conv:
                     scale=self.scale, shift=self.shift, act=self.act, slope=self.slope, stride=self.stride,
                     pad=self.pad, dil=self.dil, groups=self.groups)
 
-    def __call__(self, x, residual=None, out_nchw=False, n_offset_ch=0, mask_scale=1.0, act=None):
+    def as_tail(self, residual, act=None):
+        """This (1x1) convolution as the fused tail of the preceding one (ops.conv_batch "tail")."""
+        return dict(wpack=self.wpack, Cout=self.Cout, scale=self.scale, shift=self.shift, residual=residual,
+                    act=self.act if act is None else act)
+
+    def __call__(self, x, residual=None, out_nchw=False, n_offset_ch=0, mask_scale=1.0, act=None, tail=None):
         return ops.conv2d_nhwc(x, self.wpack, self.Cout, self.kh, self.kw, self.bias, self.scale, self.shift,
                                residual, self.act if act is None else act, self.slope, self.stride, self.pad,
-                               self.dil, self.groups, out_nchw, n_offset_ch, mask_scale)
+                               self.dil, self.groups, out_nchw, n_offset_ch, mask_scale, tail=tail)
 
 
 class _Deform:
@@ -98,13 +103,13 @@ class _Deform:
         sc, sh = bn_affine(self._bn)
         self.scale.copy_(sc); self.shift.copy_(sh)
 
-    def __call__(self, x):
+    def __call__(self, x, tail=None):
         # offsets pass through, mask channels get mask_scale * sigmoid (deform.py:82-89), one tensor, written
         # as channel planes: the DCN producers read it pixel-contiguously
         om = self.head(x, act=ops.ACT_OFFSET_MASK, n_offset_ch=self.n_off, mask_scale=self.mask_scale,
                        out_nchw=True)
         return ops.mdcn_nhwc(x, om, self.wpack, self.Cout, self.kh, self.kw, self.bias, self.scale, self.shift,
-                             True, self.stride, self.pad, self.dil, self.groups, self.dg, om_nchw=True)
+                             True, self.stride, self.pad, self.dil, self.groups, self.dg, om_nchw=True, tail=tail)
 
 
 class _Bottleneck:
@@ -115,13 +120,38 @@ class _Bottleneck:
         else:
             self.c2 = _Conv(blk.conv2, blk.bn2, ops.ACT_RELU)
         self.c3 = _Conv(blk.conv3, blk.bn3, ops.ACT_RELU)     # relu(bn3(conv3) + identity)
+        self._tail = {}
 
     def refresh(self):
         for c in (self.c1, self.c2, self.c3):
             c.refresh()
 
+    def _tail_ok(self, y1):
+        """Is conv3 (1x1 + bn3 + identity + ReLU) fusable into conv2's launch for this input shape?  (Tensor-memory
+        kernels: 32-channel blocks, one N tile; asked once per shape.)"""
+        # the A/B switches of the kernels are read per launch, so they are part of the key
+        key = (tuple(y1.shape), y1.device) + tuple(os.environ.get(k) for k in
+                                                   ("AANET_DENSE_TMEM", "AANET_DEFORM_TMEM", "AANET_TAIL_FUSION"))
+        if key not in self._tail:
+            c2, c3 = self.c2, self.c3
+            ok = c3.kh == 1 and c3.kw == 1 and c3.groups == 1 and c3.bias is None and c3.stride == 1 and c3.pad == 0
+            if ok:
+                deform = isinstance(c2, _Deform)
+                q = dict(x=y1, wpack=c2.wpack, Cout=c2.Cout, kh=c2.kh, kw=c2.kw, bias=c2.bias, scale=c2.scale,
+                         shift=c2.shift, act=ops.ACT_RELU, stride=c2.stride, pad=c2.pad, dil=c2.dil, groups=c2.groups,
+                         tail=c3.as_tail(None))
+                if deform:
+                    B, H, W, _ = y1.shape
+                    q.update(dg=c2.dg, om_nchw=True, offmask=y1.new_empty(B, c2.n_off * 3 // 2, H, W))
+                ok = ops.conv_tail_supported(q, deform)
+            self._tail[key] = ok
+        return self._tail[key]
+
     def __call__(self, x):
-        return self.c3(self.c2(self.c1(x)), residual=x)
+        y1 = self.c1(x)
+        if self._tail_ok(y1):
+            return self.c2(y1, tail=self.c3.as_tail(x))          # conv2 (+ bn2 + ReLU) and conv3 + bn3 + x + ReLU: one launch
+        return self.c3(self.c2(y1), residual=x)
 
 
 # One multi-problem launch for the last conv of all exchange chains of a CSA row (A/B on one box: 913 vs 910

@@ -429,43 +429,73 @@ def _cl(t, name, dev, shape=None):
     return t
 
 
+def _fill_desc(d, q, out):
+    """Fill one aanet_conv_desc from a problem dict (see conv_batch); `out` is the output tensor or None."""
+    x = q["x"]
+    if x.dim() != 4:
+        raise ValueError("aanet_b200.conv_batch: x must be channels-last [B,H,W,C]")
+    dev = x.device
+    _cl(x, "x", dev)
+    B, H, W, Cin = x.shape
+    Ho, Wo = _out_hw(H, W, q["kh"], q["kw"], q["stride"], q["pad"], q["dil"])
+    tail = q.get("tail")
+    c_out = tail["Cout"] if tail else q["Cout"]
+    oshape = (B, c_out, Ho, Wo) if q.get("out_nchw") else (B, Ho, Wo, c_out)
+    om = q.get("offmask")
+    for nm in ("bias", "scale", "shift"):
+        _cl(q.get(nm), nm, dev, (q["Cout"],))
+    _cl(q.get("residual"), "residual", dev, oshape)
+    if om is not None:
+        if om.dim() != 4 or (tuple(om.shape[2:]) if q.get("om_nchw") else tuple(om.shape[1:3])) != (Ho, Wo) \
+                or om.shape[0] != B:
+            raise ValueError("aanet_b200.conv_batch: offmask must be [B,om,Ho,Wo] (om_nchw) or [B,Ho,Wo,om]")
+        _cl(om, "offmask", dev)
+    if q["wpack"].device != dev:
+        raise ValueError("aanet_b200.conv_batch: packed weights are on %s, x is on %s" % (q["wpack"].device, dev))
+    d.x, d.wpack = x.data_ptr(), q["wpack"].data_ptr()
+    d.out = None if out is None else out.data_ptr()
+    d.bias, d.scale, d.shift = _dp(q.get("bias")), _dp(q.get("scale")), _dp(q.get("shift"))
+    d.residual, d.offmask = _dp(q.get("residual")), _dp(om)
+    d.om_nchw = int(bool(q.get("om_nchw")))
+    d.om_channels = 0 if om is None else (om.shape[1] if d.om_nchw else om.shape[-1])
+    d.B, d.Cin, d.H, d.W, d.Cout, d.kh, d.kw = B, Cin, H, W, q["Cout"], q["kh"], q["kw"]
+    d.stride, d.pad, d.dil, d.groups, d.dg = q["stride"], q["pad"], q["dil"], q.get("groups", 1), q.get("dg", 1)
+    d.act, d.slope = int(q.get("act", ACT_NONE)), float(q.get("slope", 0.2))
+    d.n_offset_ch, d.mask_scale = int(q.get("n_offset_ch", 0)), float(q.get("mask_scale", 1.0))
+    d.out_nchw = int(bool(q.get("out_nchw")))
+    if tail:
+        if q.get("residual") is not None or q.get("out_nchw"):
+            raise ValueError("aanet_b200.conv_batch: a problem with a fused tail has no main residual / NCHW output")
+        for nm in ("scale", "shift"):
+            _cl(tail.get(nm), "tail " + nm, dev, (tail["Cout"],))
+        _cl(tail.get("residual"), "tail residual", dev, oshape)
+        d.tail_wpack = tail["wpack"].data_ptr()
+        d.tail_scale, d.tail_shift = _dp(tail.get("scale")), _dp(tail.get("shift"))
+        d.tail_residual = _dp(tail.get("residual"))
+        d.tail_cout, d.tail_act = int(tail["Cout"]), int(tail.get("act", ACT_NONE))
+    return oshape
+
+
+def conv_tail_supported(problem, deform=False):
+    """Can `problem` (a conv_batch dict with a "tail" entry: the bottleneck's trailing 1x1 + BN + residual + act) run
+    as ONE launch of the tensor-memory kernels?"""
+    d = _lib.ConvDesc()
+    _fill_desc(d, problem, problem["x"])          # any valid pointer: the query does not launch
+    return bool(_lib.load().aanet_conv_tail_supported(ctypes.byref(d), int(deform)))
+
+
 def conv_batch(problems, deform=False, bn=0):
-    """Run 1..3 problems (dicts, see conv_problem) as one persistent engine launch; returns their outputs."""
+    """Run 1..3 problems (dicts: x, wpack, Cout, kh, kw, stride, pad, dil [, bias, scale, shift, residual, act,
+    slope, groups, dg, offmask, om_nchw, out_nchw, n_offset_ch, mask_scale, tail]) as one persistent engine launch;
+    returns their outputs."""
     n = len(problems)
     descs = (_lib.ConvDesc * n)()
     outs = []
     for d, q in zip(descs, problems):
-        x = q["x"]
-        if x.dim() != 4:
-            raise ValueError("aanet_b200.conv_batch: x must be channels-last [B,H,W,C]")
-        dev = x.device
-        _cl(x, "x", dev)
-        B, H, W, Cin = x.shape
-        Ho, Wo = _out_hw(H, W, q["kh"], q["kw"], q["stride"], q["pad"], q["dil"])
-        oshape = (B, q["Cout"], Ho, Wo) if q.get("out_nchw") else (B, Ho, Wo, q["Cout"])
-        out = x.new_empty(oshape)
+        oshape = _fill_desc(d, q, None)
+        out = q["x"].new_empty(oshape)
+        d.out = out.data_ptr()
         outs.append(out)
-        om = q.get("offmask")
-        for nm in ("bias", "scale", "shift"):
-            _cl(q.get(nm), nm, dev, (q["Cout"],))
-        _cl(q.get("residual"), "residual", dev, oshape)
-        if om is not None:
-            if om.dim() != 4 or (tuple(om.shape[2:]) if q.get("om_nchw") else tuple(om.shape[1:3])) != (Ho, Wo) \
-                    or om.shape[0] != B:
-                raise ValueError("aanet_b200.conv_batch: offmask must be [B,om,Ho,Wo] (om_nchw) or [B,Ho,Wo,om]")
-            _cl(om, "offmask", dev)
-        if q["wpack"].device != dev:
-            raise ValueError("aanet_b200.conv_batch: packed weights are on %s, x is on %s" % (q["wpack"].device, dev))
-        d.x, d.wpack, d.out = x.data_ptr(), q["wpack"].data_ptr(), out.data_ptr()
-        d.bias, d.scale, d.shift = _dp(q.get("bias")), _dp(q.get("scale")), _dp(q.get("shift"))
-        d.residual, d.offmask = _dp(q.get("residual")), _dp(om)
-        d.om_nchw = int(bool(q.get("om_nchw")))
-        d.om_channels = 0 if om is None else (om.shape[1] if d.om_nchw else om.shape[-1])
-        d.B, d.Cin, d.H, d.W, d.Cout, d.kh, d.kw = B, Cin, H, W, q["Cout"], q["kh"], q["kw"]
-        d.stride, d.pad, d.dil, d.groups, d.dg = q["stride"], q["pad"], q["dil"], q.get("groups", 1), q.get("dg", 1)
-        d.act, d.slope = int(q.get("act", ACT_NONE)), float(q.get("slope", 0.2))
-        d.n_offset_ch, d.mask_scale = int(q.get("n_offset_ch", 0)), float(q.get("mask_scale", 1.0))
-        d.out_nchw = int(bool(q.get("out_nchw")))
     x0 = problems[0]["x"]
     with torch.cuda.device(x0.device):
         _lib.check(_lib.load().aanet_conv_batch_nhwc(ctypes.cast(descs, ctypes.c_void_p), n, int(deform), int(bn),
@@ -476,21 +506,22 @@ def conv_batch(problems, deform=False, bn=0):
 
 def conv2d_nhwc(x, wpack, Cout, kh, kw, bias=None, scale=None, shift=None, residual=None, act=ACT_NONE,
                 slope=0.2, stride=1, padding=0, dilation=1, groups=1, out_nchw=False, n_offset_ch=0,
-                mask_scale=1.0):
+                mask_scale=1.0, tail=None):
     """Dense convolution on channels-last activations x [B,H,W,Cin] with pre-packed weights."""
     return conv_batch([dict(x=x, wpack=wpack, Cout=Cout, kh=kh, kw=kw, bias=bias, scale=scale, shift=shift,
                             residual=residual, act=act, slope=slope, stride=stride, pad=padding, dil=dilation,
-                            groups=groups, out_nchw=out_nchw, n_offset_ch=n_offset_ch, mask_scale=mask_scale)])[0]
+                            groups=groups, out_nchw=out_nchw, n_offset_ch=n_offset_ch, mask_scale=mask_scale,
+                            tail=tail)])[0]
 
 
 def mdcn_nhwc(x, offmask, wpack, Cout, kh, kw, bias=None, scale=None, shift=None, relu=False, stride=1,
-              padding=0, dilation=1, groups=1, deformable_groups=1, out_nchw=False, om_nchw=False):
+              padding=0, dilation=1, groups=1, deformable_groups=1, out_nchw=False, om_nchw=False, tail=None):
     """DCNv2 on channels-last x [B,H,W,Cin] with offsets+mask in one tensor: channels-last [B,Ho,Wo,om] or,
     with om_nchw, channel planes [B,om,Ho,Wo] (one L1 wavefront per offset load instead of ~20)."""
     return conv_batch([dict(x=x, offmask=offmask, wpack=wpack, Cout=Cout, kh=kh, kw=kw, bias=bias, scale=scale,
                             shift=shift, act=ACT_RELU if relu else ACT_NONE, stride=stride, pad=padding,
                             dil=dilation, groups=groups, dg=deformable_groups, out_nchw=out_nchw,
-                            om_nchw=om_nchw)], deform=True)[0]
+                            om_nchw=om_nchw, tail=tail)], deform=True)[0]
 
 
 def csa_fuse_nhwc(terms, slope=0.2):

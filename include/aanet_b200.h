@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define AANET_B200_ABI_VERSION 1
+#define AANET_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define AANET_API __attribute__((visibility("default")))
@@ -203,6 +203,14 @@ typedef struct aanet_conv_desc {
     float mask_scale;        /* act == 3 */
     int out_nchw;
     int om_nchw;             /* DEFORM: offmask is [B][om_channels][Ho*Wo] (channel planes) instead of channels-last */
+    /* Optional fused 1x1 tail (tail_wpack != NULL), the trailing conv3 + bn3 + identity + ReLU of a bottleneck
+     * (nets/deform.py:177-183, :229-235) inside the same launch:
+     *   out = tail_act( conv1x1(act(main result), tail weights) * tail_scale + tail_shift + tail_residual )
+     * `out` and `tail_residual` are then [B][Ho*Wo][tail_cout]; bias/scale/shift/act describe the main convolution,
+     * whose result never leaves the chip.  Only problems for which aanet_conv_tail_supported() returns 1. */
+    const void *tail_wpack;  /* aanet_conv_pack_weights of the [tail_cout, Cout, 1, 1] weight */
+    const float *tail_scale, *tail_shift, *tail_residual;
+    int tail_cout, tail_act;
 } aanet_conv_desc;
 
 #define AANET_CONV_MAX_BATCH 3
@@ -211,6 +219,9 @@ typedef struct aanet_conv_desc {
  * tile list spans all of them -- the three pyramid scales of one aggregation stage.  All problems use the
  * same N-tile width bn (0 = the widest natural width among them); their weights must be packed for it. */
 AANET_API int aanet_conv_batch_nhwc(const aanet_conv_desc *descs, int n, int deform, int bn, void *stream);
+/* 1 when `desc` (with its tail fields set) can run as ONE launch of the tensor-memory kernels, else 0: the caller
+ * then issues the main convolution and the 1x1 as two problems. */
+AANET_API int aanet_conv_tail_supported(const aanet_conv_desc *desc, int deform);
 /* Channels-last twin of aanet_csa_fuse_fwd: terms and out are [B][h][w][C], C % 4 == 0. */
 AANET_API int aanet_csa_fuse_nhwc(const float *const *terms, const int *th, const int *tw, int n_terms,
                                   float *out, int B, int C, int H, int W, float slope, void *stream);

@@ -100,3 +100,48 @@ def test_halo_fused_executor_matches_gather_engine(halo):
         old = agg([c.clone() for c in costs])[0]
         _select(halo)
     assert rel_err(npy(new), npy(old)) < 1e-5
+
+
+@pytest.mark.parametrize("cfg", [
+    # B, C (= bottleneck width), H, W, deform, dil
+    (1, 64, 128, 416, False, 1),      # SimpleBottleneck conv2 + conv3 at the 1/3 scale (config 2)
+    (1, 64, 128, 416, True, 2),       # DeformSimpleBottleneck conv2 + conv3
+    (2, 32, 33, 47, False, 1),        # one channel block, ragged tiles, batch 2, one K block in the tail
+    (1, 64, 24, 52, True, 2),
+    (3, 64, 9, 20, False, 1),         # more tiles than two per CTA never happens here; several images
+])
+def test_fused_tail_matches_two_launches(cfg):
+    """conv2 (+ bn2 + ReLU) with the bottleneck's trailing conv3 + bn3 + identity + ReLU fused into the same launch
+    (activated tile written back into tensor memory as the A operand of the 1x1) against the two-launch path, and
+    against float64 torch for the dense case."""
+    import aanet_b200.ops as ops
+    B, C, H, W, deform, dil = cfg
+    torch.manual_seed(29)
+    x = torch.randn(B, H, W, C, device="cuda")
+    idn = torch.randn(B, H, W, C, device="cuda")
+    w2 = torch.randn(C, C, 3, 3, device="cuda") / (C * 9) ** 0.5
+    w3 = torch.randn(C, C, 1, 1, device="cuda") / C ** 0.5
+    s2, h2 = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda")
+    s3, h3 = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda")
+    wp2, wp3 = ops.pack_conv_weight(w2), ops.pack_conv_weight(w3)
+    tail = dict(wpack=wp3, Cout=C, scale=s3, shift=h3, residual=idn, act=ops.ACT_RELU)
+    if deform:
+        om = torch.cat([0.7 * torch.randn(B, 36, H, W, device="cuda"),
+                        2 * torch.sigmoid(torch.randn(B, 18, H, W, device="cuda"))], 1).contiguous()
+        q = dict(x=x, offmask=om, om_nchw=True, wpack=wp2, Cout=C, kh=3, kw=3, scale=s2, shift=h2, act=ops.ACT_RELU,
+                 stride=1, pad=dil, dil=dil, groups=1, dg=2)
+    else:
+        q = dict(x=x, wpack=wp2, Cout=C, kh=3, kw=3, scale=s2, shift=h2, act=ops.ACT_RELU, stride=1, pad=dil, dil=dil,
+                 groups=1)
+    assert ops.conv_tail_supported(dict(q, tail=tail), deform)
+    fused = ops.conv_batch([dict(q, tail=tail)], deform=deform)[0]
+    y2 = ops.conv_batch([q], deform=deform)[0]
+    two = ops.conv2d_nhwc(y2, wp3, C, 1, 1, None, s3, h3, idn, ops.ACT_RELU)
+    assert fused.shape == two.shape
+    assert rel_err(npy(fused), npy(two)) < 1e-5
+    if not deform:
+        xr = x.permute(0, 3, 1, 2).double()
+        r2 = torch.relu(torch.nn.functional.conv2d(xr, w2.double(), None, 1, dil, dil) * s2.view(1, -1, 1, 1) + h2.view(1, -1, 1, 1))
+        r3 = torch.relu(torch.nn.functional.conv2d(r2, w3.double()) * s3.view(1, -1, 1, 1) + h3.view(1, -1, 1, 1)
+                        + idn.permute(0, 3, 1, 2))
+        assert rel_err(npy(fused.permute(0, 3, 1, 2)), npy(r3)) < 1e-5

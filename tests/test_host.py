@@ -32,7 +32,7 @@ def test_library_exports_every_header_symbol(lib_path):
     from aanet_b200 import _lib
     assert set(_lib.SIGNATURES) == declared          # binding covers exactly the header
     loaded = _lib.load()
-    assert loaded.aanet_abi_version() == 1
+    assert loaded.aanet_abi_version() == _lib.ABI_VERSION == 2
     assert loaded.aanet_status_string(0) == b"ok"
     assert b"shape" in loaded.aanet_status_string(2)
 
