@@ -31,19 +31,23 @@ def _deps():
     return out
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, defs=()):
+    """variant / defs: a second build of the same library with extra -D switches (e.g. the instrumented kernels,
+    variant="prof", defs=["-DAANET_TMEM_PROF"]) written to lib/libaanet_b200_<variant>.so; load it with
+    AANET_B200_LIB=<path>."""
+    LIB = globals()["LIB"] if not variant else os.path.join(HERE, "lib", "libaanet_b200_%s.so" % variant)
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     if (not force and os.path.exists(LIB)
             and all(os.path.getmtime(LIB) >= os.path.getmtime(p) for p in _deps())):
         return LIB
     objs = []
     procs = []
-    build_dir = os.path.join(HERE, "lib", "obj")
+    build_dir = os.path.join(HERE, "lib", "obj" if not variant else "obj_" + variant)
     os.makedirs(build_dir, exist_ok=True)
     for src in SOURCES:
         obj = os.path.join(build_dir, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("AANET_NVCC_DEFS", "").split() + \
+        cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("AANET_NVCC_DEFS", "").split() + list(defs) + \
               (["-Xptxas", "-v"] if verbose else []) + \
               ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
@@ -61,4 +65,7 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--prof" in sys.argv:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant="prof", defs=["-DAANET_TMEM_PROF"]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -54,9 +54,22 @@ struct DeformTmemParams {
     ConvParams p;
     int HH, HWd, lines, slot_bytes;    // halo box (rows, pixels per row), lines = HH * HWd, bytes rounded to 1024
     int margin_y, margin_x, n_cb, prof;   // pixels of offset the halo covers above/below and left/right
+    int spin;                             // experiment: the MMA thread polls its barriers instead of sleeping on them
 };
 
 struct TItem { int grp, nt, b, ty, tx; };
+
+// AANET_HALO_PROF=2: block 0 records clock64 stamps of the first kTraceKB K blocks (producer: stage free seen / stores
+// issued / wait::st done / arrived; MMA thread: A seen / B seen / issued + committed) and prints them at exit.
+// Both need a -DAANET_TMEM_PROF build (AANET_NVCC_DEFS): the clock64 reads and counters sit on the critical path of the
+// single MMA-issuing thread (measured: ~490 of its ~980 cycles per K block were instrumentation and barrier overhead).
+constexpr int kTraceKB = 48;
+#ifdef AANET_TMEM_PROF
+__device__ long long g_ttrace[kTraceKB][8];
+#define TP(...) __VA_ARGS__
+#else
+#define TP(...)
+#endif
 
 __device__ __forceinline__ TItem t_item(const ConvParams &p, int t) {
     TItem it;
@@ -119,13 +132,14 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
     static_assert(2 * BN <= 128, "accumulator stride is 128 columns");
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_halo_full[2], bar_halo_empty[2];
-    __shared__ __align__(8) uint64_t bar_full_a[S], bar_full_b[S], bar_empty[S];
+    __shared__ __align__(8) uint64_t bar_full[S], bar_empty[S];   // full: 4 producer warps + the weight block's bytes
     __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2];
     __shared__ __align__(8) uint64_t bar_y2[2], bar_acc3_full, bar_acc3_empty, bar_tailw;      // TAIL only
     __shared__ uint32_t s_tmem;
     __shared__ __align__(16) float s_aff[2][BN];
     __shared__ __align__(16) float s_aff3[2][64];
     __shared__ int2 s_tapoff[64];                             // per tap: (ki * dil - pad, kj * dil - pad)
+    __shared__ int s_dgk[64];                                 // per 32-channel block of the input: first offset channel of its deformable group
 
     const ConvParams &p = hp.p;
     const MdcnDims &d = p.d;
@@ -134,6 +148,7 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
     uint8_t *halo0 = smem + (size_t)S * kBTile;               // two halo slots behind the weight ring
     uint8_t *tailw = halo0 + 2 * (size_t)hp.slot_bytes;       // TAIL: resident packed weights of the 1x1 convolution
     if (tid < d.K) s_tapoff[tid] = make_int2((tid / d.kw) * d.dil - d.pad, (tid % d.kw) * d.dil - d.pad);
+    if (!DENSE && tid < 64) s_dgk[tid] = ((tid * 32) / max(d.Cd, 1)) * d.K;
     const int T = d.K, n_cb = hp.n_cb, total = p.total_tiles;
 
     if (tid == 0) {
@@ -142,8 +157,10 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
             umma::mbar_init(&bar_halo_empty[s], kTProdWarps); // every producer warp, after its last tap of the slot
         }
         for (int s = 0; s < S; ++s) {
-            umma::mbar_init(&bar_full_a[s], 4);               // the four warps of the filling group
-            umma::mbar_init(&bar_full_b[s], 1);
+            umma::mbar_init(&bar_full[s], 5);                 // the four warps of the filling group + arrive.expect_tx of
+                                                              // the weight loader: ONE wait per K block for the MMA thread
+                                                              // (a barrier operation costs that thread ~100 cycles; a
+                                                              // separate, deeper weight ring measured slower: 25 -> 30 us)
             umma::mbar_init(&bar_empty[s], 1);                // tcgen05.commit: A stage (TMEM) and B stage (smem) free
         }
         for (int a = 0; a < 2; ++a) {
@@ -161,6 +178,10 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
     __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem_base = s_tmem;
+    // Register rebalancing (warpgroup-collective): 640 threads cap a uniform allocation at 96 registers, with which the
+    // deformable producers spill (110 bytes once the instrumentation left the loop: 45.6 -> 53 us).  Same split the
+    // round-1 engine runs with: producers 112, epilogue 96, control warps 40.
+    // (issued at the top of the role branches: values live across a setmaxnreg must fit the smaller budget)
     pdl_wait();
     bool triggered = false;
 
@@ -334,22 +355,21 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
         }
     } else if (warp < kTProdWarp0 + kTProdWarps) {
         // ================================ A producers: thread = pixel = TMEM lane =================
+        if (G == 3) umma::setmaxnreg_inc<112>();      // 384 x 112 + 128 x 96 + 128 x 40 <= 640 x 96
         const int pw = warp - kTProdWarp0;
         const int grpi = pw >> 2, q = pw & 3;                 // producer group; TMEM lane quarter (== warp % 4)
         const int row = q * 32 + lane;                        // row of the tile this thread produces
-        long long c_wait_halo = 0, c_wait_stage = 0;
-        const long long pt0 = clock64();
+        TP(long long c_wait_halo = 0, c_wait_stage = 0; const long long pt0 = clock64();)
 
-        // Walk state of this group's K blocks (every kTGroups-th of the CTA's (tile, channel block, tap) sequence).
-        // Everything that only changes with the tile or the channel block is decoded when it changes, not per K
-        // block (the first version spent 450 of its 730 instructions per K block on index arithmetic).
-        struct St {
-            int t, cb, tap; uint32_t it, hs;
-            int b, grp, oh, ow, hy0, hx0; bool ok;
+        // Walk of this group's K blocks (every G-th of the CTA's (tile, channel block, tap) sequence).  State is kept
+        // small on purpose: per-tile values in `tl`, (cb, tap, hs, ph) for the position, and only the three prefetched
+        // geometry values live across the body.  (An earlier cur / nxt pair of full states made ptxas spill the
+        // prefetched offsets right after the load, i.e. wait for the DRAM miss it was meant to hide: 45 -> 53 us.)
+        struct Tile {
+            int t, b, grp, oh, ow, hy0, hx0; bool ok;
             const float *off, *msk;          // offset / mask pointers of my pixel, channel 0
-            long ch0;                        // first offset channel of the deformable group of (grp, cb)
         };
-        auto decode_tile = [&](St &c) {
+        auto decode_tile = [&](Tile &c) {
             const TItem item = t_item(p, c.t);
             c.b = item.b; c.grp = item.grp;
             c.oh = item.ty * kTTH + (row >> 4); c.ow = item.tx * kTTW + (row & 15);
@@ -360,59 +380,57 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
             c.off = DENSE ? nullptr : p.offset + (long)item.b * p.off_bs + pc * p.off_ps;
             c.msk = (!DENSE && p.mask) ? p.mask + (long)item.b * p.mask_bs + pc * p.mask_ps : nullptr;
         };
-        auto decode_cb = [&](St &c) { c.ch0 = DENSE ? 0 : (long)((c.grp * d.Cg + c.cb * 32) / d.Cd) * d.K; };
-        auto advance = [&](St &c, int n) {
-            c.it += n; c.tap += n;
-            if (c.tap < T) return;
-            bool new_tile = false;
-            while (c.tap >= T) {
-                c.tap -= T; ++c.cb; ++c.hs;
-                if (c.cb == n_cb) { c.cb = 0; c.t += gridDim.x; new_tile = true; }
-            }
-            if (c.t < total) {
-                if (new_tile) decode_tile(c);
-                decode_cb(c);
-            }
-        };
-        auto load_geom = [&](const St &c, float &gh, float &gw, float &gm) {
+        // s_dgk[grp * n_cb + cb] = first offset channel of the deformable group the 32-channel block belongs to
+        auto load_geom = [&](const Tile &c, int cb_, int tap_, float &gh_, float &gw_, float &gm_) {
             if (DENSE) return;
-            const long ch = c.ch0 + c.tap;
-            gh = __ldg(c.off + (ch * 2) * p.off_cs);
-            gw = __ldg(c.off + (ch * 2 + 1) * p.off_cs);
-            gm = c.msk ? __ldg(c.msk + ch * p.mask_cs) : 1.f;
+            const long ch = s_dgk[c.grp * n_cb + cb_] + tap_;
+            gh_ = __ldg(c.off + (ch * 2) * p.off_cs);
+            gw_ = __ldg(c.off + (ch * 2 + 1) * p.off_cs);
+            gm_ = c.msk ? __ldg(c.msk + ch * p.mask_cs) : 1.f;
         };
 
-        St cur;
-        cur.t = (int)blockIdx.x; cur.cb = 0; cur.tap = 0; cur.it = 0u; cur.hs = 0u;
-        if (cur.t < total) { decode_tile(cur); decode_cb(cur); }
-        advance(cur, grpi);
+        Tile tl;
+        tl.t = (int)blockIdx.x;
+        int cb = 0, tap = grpi;                               // G <= T: the group's first K block is tap grpi of block 0
+        uint32_t hs = 0u, ph = 0u;                            // halo slot sequence number; parity of my stage's use count
+        TP(uint32_t it_seq = grpi;)
+        const int s = grpi;                                   // S == G: group g always refills A stage g
         float gh = 0.f, gw = 0.f, gm = 0.f;
-        if (cur.t < total) load_geom(cur, gh, gw, gm);
-        int2 tapo = s_tapoff[cur.tap];
+        if (tl.t < total) { decode_tile(tl); load_geom(tl, cb, tap, gh, gw, gm); }
+        int2 tapo = s_tapoff[tap];
         uint32_t ready_hs = 0xffffffffu;
-        while (cur.t < total) {
+        while (tl.t < total) {
             // offsets / mask of my NEXT K block: each (tap, deformable group) plane is touched once per tile, so
             // these loads are DRAM misses and must be in flight while the current K block is produced
-            St nxt = cur;
-            advance(nxt, kTGroups);
+            const bool last_in_slot = tap + G >= T;           // my last tap inside this halo slot
             float ngh = 0.f, ngw = 0.f, ngm = 0.f;
-            if (nxt.t < total) load_geom(nxt, ngh, ngw, ngm);
-            const int2 ntapo = s_tapoff[nxt.tap];                                // (ki * dil - pad, kj * dil - pad)
-            const int s = cur.it % S;
-            const uint32_t ph = (cur.it / S) & 1;
-            const int hslot = cur.hs & 1;
+            if (!DENSE) {
+                const int ntap = last_in_slot ? tap + G - T : tap + G;
+                const int ncb = last_in_slot ? cb + 1 : cb;
+                if (ncb < n_cb) {
+                    load_geom(tl, ncb, ntap, ngh, ngw, ngm);
+                } else if (tl.t + (int)gridDim.x < total) {   // first K block of my next tile
+                    Tile tn;
+                    tn.t = tl.t + (int)gridDim.x;
+                    decode_tile(tn);
+                    load_geom(tn, 0, ntap, ngh, ngw, ngm);
+                }
+            }
+            const int hslot = hs & 1;
             const uint32_t halo = umma::smem_u32(halo0 + (size_t)hslot * hp.slot_bytes);
             if (DENSE) {
                 // the tap's input pixel of my output pixel: always inside the staged patch (margin 0); out-of-image
                 // pixels were zero-filled by the TMA unit (= the convolution's zero padding)
-                if (ready_hs != cur.hs) {
-                    umma::mbar_wait(&bar_halo_full[hslot], (cur.hs >> 1) & 1);
-                    ready_hs = cur.hs;
+                if (ready_hs != hs) {
+                    umma::mbar_wait(&bar_halo_full[hslot], (hs >> 1) & 1);
+                    ready_hs = hs;
                 }
                 umma::mbar_wait(&bar_empty[s], ph ^ 1);
+                TP(const bool tr = hp.prof == 2 && blockIdx.x == 0 && q == 0 && lane == 0 && it_seq < (uint32_t)kTraceKB;
+                   if (tr) g_ttrace[it_seq][0] = clock64();)
                 umma::tc_fence_after();
                 const uint32_t a_col = tmem_base + ((uint32_t)(q * 32) << 16) + kTACol + s * kTAStageCols;
-                const int l0 = (cur.oh + tapo.x - cur.hy0) * hp.HWd + (cur.ow + tapo.y - cur.hx0);
+                const int l0 = (tl.oh + tapo.x - tl.hy0) * hp.HWd + (tl.ow + tapo.y - tl.hx0);
                 const uint32_t P0 = (halo + (uint32_t)l0 * 128) | ((uint32_t)(l0 & 7) << 4);
                 float4 qd[8];
 #pragma unroll
@@ -427,37 +445,49 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                     tmem_st8(a_col + c8 * 8, hi);
                     tmem_st8(a_col + 32 + c8 * 8, lo);
                 }
+                TP(if (tr) g_ttrace[it_seq][1] = clock64();)
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                TP(if (tr) g_ttrace[it_seq][2] = clock64();)
                 umma::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    umma::mbar_arrive(&bar_full_a[s]);
-                    if (nxt.hs != cur.hs) umma::mbar_arrive(&bar_halo_empty[hslot]);
+                    umma::mbar_arrive(&bar_full[s]);
+                    if (last_in_slot) umma::mbar_arrive(&bar_halo_empty[hslot]);
                 }
-                cur = nxt; tapo = ntapo;
+                TP(if (tr) g_ttrace[it_seq][3] = clock64();)
+                {   // step to my next K block
+                    tap += G; ph ^= 1u; TP(it_seq += G;)
+                    if (tap >= T) {
+                        tap -= T; ++hs;
+                        if (++cb == n_cb) { cb = 0; tl.t += (int)gridDim.x; if (tl.t < total) decode_tile(tl); }
+                    }
+                    tapo = s_tapoff[tap];
+                }
                 continue;
             }
             // ---- my bilinear sample for this (tap, deformable group)
-            const float py = (float)(cur.oh + tapo.x) + gh;
-            const float px = (float)(cur.ow + tapo.y) + gw;
+            const float py = (float)(tl.oh + tapo.x) + gh;
+            const float px = (float)(tl.ow + tapo.y) + gw;
             const float fy = floorf(py), fx = floorf(px);
             const float lh = py - fy, lw = px - fx;
-            const float m = cur.ok ? gm : 0.f;
-            const float ry = fy - (float)cur.hy0, rx = fx - (float)cur.hx0;      // top-left corner inside the halo?
+            const float m = tl.ok ? gm : 0.f;
+            const float ry = fy - (float)tl.hy0, rx = fx - (float)tl.hx0;      // top-left corner inside the halo?
             const bool inside = ry >= 0.f && rx >= 0.f && ry <= (float)(hp.HH - 2) && rx <= (float)(hp.HWd - 2);
             float w0 = (1.f - lh) * (1.f - lw) * m, w1 = (1.f - lh) * lw * m, w2 = lh * (1.f - lw) * m, w3 = lh * lw * m;
 
-            if (ready_hs != cur.hs) {
-                const long long t0 = clock64();
-                umma::mbar_wait(&bar_halo_full[hslot], (cur.hs >> 1) & 1);
-                c_wait_halo += clock64() - t0;
-                ready_hs = cur.hs;
+            if (ready_hs != hs) {
+                TP(const long long t0 = clock64();)
+                umma::mbar_wait(&bar_halo_full[hslot], (hs >> 1) & 1);
+                TP(c_wait_halo += clock64() - t0;)
+                ready_hs = hs;
             }
             {
-                const long long t0 = clock64();
+                TP(const long long t0 = clock64();)
                 umma::mbar_wait(&bar_empty[s], ph ^ 1);       // the MMAs that read this A stage have retired
-                c_wait_stage += clock64() - t0;
+                TP(c_wait_stage += clock64() - t0;)
             }
+            TP(const bool tr = hp.prof == 2 && blockIdx.x == 0 && q == 0 && lane == 0 && it_seq < (uint32_t)kTraceKB;
+               if (tr) g_ttrace[it_seq][0] = clock64();)
             umma::tc_fence_after();
             const uint32_t a_col = tmem_base + ((uint32_t)(q * 32) << 16) + kTACol + s * kTAStageCols;
 
@@ -476,7 +506,7 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
             } else {
                 const Sample sm = make_sample(py, px, d.H, d.W);
                 w0 = sm.w[0] * m; w1 = sm.w[1] * m; w2 = sm.w[2] * m; w3 = sm.w[3] * m;
-                const float *x_b = p.x + (long)cur.b * d.HW * d.Cin + cur.grp * d.Cg + cur.cb * 32;
+                const float *x_b = p.x + (long)tl.b * d.HW * d.Cin + tl.grp * d.Cg + cb * 32;
                 g0 = reinterpret_cast<const float4 *>(x_b + (long)sm.i[0] * d.Cin);
                 g1 = reinterpret_cast<const float4 *>(x_b + (long)sm.i[1] * d.Cin);
                 g2 = reinterpret_cast<const float4 *>(x_b + (long)sm.i[2] * d.Cin);
@@ -540,20 +570,33 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                     combine_store(c8, qa);
                 }
             }
+            TP(if (tr) g_ttrace[it_seq][1] = clock64();)
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            TP(if (tr) g_ttrace[it_seq][2] = clock64();)
             umma::tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                umma::mbar_arrive(&bar_full_a[s]);
+                umma::mbar_arrive(&bar_full[s]);
                 // last K block of this group inside the halo slot: this warp has read everything it needs from it
-                if (nxt.hs != cur.hs) umma::mbar_arrive(&bar_halo_empty[hslot]);
+                if (last_in_slot) umma::mbar_arrive(&bar_halo_empty[hslot]);
             }
-            cur = nxt; gh = ngh; gw = ngw; gm = ngm; tapo = ntapo;
+            TP(if (tr) g_ttrace[it_seq][3] = clock64();)
+            gh = ngh; gw = ngw; gm = ngm;
+            {   // step to my next K block
+                tap += G; ph ^= 1u; TP(it_seq += G;)
+                if (tap >= T) {
+                    tap -= T; ++hs;
+                    if (++cb == n_cb) { cb = 0; tl.t += (int)gridDim.x; if (tl.t < total) decode_tile(tl); }
+                }
+                tapo = s_tapoff[tap];
+            }
         }
-        if (hp.prof && blockIdx.x == 0 && lane == 0 && q == 0)
-            printf("deform tmem producer group %d: total %lld cycles, wait halo %lld, wait stage %lld\n", grpi,
-                   clock64() - pt0, c_wait_halo, c_wait_stage);
-    } else if (warp == kTTmaWarp) {
+        TP(if (hp.prof == 1 && blockIdx.x == 0 && lane == 0 && q == 0)
+               printf("deform tmem producer group %d: total %lld cycles, wait halo %lld, wait stage %lld\n", grpi,
+                      clock64() - pt0, c_wait_halo, c_wait_stage);)
+    } else {
+      if (G == 3) umma::setmaxnreg_dec<40>();
+      if (warp == kTTmaWarp) {
         if (lane == 0) {
             // ================================ halo loader (tensor-map TMA) ========================
             uint32_t hs = 0;
@@ -585,22 +628,23 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                 for (int cb = 0; cb < n_cb; ++cb)
                     for (int tap = 0; tap < T; ++tap, ++itc) {
                         const int s = itc % S;
-                        umma::mbar_wait_sleep(&bar_empty[s], ((itc / S) & 1) ^ 1);
-                        umma::mbar_expect_tx(&bar_full_b[s], kBTile);
+                        umma::mbar_wait(&bar_empty[s], ((itc / S) & 1) ^ 1);
+                        umma::mbar_expect_tx(&bar_full[s], kBTile);
                         umma::bulk_g2s(smem + (size_t)s * kBTile, src + (size_t)(tap * n_cb + cb) * kBTile, kBTile,
-                                       &bar_full_b[s]);
+                                       &bar_full[s]);
                     }
             }
         }
-    } else if (warp == kTMmaWarp) {
-        if (lane == 0) {
+      } else if (warp == kTMmaWarp) {
+        {
             // ================================ MMA issuer (A from tensor memory) ====================
+            // The whole warp walks the loop (uniform control flow); one elected lane issues the tcgen05 instructions.
+            // Under `if (lane == 0)` the compiler wraps every UTCHMMA in an ELECT / BRA.U.ANY retry loop.
             constexpr uint32_t idesc = umma::make_idesc_tf32(kTM, BN);
             constexpr uint32_t idesc2 = umma::make_idesc_tf32(kTM, 2 * BN);
-            uint32_t itc = 0, ti = 0;
-            long long c_acc = 0, c_a = 0, c_b = 0, c_issue = 0, t0 = clock64();
-            const long long t_start = t0;
-#define TPROF(acc_) do { const long long t1 = clock64(); acc_ += t1 - t0; t0 = t1; } while (0)
+            uint32_t ti = 0;
+            TP(const bool l0 = lane == 0; uint32_t itc = 0; long long c_acc = 0, c_a = 0, c_issue = 0, t0 = clock64(); const long long t_start = t0;)
+#define TPROF(acc_) TP(do { const long long t1 = clock64(); acc_ += t1 - t0; t0 = t1; } while (0))
             const int nkb = n_cb * T;
             // TAIL: the 1x1 convolution of tile j: A = activated tile in TMEM (hi at the accumulator's columns
             // [0, BN), lo at [BN, 2 BN)), B = resident tail weights ([B_hi | B_lo] blocks of 32 input channels)
@@ -613,20 +657,29 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                 umma::mbar_wait_sleep(&bar_acc3_empty, (j & 1) ^ 1);
                 umma::tc_fence_after();
                 const uint32_t a0 = tmem_base + kTAccCol + a * 128, d3 = tmem_base + kTAcc3Col;
+                if (umma::elect_one()) {
 #pragma unroll 1
-                for (int kb = 0; kb < BN / 32; ++kb) {
-                    const uint32_t wb = umma::smem_u32(tailw) + (uint32_t)kb * 2u * (uint32_t)Ct * 128u;
-                    const uint64_t b_hi = umma::make_desc_sw128(wb), b_lo = umma::make_desc_sw128(wb + (uint32_t)Ct * 128u);
+                    for (int kb = 0; kb < BN / 32; ++kb) {
+                        const uint32_t wb = umma::smem_u32(tailw) + (uint32_t)kb * 2u * (uint32_t)Ct * 128u;
+                        const uint64_t b_hi = umma::make_desc_sw128(wb), b_lo = umma::make_desc_sw128(wb + (uint32_t)Ct * 128u);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t ah = a0 + kb * 32 + k * 8, al = a0 + BN + kb * 32 + k * 8;
-                        mma_tf32_ts(d3, ah, umma::desc_advance(b_hi, k * 32), idesc_t, (kb | k) != 0);
-                        mma_tf32_ts(d3, ah, umma::desc_advance(b_lo, k * 32), idesc_t, 1);
-                        mma_tf32_ts(d3, al, umma::desc_advance(b_hi, k * 32), idesc_t, 1);
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t ah = a0 + kb * 32 + k * 8, al = a0 + BN + kb * 32 + k * 8;
+                            mma_tf32_ts(d3, ah, umma::desc_advance(b_hi, k * 32), idesc_t, (kb | k) != 0);
+                            mma_tf32_ts(d3, ah, umma::desc_advance(b_lo, k * 32), idesc_t, 1);
+                            mma_tf32_ts(d3, al, umma::desc_advance(b_hi, k * 32), idesc_t, 1);
+                        }
                     }
+                    umma::tc_commit(&bar_acc3_full);
                 }
-                umma::tc_commit(&bar_acc3_full);
+                __syncwarp();
             };
+            // The loop below is the critical path of the whole CTA: one thread feeds the tensor pipe, and everything it
+            // executes between two K blocks is time the pipe drains (trace of the first version: 490 of 980 cycles per
+            // K block).  Hence ONE barrier per stage (A arrivals + weight bytes), a wrapping stage counter instead of
+            // % and /, no instrumentation unless built for it.
+            uint32_t stage = 0, phase = 0;
+            const uint32_t b_base = umma::smem_u32(smem);
             for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
                 const int a = ti & 1;
                 if (!TAIL) {    // TAIL: tile i-2's tail MMAs (which follow its activation pass) precede this tile in the pipe
@@ -635,32 +688,40 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                 }
                 TPROF(c_acc);
                 const uint32_t d_tmem = tmem_base + kTAccCol + a * 128;
-                for (int kb = 0; kb < nkb; ++kb, ++itc) {
-                    const int s = itc % S;
-                    const uint32_t ph = (itc / S) & 1;
-                    umma::mbar_wait_sleep(&bar_full_a[s], ph);
-                    TPROF(c_a);
-                    umma::mbar_wait_sleep(&bar_full_b[s], ph);
+#pragma unroll 1
+                for (int kb = 0; kb < nkb; ++kb) {
+                    TP(const bool tr = l0 && hp.prof == 2 && blockIdx.x == 0 && itc < (uint32_t)kTraceKB;)
+                    if (hp.spin) umma::mbar_wait(&bar_full[stage], phase); else umma::mbar_wait_sleep(&bar_full[stage], phase);
                     umma::tc_fence_after();
-                    TPROF(c_b);
-                    const uint32_t a_col = tmem_base + kTACol + s * kTAStageCols;
-                    const uint64_t b_hi = umma::make_desc_sw128(umma::smem_u32(smem + (size_t)s * kBTile));
+                    TPROF(c_a);
+                    TP(if (tr) g_ttrace[itc][4] = g_ttrace[itc][5] = t0;)
+                    const uint32_t a_col = tmem_base + kTACol + stage * kTAStageCols;
+                    const uint64_t b_hi = umma::make_desc_sw128(b_base + stage * (uint32_t)kBTile);
+                    if (umma::elect_one()) {
+                        mma_tf32_ts(d_tmem, a_col, b_hi, idesc2, kb != 0);
+                        mma_tf32_ts(d_tmem, a_col + 32, b_hi, idesc, 1);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        mma_tf32_ts(d_tmem, a_col + k * 8, umma::desc_advance(b_hi, k * 32), idesc2, (kb | k) != 0);
-                        mma_tf32_ts(d_tmem, a_col + 32 + k * 8, umma::desc_advance(b_hi, k * 32), idesc, 1);
+                        for (int k = 1; k < 4; ++k) {
+                            mma_tf32_ts(d_tmem, a_col + k * 8, umma::desc_advance(b_hi, k * 32), idesc2, 1);
+                            mma_tf32_ts(d_tmem, a_col + 32 + k * 8, umma::desc_advance(b_hi, k * 32), idesc, 1);
+                        }
+                        umma::tc_commit(&bar_empty[stage]);
                     }
-                    umma::tc_commit(&bar_empty[s]);
+                    __syncwarp();
                     TPROF(c_issue);
+                    TP(if (tr) g_ttrace[itc][6] = t0; ++itc;)
+                    if (++stage == S) { stage = 0; phase ^= 1; }
                 }
-                umma::tc_commit(&bar_acc_full[a]);
+                if (umma::elect_one()) umma::tc_commit(&bar_acc_full[a]);
+                __syncwarp();
                 if (TAIL && ti >= 1) issue_tail(ti - 1);
             }
             if (TAIL && ti >= 1) issue_tail(ti - 1);
-            if (hp.prof && blockIdx.x == 0)
-                printf("deform tmem MMA thread: %u tiles, total %lld cycles; wait acc %lld, wait A %lld, wait B %lld, issue %lld\n",
-                       ti, clock64() - t_start, c_acc, c_a, c_b, c_issue);
+            TP(if (l0 && hp.prof == 1 && blockIdx.x == 0)
+                   printf("deform tmem MMA thread: %u tiles, total %lld cycles; wait acc %lld, wait A+B %lld, issue %lld\n",
+                          ti, clock64() - t_start, c_acc, c_a, c_issue);)
         }
+    }
     }
     if (!triggered) pdl_trigger();
     umma::tc_fence_before();
@@ -669,6 +730,15 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
         umma::tc_fence_after();
         umma::tmem_dealloc<512>(tmem_base);
     }
+#ifdef AANET_TMEM_PROF
+    if (hp.prof == 2 && blockIdx.x == 0 && tid == 0) {
+        const long long z = g_ttrace[0][0];
+        printf("# K block: producer [stage free seen, stores issued, wait::st done, arrived]  MMA thread [A + B seen, same, issued + committed]\n");
+        for (int i = 0; i < kTraceKB && i < n_cb * T * 3; ++i)
+            printf("kb %2d: %6lld %6lld %6lld %6lld | %6lld %6lld %6lld\n", i, g_ttrace[i][0] - z, g_ttrace[i][1] - z,
+                   g_ttrace[i][2] - z, g_ttrace[i][3] - z, g_ttrace[i][4] - z, g_ttrace[i][5] - z, g_ttrace[i][6] - z);
+    }
+#endif
 }
 
 // --------------------------------------------------------------------------------------------- host side
@@ -738,7 +808,8 @@ static int tmem_plan(const ConvParams &src, int BN, int margin_req, int groups, 
     hp.margin_y = margin;
     hp.margin_x = src.offset ? mx : 0;
     hp.n_cb = d.Cg / 32;
-    { const char *ep = getenv("AANET_HALO_PROF"); hp.prof = ep && ep[0] == '1'; }
+    { const char *ep = getenv("AANET_HALO_PROF"); hp.prof = ep ? atoi(ep) : 0; }
+    { const char *ep = getenv("AANET_MMA_SPIN"); hp.spin = ep && ep[0] == '1'; }
     ConvParams &p = hp.p;
     p.n_tiles_n = ceil_div(d.Og, BN);
     p.K = d.K * d.Cg;
@@ -759,7 +830,7 @@ static int tmem_plan(const ConvParams &src, int BN, int margin_req, int groups, 
 int deform_tmem_launch(const ConvParams &src, int BN, cudaStream_t stream) {
     { const char *e = getenv("AANET_DEFORM_TMEM"); if (e && e[0] == '0') return AANET_ERR_UNSUPPORTED; }   // A/B switch
     const MdcnDims &d = src.d;
-    if (d.stride != 1 || d.Cg % 32 || d.Cd % 32 || !aligned16(src.x)) return AANET_ERR_UNSUPPORTED;
+    if (d.stride != 1 || d.Cg % 32 || d.Cd % 32 || d.Cin > 64 * 32 || !aligned16(src.x)) return AANET_ERR_UNSUPPORTED;
     if (src.out_nchw || src.residual || d.Og % 16 || (d.Cout & 3) || src.act == ACT_OFFSET_MASK) return AANET_ERR_UNSUPPORTED;
     if (BN != 32 && BN != 64) return AANET_ERR_UNSUPPORTED;
     const bool tail = src.tail_wpack != nullptr;

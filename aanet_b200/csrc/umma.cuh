@@ -126,6 +126,13 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar) {
                      smem_u32(bar))
                  : "memory");
 }
+// One lane of a converged warp (elect.sync); the branch it guards is how a warp-uniform role issues the
+// single-thread tcgen05 instructions without the compiler's per-instruction ELECT retry loops.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 // D[tmem] (+)= A[smem] * B[smem], TF32 inputs, FP32 accumulate; one thread issues for the CTA.
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                          uint32_t accumulate) {
