@@ -47,7 +47,7 @@ template <int G> struct TCfg {
     static constexpr int kThreads = ((kMmaWarp + 1 + 3) / 4) * 4 * 32;
     static_assert(kTACol + G * kTAStageCols <= 512, "TMEM: two accumulators + G operand stages");
 };
-constexpr int kTSmemBudget = 222 * 1024;
+constexpr int kTSmemBudget = 219 * 1024;   // dynamic; + 1 KB alignment slack + ~6.5 KB static (barriers, tables, geometry slots) <= 227 KB
 constexpr int kTAcc3Col = 448;           // TAIL: accumulator of the fused 1x1 convolution (<= 64 columns)
 
 struct DeformTmemParams {
@@ -108,6 +108,10 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
         : "memory");
 }
 
+__device__ __forceinline__ void cp_async4(float *dst_smem, const float *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(umma::smem_u32(dst_smem)), "l"(src) : "memory");
+}
+
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -139,6 +143,9 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
     __shared__ __align__(16) float s_aff[2][BN];
     __shared__ __align__(16) float s_aff3[2][64];
     __shared__ int2 s_tapoff[64];                             // per tap: (ki * dil - pad, kj * dil - pad)
+    // offset / mask values of every producer thread's NEXT K block, written by cp.async (no register is live across
+    // the K block for them: ptxas spilled the prefetched values right after the load, i.e. waited for the DRAM miss)
+    __shared__ float s_geom[3][DENSE ? 1 : 128 * G];
     __shared__ int s_dgk[64];                                 // per 32-channel block of the input: first offset channel of its deformable group
 
     const ConvParams &p = hp.p;
@@ -381,12 +388,13 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
             c.msk = (!DENSE && p.mask) ? p.mask + (long)item.b * p.mask_bs + pc * p.mask_ps : nullptr;
         };
         // s_dgk[grp * n_cb + cb] = first offset channel of the deformable group the 32-channel block belongs to
-        auto load_geom = [&](const Tile &c, int cb_, int tap_, float &gh_, float &gw_, float &gm_) {
+        const int ptid = DENSE ? 0 : pw * 32 + lane;
+        auto prefetch_geom = [&](const Tile &c, int cb_, int tap_) {
             if (DENSE) return;
             const long ch = s_dgk[c.grp * n_cb + cb_] + tap_;
-            gh_ = __ldg(c.off + (ch * 2) * p.off_cs);
-            gw_ = __ldg(c.off + (ch * 2 + 1) * p.off_cs);
-            gm_ = c.msk ? __ldg(c.msk + ch * p.mask_cs) : 1.f;
+            cp_async4(&s_geom[0][ptid], c.off + (ch * 2) * p.off_cs);
+            cp_async4(&s_geom[1][ptid], c.off + (ch * 2 + 1) * p.off_cs);
+            if (c.msk) cp_async4(&s_geom[2][ptid], c.msk + ch * p.mask_cs);
         };
 
         Tile tl;
@@ -395,27 +403,13 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
         uint32_t hs = 0u, ph = 0u;                            // halo slot sequence number; parity of my stage's use count
         TP(uint32_t it_seq = grpi;)
         const int s = grpi;                                   // S == G: group g always refills A stage g
-        float gh = 0.f, gw = 0.f, gm = 0.f;
-        if (tl.t < total) { decode_tile(tl); load_geom(tl, cb, tap, gh, gw, gm); }
+        if (tl.t < total) { decode_tile(tl); prefetch_geom(tl, cb, tap); }
         int2 tapo = s_tapoff[tap];
         uint32_t ready_hs = 0xffffffffu;
         while (tl.t < total) {
             // offsets / mask of my NEXT K block: each (tap, deformable group) plane is touched once per tile, so
             // these loads are DRAM misses and must be in flight while the current K block is produced
             const bool last_in_slot = tap + G >= T;           // my last tap inside this halo slot
-            float ngh = 0.f, ngw = 0.f, ngm = 0.f;
-            if (!DENSE) {
-                const int ntap = last_in_slot ? tap + G - T : tap + G;
-                const int ncb = last_in_slot ? cb + 1 : cb;
-                if (ncb < n_cb) {
-                    load_geom(tl, ncb, ntap, ngh, ngw, ngm);
-                } else if (tl.t + (int)gridDim.x < total) {   // first K block of my next tile
-                    Tile tn;
-                    tn.t = tl.t + (int)gridDim.x;
-                    decode_tile(tn);
-                    load_geom(tn, 0, ntap, ngh, ngw, ngm);
-                }
-            }
             const int hslot = hs & 1;
             const uint32_t halo = umma::smem_u32(halo0 + (size_t)hslot * hp.slot_bytes);
             if (DENSE) {
@@ -425,16 +419,18 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                     umma::mbar_wait(&bar_halo_full[hslot], (hs >> 1) & 1);
                     ready_hs = hs;
                 }
-                umma::mbar_wait(&bar_empty[s], ph ^ 1);
-                TP(const bool tr = hp.prof == 2 && blockIdx.x == 0 && q == 0 && lane == 0 && it_seq < (uint32_t)kTraceKB;
-                   if (tr) g_ttrace[it_seq][0] = clock64();)
-                umma::tc_fence_after();
+                // the line is read into registers BEFORE the stage is awaited: the stage (tensor memory) is then held
+                // only for the split + tcgen05.st, and the loads overlap the MMAs that still read it
                 const uint32_t a_col = tmem_base + ((uint32_t)(q * 32) << 16) + kTACol + s * kTAStageCols;
                 const int l0 = (tl.oh + tapo.x - tl.hy0) * hp.HWd + (tl.ow + tapo.y - tl.hx0);
                 const uint32_t P0 = (halo + (uint32_t)l0 * 128) | ((uint32_t)(l0 & 7) << 4);
                 float4 qd[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) qd[c] = lds128(P0 ^ (uint32_t)(c << 4));
+                umma::mbar_wait(&bar_empty[s], ph ^ 1);
+                TP(const bool tr = hp.prof == 2 && blockIdx.x == 0 && q == 0 && lane == 0 && it_seq < (uint32_t)kTraceKB;
+                   if (tr) g_ttrace[it_seq][0] = clock64();)
+                umma::tc_fence_after();
 #pragma unroll
                 for (int c8 = 0; c8 < 4; ++c8) {
                     float hi[8], lo[8];
@@ -466,11 +462,25 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                 continue;
             }
             // ---- my bilinear sample for this (tap, deformable group)
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            const float gh = s_geom[0][ptid], gw = s_geom[1][ptid], gm = tl.msk ? s_geom[2][ptid] : 1.f;
             const float py = (float)(tl.oh + tapo.x) + gh;
             const float px = (float)(tl.ow + tapo.y) + gw;
             const float fy = floorf(py), fx = floorf(px);
             const float lh = py - fy, lw = px - fx;
             const float m = tl.ok ? gm : 0.f;
+            {   // the values are in registers (consumed above): request my next K block's into the same slots
+                const int ntap = last_in_slot ? tap + G - T : tap + G;
+                const int ncb = last_in_slot ? cb + 1 : cb;
+                if (ncb < n_cb) {
+                    prefetch_geom(tl, ncb, ntap);
+                } else if (tl.t + (int)gridDim.x < total) {   // first K block of my next tile
+                    Tile tn;
+                    tn.t = tl.t + (int)gridDim.x;
+                    decode_tile(tn);
+                    prefetch_geom(tn, 0, ntap);
+                }
+            }
             const float ry = fy - (float)tl.hy0, rx = fx - (float)tl.hx0;      // top-left corner inside the halo?
             const bool inside = ry >= 0.f && rx >= 0.f && ry <= (float)(hp.HH - 2) && rx <= (float)(hp.HWd - 2);
             float w0 = (1.f - lh) * (1.f - lw) * m, w1 = (1.f - lh) * lw * m, w2 = lh * (1.f - lw) * m, w3 = lh * lw * m;
@@ -481,21 +491,15 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                 TP(c_wait_halo += clock64() - t0;)
                 ready_hs = hs;
             }
-            {
-                TP(const long long t0 = clock64();)
-                umma::mbar_wait(&bar_empty[s], ph ^ 1);       // the MMAs that read this A stage have retired
-                TP(c_wait_stage += clock64() - t0;)
-            }
-            TP(const bool tr = hp.prof == 2 && blockIdx.x == 0 && q == 0 && lane == 0 && it_seq < (uint32_t)kTraceKB;
-               if (tr) g_ttrace[it_seq][0] = clock64();)
-            umma::tc_fence_after();
             const uint32_t a_col = tmem_base + ((uint32_t)(q * 32) << 16) + kTACol + s * kTAStageCols;
 
             // Fast path: corner line L sits at L * 128 bytes of the slot; its 16-byte chunk c at (c ^ (L & 7)) * 16
             // (SWIZZLE_128B).  With P = line address | ((L & 7) << 4) the chunk address is P ^ (c << 4).
             // Slow path (footprint leaves the staged patch): global gather with the reference's validity rules.
-            // tcgen05.st is warp-collective (.sync.aligned): only the LOADS may diverge, the stores are issued by the
-            // whole warp after reconvergence.
+            // The 32 sampled values are produced into REGISTERS before the A stage is awaited: a group owns one stage,
+            // so whatever happens while it holds the stage is serial with the MMAs that consume it.  (First version:
+            // gather + combine + store all under the stage, ~1500 cycles per K block and group on top of the MMA
+            // turnaround.)  Now the stage is held for the hi / lo split and eight tcgen05.st only.
             uint32_t P0 = 0, P1 = 0, P2 = 0, P3 = 0;
             const float4 *g0 = nullptr, *g1 = nullptr, *g2 = nullptr, *g3 = nullptr;
             if (inside) {
@@ -512,27 +516,12 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                 g2 = reinterpret_cast<const float4 *>(x_b + (long)sm.i[2] * d.Cin);
                 g3 = reinterpret_cast<const float4 *>(x_b + (long)sm.i[3] * d.Cin);
             }
-            auto combine_store = [&](int c8, const float4 (&qa)[2][4]) {
-                float hi[8], lo[8];
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    const float v0 = w0 * qa[cc][0].x + w1 * qa[cc][1].x + w2 * qa[cc][2].x + w3 * qa[cc][3].x;
-                    const float v1 = w0 * qa[cc][0].y + w1 * qa[cc][1].y + w2 * qa[cc][2].y + w3 * qa[cc][3].y;
-                    const float v2 = w0 * qa[cc][0].z + w1 * qa[cc][1].z + w2 * qa[cc][2].z + w3 * qa[cc][3].z;
-                    const float v3 = w0 * qa[cc][0].w + w1 * qa[cc][1].w + w2 * qa[cc][2].w + w3 * qa[cc][3].w;
-                    umma::split_tf32(v0, hi[cc * 4 + 0], lo[cc * 4 + 0]); umma::split_tf32(v1, hi[cc * 4 + 1], lo[cc * 4 + 1]);
-                    umma::split_tf32(v2, hi[cc * 4 + 2], lo[cc * 4 + 2]); umma::split_tf32(v3, hi[cc * 4 + 3], lo[cc * 4 + 3]);
-                }
-                tmem_st8(a_col + c8 * 8, hi);
-                tmem_st8(a_col + 32 + c8 * 8, lo);
-            };
+            float v[32];
             if (__all_sync(0xffffffffu, inside)) {
                 // the whole warp reads from the staged patch (the common case): no branches in the loop; the four
-                // corner chunks of chunk c+1 are requested before chunk c is combined (LDS latency under load is
-                // ~100 cycles and only three producer warps share a scheduler)
+                // corner chunks of chunk c+1 are requested before chunk c is combined
                 float4 qb[2][4];
                 qb[0][0] = lds128(P0); qb[0][1] = lds128(P1); qb[0][2] = lds128(P2); qb[0][3] = lds128(P3);
-                float hi[8], lo[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const int b = c & 1;
@@ -541,34 +530,44 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                         qb[b ^ 1][0] = lds128(P0 ^ x); qb[b ^ 1][1] = lds128(P1 ^ x);
                         qb[b ^ 1][2] = lds128(P2 ^ x); qb[b ^ 1][3] = lds128(P3 ^ x);
                     }
-                    const float v0 = w0 * qb[b][0].x + w1 * qb[b][1].x + w2 * qb[b][2].x + w3 * qb[b][3].x;
-                    const float v1 = w0 * qb[b][0].y + w1 * qb[b][1].y + w2 * qb[b][2].y + w3 * qb[b][3].y;
-                    const float v2 = w0 * qb[b][0].z + w1 * qb[b][1].z + w2 * qb[b][2].z + w3 * qb[b][3].z;
-                    const float v3 = w0 * qb[b][0].w + w1 * qb[b][1].w + w2 * qb[b][2].w + w3 * qb[b][3].w;
-                    umma::split_tf32(v0, hi[b * 4 + 0], lo[b * 4 + 0]); umma::split_tf32(v1, hi[b * 4 + 1], lo[b * 4 + 1]);
-                    umma::split_tf32(v2, hi[b * 4 + 2], lo[b * 4 + 2]); umma::split_tf32(v3, hi[b * 4 + 3], lo[b * 4 + 3]);
-                    if (b) {
-                        tmem_st8(a_col + (c >> 1) * 8, hi);
-                        tmem_st8(a_col + 32 + (c >> 1) * 8, lo);
-                    }
+                    v[4 * c + 0] = w0 * qb[b][0].x + w1 * qb[b][1].x + w2 * qb[b][2].x + w3 * qb[b][3].x;
+                    v[4 * c + 1] = w0 * qb[b][0].y + w1 * qb[b][1].y + w2 * qb[b][2].y + w3 * qb[b][3].y;
+                    v[4 * c + 2] = w0 * qb[b][0].z + w1 * qb[b][1].z + w2 * qb[b][2].z + w3 * qb[b][3].z;
+                    v[4 * c + 3] = w0 * qb[b][0].w + w1 * qb[b][1].w + w2 * qb[b][2].w + w3 * qb[b][3].w;
                 }
             } else {
 #pragma unroll
-                for (int c8 = 0; c8 < 4; ++c8) {
-                    float4 qa[2][4];
-#pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) {
-                        const int c = c8 * 2 + cc;
-                        if (inside) {
-                            const uint32_t x = (uint32_t)(c << 4);
-                            qa[cc][0] = lds128(P0 ^ x); qa[cc][1] = lds128(P1 ^ x); qa[cc][2] = lds128(P2 ^ x); qa[cc][3] = lds128(P3 ^ x);
-                        } else {
-                            qa[cc][0] = __ldg(g0 + c); qa[cc][1] = __ldg(g1 + c); qa[cc][2] = __ldg(g2 + c); qa[cc][3] = __ldg(g3 + c);
-                        }
+                for (int c = 0; c < 8; ++c) {
+                    float4 q0, q1, q2, q3;
+                    if (inside) {
+                        const uint32_t x = (uint32_t)(c << 4);
+                        q0 = lds128(P0 ^ x); q1 = lds128(P1 ^ x); q2 = lds128(P2 ^ x); q3 = lds128(P3 ^ x);
+                    } else {
+                        q0 = __ldg(g0 + c); q1 = __ldg(g1 + c); q2 = __ldg(g2 + c); q3 = __ldg(g3 + c);
                     }
-                    __syncwarp();
-                    combine_store(c8, qa);
+                    v[4 * c + 0] = w0 * q0.x + w1 * q1.x + w2 * q2.x + w3 * q3.x;
+                    v[4 * c + 1] = w0 * q0.y + w1 * q1.y + w2 * q2.y + w3 * q3.y;
+                    v[4 * c + 2] = w0 * q0.z + w1 * q1.z + w2 * q2.z + w3 * q3.z;
+                    v[4 * c + 3] = w0 * q0.w + w1 * q1.w + w2 * q2.w + w3 * q3.w;
                 }
+                __syncwarp();
+            }
+            {
+                TP(const long long t0 = clock64();)
+                umma::mbar_wait(&bar_empty[s], ph ^ 1);       // the MMAs that read this A stage have retired
+                TP(c_wait_stage += clock64() - t0;)
+            }
+            TP(const bool tr = hp.prof == 2 && blockIdx.x == 0 && q == 0 && lane == 0 && it_seq < (uint32_t)kTraceKB;
+               if (tr) g_ttrace[it_seq][0] = clock64();)
+            umma::tc_fence_after();
+            // tcgen05.st is warp-collective (.sync.aligned): issued by the whole, reconverged warp
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+                float hi[8], lo[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) umma::split_tf32(v[c8 * 8 + i], hi[i], lo[i]);
+                tmem_st8(a_col + c8 * 8, hi);
+                tmem_st8(a_col + 32 + c8 * 8, lo);
             }
             TP(if (tr) g_ttrace[it_seq][1] = clock64();)
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -581,7 +580,6 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                 if (last_in_slot) umma::mbar_arrive(&bar_halo_empty[hslot]);
             }
             TP(if (tr) g_ttrace[it_seq][3] = clock64();)
-            gh = ngh; gw = ngw; gm = ngm;
             {   // step to my next K block
                 tap += G; ph ^= 1u; TP(it_seq += G;)
                 if (tap >= T) {
@@ -629,6 +627,7 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                     for (int tap = 0; tap < T; ++tap, ++itc) {
                         const int s = itc % S;
                         umma::mbar_wait(&bar_empty[s], ((itc / S) & 1) ^ 1);
+                        TP(if (hp.prof == 2 && blockIdx.x == 0 && itc < (uint32_t)kTraceKB) g_ttrace[itc][7] = clock64();)
                         umma::mbar_expect_tx(&bar_full[s], kBTile);
                         umma::bulk_g2s(smem + (size_t)s * kBTile, src + (size_t)(tap * n_cb + cb) * kBTile, kBTile,
                                        &bar_full[s]);
@@ -691,7 +690,9 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
 #pragma unroll 1
                 for (int kb = 0; kb < nkb; ++kb) {
                     TP(const bool tr = l0 && hp.prof == 2 && blockIdx.x == 0 && itc < (uint32_t)kTraceKB;)
-                    if (hp.spin) umma::mbar_wait(&bar_full[stage], phase); else umma::mbar_wait_sleep(&bar_full[stage], phase);
+                    if (hp.spin == 1) umma::mbar_wait(&bar_full[stage], phase);
+                    else if (hp.spin == 2) { if (lane == 0) umma::mbar_wait(&bar_full[stage], phase); __syncwarp(); }
+                    else umma::mbar_wait_sleep(&bar_full[stage], phase);
                     umma::tc_fence_after();
                     TPROF(c_a);
                     TP(if (tr) g_ttrace[itc][4] = g_ttrace[itc][5] = t0;)
@@ -733,10 +734,10 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
 #ifdef AANET_TMEM_PROF
     if (hp.prof == 2 && blockIdx.x == 0 && tid == 0) {
         const long long z = g_ttrace[0][0];
-        printf("# K block: producer [stage free seen, stores issued, wait::st done, arrived]  MMA thread [A + B seen, same, issued + committed]\n");
+        printf("# K block: producer [stage free seen, stores issued, wait::st done, arrived]  MMA thread [A + B seen, issued + committed]  weight copy issued\n");
         for (int i = 0; i < kTraceKB && i < n_cb * T * 3; ++i)
-            printf("kb %2d: %6lld %6lld %6lld %6lld | %6lld %6lld %6lld\n", i, g_ttrace[i][0] - z, g_ttrace[i][1] - z,
-                   g_ttrace[i][2] - z, g_ttrace[i][3] - z, g_ttrace[i][4] - z, g_ttrace[i][5] - z, g_ttrace[i][6] - z);
+            printf("kb %2d: %6lld %6lld %6lld %6lld | %6lld %6lld | %6lld\n", i, g_ttrace[i][0] - z, g_ttrace[i][1] - z,
+                   g_ttrace[i][2] - z, g_ttrace[i][3] - z, g_ttrace[i][4] - z, g_ttrace[i][6] - z, g_ttrace[i][7] - z);
     }
 #endif
 }
@@ -765,7 +766,7 @@ static int tmem_launch_tail(const DeformTmemParams &hp, const CUtensorMap &tm, i
 static int tmem_groups(bool dense) {
     const char *e = getenv(dense ? "AANET_DENSE_GROUPS" : "AANET_DEFORM_GROUPS");
     const int g = e ? atoi(e) : 3;      // measured: 4 groups buy nothing (dense) or cost spills (deformable)
-    return g == 4 ? 4 : 3;
+    return g == 4 && dense ? 4 : 3;     // (deformable: the geometry slots of a 4th group do not fit the static smem)
 }
 
 template <int BN, bool DENSE, bool LEAN>
@@ -809,7 +810,7 @@ static int tmem_plan(const ConvParams &src, int BN, int margin_req, int groups, 
     hp.margin_x = src.offset ? mx : 0;
     hp.n_cb = d.Cg / 32;
     { const char *ep = getenv("AANET_HALO_PROF"); hp.prof = ep ? atoi(ep) : 0; }
-    { const char *ep = getenv("AANET_MMA_SPIN"); hp.spin = ep && ep[0] == '1'; }
+    { const char *ep = getenv("AANET_MMA_SPIN"); hp.spin = ep ? atoi(ep) : 0; }
     ConvParams &p = hp.p;
     p.n_tiles_n = ceil_div(d.Og, BN);
     p.K = d.K * d.Cg;

@@ -54,3 +54,29 @@ if os.environ.get("TRACE", "1") == "1":
             torch.cuda.synchronize()
             print("^", name, "prof", prof, flush=True)
     os.environ["AANET_HALO_PROF"] = "0"
+
+# the dominant launch exactly as the pipeline issues it (network's own offsets, fused tail)
+if os.environ.get("PIPE", "1") == "1":
+    hp = bench.make_hot_path().to(dev)
+    (L, R), = bench.make_inputs(1, 1, dev)
+    with torch.no_grad():
+        hp(L, R)
+        q = bench.capture_dominant_launch(hp, L, R, (H, W))
+    if q is not None:
+        sets = []
+        for _ in range(n):
+            qq = dict(q, x=q["x"].clone(), offmask=q["offmask"].clone())
+            if q.get("tail"):
+                qq["tail"] = dict(q["tail"], residual=q["tail"]["residual"].clone())
+            sets.append(qq)
+        print("%-18s %6.1f us   (mean |offset| %.3f px, tail %s)" % (
+            "pipeline dcn", bench._timed(lambda i: ops.conv_batch([sets[i]], deform=True), n, 24, dev) * 1e3,
+            float(q["offmask"][:, :36].abs().mean()), bool(q.get("tail"))), flush=True)
+        q2 = dict(sets[0]); q2.pop("tail", None)
+        if os.environ.get("TRACE", "1") == "1":
+            for prof in ("1", "2"):
+                os.environ["AANET_HALO_PROF"] = prof
+                ops.conv_batch([sets[0]], deform=True)
+                torch.cuda.synchronize()
+                print("^ pipeline dcn prof", prof, flush=True)
+            os.environ["AANET_HALO_PROF"] = "0"
