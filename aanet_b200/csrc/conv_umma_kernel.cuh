@@ -171,7 +171,7 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
     using Cfg = EngineCfg<BN>;
     constexpr int S = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full_a[S], bar_full_b[S], bar_empty[S];
+    __shared__ __align__(8) uint64_t bar_full[S], bar_empty[S];   // full: the filling group's warps + the weight block's bytes
     __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2];
     __shared__ uint32_t s_tmem;
     // (tap, first channel) of every 16-byte chunk of every K block: c | ki << 16 | kj << 20 | tap << 24 | ok << 31
@@ -188,8 +188,10 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            umma::mbar_init(&bar_full_a[s], kProdWarps / kGroups);   // one arrival per warp of the filling group
-            umma::mbar_init(&bar_full_b[s], 1);            // expect_tx arrival + bulk-copy bytes
+            // one arrival per warp of the filling group + the weight loader's arrive.expect_tx (and its bytes): ONE wait
+            // per K block for the MMA warp, whose loop is the CTA's critical path (round 2: every barrier operation
+            // costs it ~100 cycles; the tensor pipe drains meanwhile)
+            umma::mbar_init(&bar_full[s], kProdWarps / kGroups + 1);
             umma::mbar_init(&bar_empty[s], 1);             // tcgen05.commit
         }
         for (int a = 0; a < 2; ++a) {
@@ -446,7 +448,7 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
             }
             umma::fence_proxy_async();
             __syncwarp();
-            if (lane == 0) umma::mbar_arrive(&bar_full_a[s]);
+            if (lane == 0) umma::mbar_arrive(&bar_full[s]);
         };
 
         while (t < total_tiles) {
@@ -607,18 +609,22 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
                     const uint32_t ph = (it / S) & 1;
                     umma::mbar_wait_sleep(&bar_empty[s], ph ^ 1);
                     PROF_ADD(5);                           // slot 5: loader waiting for a free stage
-                    umma::mbar_expect_tx(&bar_full_b[s], 2 * Cfg::kBTileBytes);
+                    umma::mbar_expect_tx(&bar_full[s], 2 * Cfg::kBTileBytes);
                     umma::bulk_g2s(smem + (size_t)s * Cfg::kStageBytes + 2 * kATileBytes,
-                                   src + (size_t)kb * 2 * Cfg::kBTileBytes, 2 * Cfg::kBTileBytes, &bar_full_b[s]);
+                                   src + (size_t)kb * 2 * Cfg::kBTileBytes, 2 * Cfg::kBTileBytes, &bar_full[s]);
                     PROF_ADD(6);
                 }
             }
             PROF_FLUSH(5); PROF_FLUSH(6);
-        } else if (warp == kMmaWarp && lane == 0) {
-        // ================================ MMA issuer (one thread) ================================
+        } else if (warp == kMmaWarp) {
+        // ================================ MMA issuer ==============================================
+        // The whole warp walks the loop (uniform control flow) and one elected lane issues the tcgen05 instructions:
+        // under `if (lane == 0)` the compiler wraps every UTCHMMA in an ELECT / BRA.U.ANY retry loop.  Wrapping stage
+        // counter instead of % and /, one barrier wait and one commit per K block.
             constexpr uint32_t idesc = umma::make_idesc_tf32(kUM, BN);
             constexpr uint32_t idesc2 = umma::make_idesc_tf32(kUM, 2 * BN);   // stacked [B_hi | B_lo]
-            uint32_t it = 0, ti = 0;
+            uint32_t ti = 0, stage = 0, phase = 0;
+            const uint32_t smem0 = umma::smem_u32(smem);
             PROF_DECL();
             PROF_T0();
             const long long prof_start = clock64();
@@ -629,33 +635,36 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
                 umma::tc_fence_after();
                 PROF_ADD(7);                               // slot 7: MMA waiting for a drained accumulator
                 const uint32_t d_tmem = tmem_base + a * Cfg::kAccStride;
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % S;
-                    const uint32_t ph = (it / S) & 1;
-                    umma::mbar_wait_sleep(&bar_full_a[s], ph);
-                    PROF_ADD(8);                           // slot 8: MMA waiting for A
-                    umma::mbar_wait_sleep(&bar_full_b[s], ph);
-                    PROF_ADD(9);                           // slot 9: MMA waiting for B
+#pragma unroll 1
+                for (int kb = 0; kb < nkb; ++kb) {
+                    umma::mbar_wait_sleep(&bar_full[stage], phase);
                     umma::tc_fence_after();
-                    const uint32_t a0 = umma::smem_u32(smem + (size_t)s * Cfg::kStageBytes);
-                    const uint64_t a_hi = umma::make_desc_sw128(a0), a_lo = umma::make_desc_sw128(a0 + kATileBytes);
-                    const uint64_t b_hi = umma::make_desc_sw128(a0 + 2 * kATileBytes);   // B_lo follows it in smem
+                    PROF_ADD(8);                           // slot 8: MMA waiting for A and B
+                    if (umma::elect_one()) {
+                        const uint32_t a0 = smem0 + stage * (uint32_t)Cfg::kStageBytes;
+                        const uint64_t a_hi = umma::make_desc_sw128(a0), a_lo = umma::make_desc_sw128(a0 + kATileBytes);
+                        const uint64_t b_hi = umma::make_desc_sw128(a0 + 2 * kATileBytes);   // B_lo follows it in smem
+                        umma::mma_tf32(d_tmem, a_hi, b_hi, idesc2, kb != 0);
+                        umma::mma_tf32(d_tmem, a_lo, b_hi, idesc, 1);
 #pragma unroll
-                    for (int k = 0; k < kUK / 8; ++k) {
-                        const uint32_t adv = k * 32;     // 8 tf32 = 32 bytes along K inside the swizzle row
-                        umma::mma_tf32(d_tmem, umma::desc_advance(a_hi, adv), umma::desc_advance(b_hi, adv), idesc2,
-                                       (kb | k) != 0);
-                        umma::mma_tf32(d_tmem, umma::desc_advance(a_lo, adv), umma::desc_advance(b_hi, adv), idesc, 1);
+                        for (int k = 1; k < kUK / 8; ++k) {
+                            const uint32_t adv = k * 32;     // 8 tf32 = 32 bytes along K inside the swizzle row
+                            umma::mma_tf32(d_tmem, umma::desc_advance(a_hi, adv), umma::desc_advance(b_hi, adv), idesc2, 1);
+                            umma::mma_tf32(d_tmem, umma::desc_advance(a_lo, adv), umma::desc_advance(b_hi, adv), idesc, 1);
+                        }
+                        umma::tc_commit(&bar_empty[stage]);      // frees this stage when the MMAs above retire
                     }
-                    umma::tc_commit(&bar_empty[s]);      // frees this stage when the MMAs above retire
+                    __syncwarp();
                     PROF_ADD(10);                          // slot 10: issuing MMAs
+                    if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
                 }
-                umma::tc_commit(&bar_acc_full[a]);       // accumulator of this tile complete
+                if (umma::elect_one()) umma::tc_commit(&bar_acc_full[a]);       // accumulator of this tile complete
+                __syncwarp();
             }
 #ifdef AANET_PROFILE
             prof_acc[0] = clock64() - prof_start; prof_acc[11] = ti;
 #endif
-            PROF_FLUSH(0); PROF_FLUSH(7); PROF_FLUSH(8); PROF_FLUSH(9); PROF_FLUSH(10); PROF_FLUSH(11);
+            if (lane == 0) { PROF_FLUSH(0); PROF_FLUSH(7); PROF_FLUSH(8); PROF_FLUSH(10); PROF_FLUSH(11); }
         }
     }
     if (!triggered) pdl_trigger();

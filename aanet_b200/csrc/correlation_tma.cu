@@ -182,35 +182,43 @@ corr_tma_kernel(const __grid_constant__ CorrTmaParams cp, const __grid_constant_
             }
         }
     } else if (warp == 9) {
-        if (lane == 0) {
+        {
             // ================================ MMA issuer ============================================
+            // warp-uniform loop, one elected lane issues (no per-instruction ELECT retry loops), wrapping stage counter
             constexpr uint32_t idesc = umma::make_idesc_tf32_major(kCtM, N, 1, 1);      // both operands MN-major
-            uint32_t it = 0, ti = 0;
+            uint32_t ti = 0, stage = 0, phase = 0;
+            const uint32_t smem0 = umma::smem_u32(smem);
             for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
                 const int a = ti & 1;
                 umma::mbar_wait_sleep(&bar_acc_empty[a], ((ti >> 1) & 1) ^ 1);
                 umma::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + a * 256;
-                for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const int s = it % S;
-                    umma::mbar_wait_sleep(&bar_lo[s], (it / S) & 1);         // raw landed and lo written
+#pragma unroll 1
+                for (int kb = 0; kb < KB; ++kb) {
+                    umma::mbar_wait_sleep(&bar_lo[stage], phase);         // raw landed and lo written
                     umma::tc_fence_after();
-                    const uint32_t raw = umma::smem_u32(smem + (size_t)s * kStageBytes);
-                    const uint32_t lo = raw + kRawBytes;
+                    if (umma::elect_one()) {
+                        const uint32_t raw = smem0 + stage * (uint32_t)kStageBytes;
+                        const uint32_t lo = raw + kRawBytes;
 #pragma unroll
-                    for (int k = 0; k < kCtKC / 8; ++k) {
-                        // one k step = 8 channels = 8 lines of 128 B = two 4-line swizzle atoms (512 B apart) of every 32-w box
-                        const uint64_t a_raw = umma::make_desc_mn_tf32(raw + k * 1024, kCtBox, 512);
-                        const uint64_t a_lo = umma::make_desc_mn_tf32(lo + k * 1024, kCtBox, 512);
-                        const uint64_t b_raw = umma::make_desc_mn_tf32(raw + 4 * kCtBox + k * 1024, kCtBox, 512);
-                        const uint64_t b_lo = umma::make_desc_mn_tf32(lo + 4 * kCtBox + k * 1024, kCtBox, 512);
-                        umma::mma_tf32(d_tmem, a_raw, b_raw, idesc, (kb | k) != 0);
-                        umma::mma_tf32(d_tmem, a_raw, b_lo, idesc, 1);
-                        umma::mma_tf32(d_tmem, a_lo, b_raw, idesc, 1);
+                        for (int k = 0; k < kCtKC / 8; ++k) {
+                            // one k step = 8 channels = 8 lines of 128 B = two 4-line swizzle atoms (512 B apart) of every 32-w box
+                            const uint64_t a_raw = umma::make_desc_mn_tf32(raw + k * 1024, kCtBox, 512);
+                            const uint64_t a_lo = umma::make_desc_mn_tf32(lo + k * 1024, kCtBox, 512);
+                            const uint64_t b_raw = umma::make_desc_mn_tf32(raw + 4 * kCtBox + k * 1024, kCtBox, 512);
+                            const uint64_t b_lo = umma::make_desc_mn_tf32(lo + 4 * kCtBox + k * 1024, kCtBox, 512);
+                            if (k == 0) umma::mma_tf32(d_tmem, a_raw, b_raw, idesc, kb != 0);
+                            else umma::mma_tf32(d_tmem, a_raw, b_raw, idesc, 1);
+                            umma::mma_tf32(d_tmem, a_raw, b_lo, idesc, 1);
+                            umma::mma_tf32(d_tmem, a_lo, b_raw, idesc, 1);
+                        }
+                        umma::tc_commit(&bar_empty[stage]);
                     }
-                    umma::tc_commit(&bar_empty[s]);
+                    __syncwarp();
+                    if (++stage == (uint32_t)S) { stage = 0; phase ^= 1; }
                 }
-                umma::tc_commit(&bar_acc_full[a]);
+                if (umma::elect_one()) umma::tc_commit(&bar_acc_full[a]);
+                __syncwarp();
             }
         }
     }

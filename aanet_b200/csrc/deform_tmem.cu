@@ -112,6 +112,46 @@ __device__ __forceinline__ void cp_async4(float *dst_smem, const float *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(umma::smem_u32(dst_smem)), "l"(src) : "memory");
 }
 
+// Packed fp32x2 arithmetic (sm_100: two FMAs per issued instruction; the producers are issue / latency bound).
+__device__ __forceinline__ uint64_t pack2(float x, float y) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t p, float &x, float &y) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(p));
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// w0 * q0 + w1 * q1 + w2 * q2 + w3 * q3 for the four channels of a 16-byte chunk, as two packed pairs; evaluated in
+// the scalar code's order (mul, then three fused multiply-adds), so the values are bit-identical to it
+__device__ __forceinline__ void combine4(const float4 &q0, const float4 &q1, const float4 &q2, const float4 &q3,
+                                         uint64_t W0, uint64_t W1, uint64_t W2, uint64_t W3, uint64_t &xy, uint64_t &zw) {
+    xy = mul2(W0, pack2(q0.x, q0.y)); zw = mul2(W0, pack2(q0.z, q0.w));
+    xy = fma2(W1, pack2(q1.x, q1.y), xy); zw = fma2(W1, pack2(q1.z, q1.w), zw);
+    xy = fma2(W2, pack2(q2.x, q2.y), xy); zw = fma2(W2, pack2(q2.z, q2.w), zw);
+    xy = fma2(W3, pack2(q3.x, q3.y), xy); zw = fma2(W3, pack2(q3.z, q3.w), zw);
+}
+// (hi, lo) tf32 split of a packed pair: hi = 13 low mantissa bits cleared, lo = x - hi (exact)
+__device__ __forceinline__ void split2(uint64_t v, float &h0, float &h1, float &l0, float &l1) {
+    const uint64_t h = v & 0xffffe000ffffe000ull;
+    unpack2(h, h0, h1);
+    unpack2(sub2(v, h), l0, l1);
+}
+
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -434,10 +474,10 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
 #pragma unroll
                 for (int c8 = 0; c8 < 4; ++c8) {
                     float hi[8], lo[8];
-                    umma::split_tf32(qd[2 * c8].x, hi[0], lo[0]); umma::split_tf32(qd[2 * c8].y, hi[1], lo[1]);
-                    umma::split_tf32(qd[2 * c8].z, hi[2], lo[2]); umma::split_tf32(qd[2 * c8].w, hi[3], lo[3]);
-                    umma::split_tf32(qd[2 * c8 + 1].x, hi[4], lo[4]); umma::split_tf32(qd[2 * c8 + 1].y, hi[5], lo[5]);
-                    umma::split_tf32(qd[2 * c8 + 1].z, hi[6], lo[6]); umma::split_tf32(qd[2 * c8 + 1].w, hi[7], lo[7]);
+                    split2(pack2(qd[2 * c8].x, qd[2 * c8].y), hi[0], hi[1], lo[0], lo[1]);
+                    split2(pack2(qd[2 * c8].z, qd[2 * c8].w), hi[2], hi[3], lo[2], lo[3]);
+                    split2(pack2(qd[2 * c8 + 1].x, qd[2 * c8 + 1].y), hi[4], hi[5], lo[4], lo[5]);
+                    split2(pack2(qd[2 * c8 + 1].z, qd[2 * c8 + 1].w), hi[6], hi[7], lo[6], lo[7]);
                     tmem_st8(a_col + c8 * 8, hi);
                     tmem_st8(a_col + 32 + c8 * 8, lo);
                 }
@@ -516,7 +556,8 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                 g2 = reinterpret_cast<const float4 *>(x_b + (long)sm.i[2] * d.Cin);
                 g3 = reinterpret_cast<const float4 *>(x_b + (long)sm.i[3] * d.Cin);
             }
-            float v[32];
+            uint64_t v[16];                                   // 32 sampled channels as packed pairs
+            const uint64_t W0 = pack2(w0, w0), W1 = pack2(w1, w1), W2 = pack2(w2, w2), W3 = pack2(w3, w3);
             if (__all_sync(0xffffffffu, inside)) {
                 // the whole warp reads from the staged patch (the common case): no branches in the loop; the four
                 // corner chunks of chunk c+1 are requested before chunk c is combined
@@ -530,10 +571,7 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                         qb[b ^ 1][0] = lds128(P0 ^ x); qb[b ^ 1][1] = lds128(P1 ^ x);
                         qb[b ^ 1][2] = lds128(P2 ^ x); qb[b ^ 1][3] = lds128(P3 ^ x);
                     }
-                    v[4 * c + 0] = w0 * qb[b][0].x + w1 * qb[b][1].x + w2 * qb[b][2].x + w3 * qb[b][3].x;
-                    v[4 * c + 1] = w0 * qb[b][0].y + w1 * qb[b][1].y + w2 * qb[b][2].y + w3 * qb[b][3].y;
-                    v[4 * c + 2] = w0 * qb[b][0].z + w1 * qb[b][1].z + w2 * qb[b][2].z + w3 * qb[b][3].z;
-                    v[4 * c + 3] = w0 * qb[b][0].w + w1 * qb[b][1].w + w2 * qb[b][2].w + w3 * qb[b][3].w;
+                    combine4(qb[b][0], qb[b][1], qb[b][2], qb[b][3], W0, W1, W2, W3, v[2 * c], v[2 * c + 1]);
                 }
             } else {
 #pragma unroll
@@ -545,10 +583,7 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                     } else {
                         q0 = __ldg(g0 + c); q1 = __ldg(g1 + c); q2 = __ldg(g2 + c); q3 = __ldg(g3 + c);
                     }
-                    v[4 * c + 0] = w0 * q0.x + w1 * q1.x + w2 * q2.x + w3 * q3.x;
-                    v[4 * c + 1] = w0 * q0.y + w1 * q1.y + w2 * q2.y + w3 * q3.y;
-                    v[4 * c + 2] = w0 * q0.z + w1 * q1.z + w2 * q2.z + w3 * q3.z;
-                    v[4 * c + 3] = w0 * q0.w + w1 * q1.w + w2 * q2.w + w3 * q3.w;
+                    combine4(q0, q1, q2, q3, W0, W1, W2, W3, v[2 * c], v[2 * c + 1]);
                 }
                 __syncwarp();
             }
@@ -565,7 +600,7 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
             for (int c8 = 0; c8 < 4; ++c8) {
                 float hi[8], lo[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) umma::split_tf32(v[c8 * 8 + i], hi[i], lo[i]);
+                for (int i = 0; i < 4; ++i) split2(v[c8 * 4 + i], hi[2 * i], hi[2 * i + 1], lo[2 * i], lo[2 * i + 1]);
                 tmem_st8(a_col + c8 * 8, hi);
                 tmem_st8(a_col + 32 + c8 * 8, lo);
             }
