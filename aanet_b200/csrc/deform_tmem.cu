@@ -55,6 +55,8 @@ struct DeformTmemParams {
     int HH, HWd, lines, slot_bytes;    // halo box (rows, pixels per row), lines = HH * HWd, bytes rounded to 1024
     int margin_y, margin_x, n_cb, prof;   // pixels of offset the halo covers above/below and left/right
     int spin;                             // experiment: the MMA thread polls its barriers instead of sleeping on them
+    int rot;                              // CTA b walks the taps of a channel block starting at tap b % T: the CTAs of a
+                                          // wave then fetch different weight blocks at any one time (L2 hot spot)
 };
 
 struct TItem { int grp, nt, b, ty, tx; };
@@ -167,7 +169,9 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 // write it back IN PLACE into the accumulator's TMEM columns, where it is the A operand of 3 x (Cm / 8) more MMAs
 // against the resident tail weights; a second epilogue pass adds bn3, the residual and the activation and stores.
 // MMA order D(0) D(1) C(0) D(2) C(1) ... so the activation pass of tile i runs under the main loop of tile i + 1.
-template <int BN, bool DENSE, bool LEAN, int G, bool TAIL = false>
+// SUB = deformable groups per 32-channel K block: 1 (>= 32 channels per deformable group) or 2 (16 channels per group,
+// the 1/6 scale of the pyramid: a thread then takes two bilinear samples per K block, one per half of its row).
+template <int BN, bool DENSE, bool LEAN, int G, bool TAIL = false, int SUB = 1>
 __global__ void __launch_bounds__(TCfg<G>::kThreads, 1)
 deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_constant__ CUtensorMap tm) {
     constexpr int S = G, kTGroups = G, kTProdWarps = TCfg<G>::kProdWarps, kTTmaWarp = TCfg<G>::kTmaWarp,
@@ -185,7 +189,7 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
     __shared__ int2 s_tapoff[64];                             // per tap: (ki * dil - pad, kj * dil - pad)
     // offset / mask values of every producer thread's NEXT K block, written by cp.async (no register is live across
     // the K block for them: ptxas spilled the prefetched values right after the load, i.e. waited for the DRAM miss)
-    __shared__ float s_geom[3][DENSE ? 1 : 128 * G];
+    __shared__ float s_geom[3 * SUB][DENSE ? 1 : 128 * G];
     __shared__ int s_dgk[64];                                 // per 32-channel block of the input: first offset channel of its deformable group
 
     const ConvParams &p = hp.p;
@@ -195,8 +199,10 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
     uint8_t *halo0 = smem + (size_t)S * kBTile;               // two halo slots behind the weight ring
     uint8_t *tailw = halo0 + 2 * (size_t)hp.slot_bytes;       // TAIL: resident packed weights of the 1x1 convolution
     if (tid < d.K) s_tapoff[tid] = make_int2((tid / d.kw) * d.dil - d.pad, (tid % d.kw) * d.dil - d.pad);
-    if (!DENSE && tid < 64) s_dgk[tid] = ((tid * 32) / max(d.Cd, 1)) * d.K;
+    if (!DENSE && tid < 64) s_dgk[tid] = ((tid * 32) / max(d.Cd, 1)) * d.K;     // SUB == 2: the block's second group follows at + K
     const int T = d.K, n_cb = hp.n_cb, total = p.total_tiles;
+    const int rot = hp.rot ? (int)(blockIdx.x % (unsigned)T) : 0;
+    auto phys = [&](int t_) { const int q_ = t_ + rot; return q_ >= T ? q_ - T : q_; };   // walk position -> tap
 
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
@@ -422,7 +428,7 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
             c.oh = item.ty * kTTH + (row >> 4); c.ow = item.tx * kTTW + (row & 15);
             c.ok = c.oh < d.Ho && c.ow < d.Wo;
             c.oh = min(c.oh, d.Ho - 1); c.ow = min(c.ow, d.Wo - 1);
-            c.hy0 = item.ty * kTTH - d.pad - hp.margin_y; c.hx0 = item.tx * kTTW - d.pad - hp.margin_x;
+            c.hy0 = item.ty * kTTH * d.stride - d.pad - hp.margin_y; c.hx0 = item.tx * kTTW * d.stride - d.pad - hp.margin_x;
             const long pc = (long)c.oh * d.Wo + c.ow;
             c.off = DENSE ? nullptr : p.offset + (long)item.b * p.off_bs + pc * p.off_ps;
             c.msk = (!DENSE && p.mask) ? p.mask + (long)item.b * p.mask_bs + pc * p.mask_ps : nullptr;
@@ -431,10 +437,13 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
         const int ptid = DENSE ? 0 : pw * 32 + lane;
         auto prefetch_geom = [&](const Tile &c, int cb_, int tap_) {
             if (DENSE) return;
-            const long ch = s_dgk[c.grp * n_cb + cb_] + tap_;
-            cp_async4(&s_geom[0][ptid], c.off + (ch * 2) * p.off_cs);
-            cp_async4(&s_geom[1][ptid], c.off + (ch * 2 + 1) * p.off_cs);
-            if (c.msk) cp_async4(&s_geom[2][ptid], c.msk + ch * p.mask_cs);
+#pragma unroll
+            for (int u = 0; u < SUB; ++u) {
+                const long ch = s_dgk[c.grp * n_cb + cb_] + u * d.K + phys(tap_);
+                cp_async4(&s_geom[3 * u + 0][ptid], c.off + (ch * 2) * p.off_cs);
+                cp_async4(&s_geom[3 * u + 1][ptid], c.off + (ch * 2 + 1) * p.off_cs);
+                if (c.msk) cp_async4(&s_geom[3 * u + 2][ptid], c.msk + ch * p.mask_cs);
+            }
         };
 
         Tile tl;
@@ -444,7 +453,7 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
         TP(uint32_t it_seq = grpi;)
         const int s = grpi;                                   // S == G: group g always refills A stage g
         if (tl.t < total) { decode_tile(tl); prefetch_geom(tl, cb, tap); }
-        int2 tapo = s_tapoff[tap];
+        int2 tapo = s_tapoff[phys(tap)];
         uint32_t ready_hs = 0xffffffffu;
         while (tl.t < total) {
             // offsets / mask of my NEXT K block: each (tap, deformable group) plane is touched once per tile, so
@@ -462,7 +471,9 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                 // the line is read into registers BEFORE the stage is awaited: the stage (tensor memory) is then held
                 // only for the split + tcgen05.st, and the loads overlap the MMAs that still read it
                 const uint32_t a_col = tmem_base + ((uint32_t)(q * 32) << 16) + kTACol + s * kTAStageCols;
-                const int l0 = (tl.oh + tapo.x - tl.hy0) * hp.HWd + (tl.ow + tapo.y - tl.hx0);
+                // (stride 2, the CSA down-sampling convs: neighbouring pixels read every other line -> 2-way bank
+                // conflicts on 8 loads per K block, irrelevant next to the L2 round trips of the gather engine)
+                const int l0 = (tl.oh * d.stride + tapo.x - tl.hy0) * hp.HWd + (tl.ow * d.stride + tapo.y - tl.hx0);
                 const uint32_t P0 = (halo + (uint32_t)l0 * 128) | ((uint32_t)(l0 & 7) << 4);
                 float4 qd[8];
 #pragma unroll
@@ -497,18 +508,25 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                         tap -= T; ++hs;
                         if (++cb == n_cb) { cb = 0; tl.t += (int)gridDim.x; if (tl.t < total) decode_tile(tl); }
                     }
-                    tapo = s_tapoff[tap];
+                    tapo = s_tapoff[phys(tap)];
                 }
                 continue;
             }
-            // ---- my bilinear sample for this (tap, deformable group)
+            // ---- my bilinear sample(s) for this (tap, deformable group [pair])
             asm volatile("cp.async.wait_all;" ::: "memory");
-            const float gh = s_geom[0][ptid], gw = s_geom[1][ptid], gm = tl.msk ? s_geom[2][ptid] : 1.f;
-            const float py = (float)(tl.oh + tapo.x) + gh;
-            const float px = (float)(tl.ow + tapo.y) + gw;
-            const float fy = floorf(py), fx = floorf(px);
-            const float lh = py - fy, lw = px - fx;
-            const float m = tl.ok ? gm : 0.f;
+            float py[SUB], px[SUB], lh[SUB], lw[SUB], m[SUB], ry[SUB], rx[SUB];
+            bool inside = true;
+#pragma unroll
+            for (int u = 0; u < SUB; ++u) {
+                const float gh = s_geom[3 * u][ptid], gw = s_geom[3 * u + 1][ptid], gm = tl.msk ? s_geom[3 * u + 2][ptid] : 1.f;
+                py[u] = (float)(tl.oh + tapo.x) + gh;
+                px[u] = (float)(tl.ow + tapo.y) + gw;
+                const float fy = floorf(py[u]), fx = floorf(px[u]);
+                lh[u] = py[u] - fy; lw[u] = px[u] - fx;
+                m[u] = tl.ok ? gm : 0.f;
+                ry[u] = fy - (float)tl.hy0; rx[u] = fx - (float)tl.hx0;         // top-left corner inside the halo?
+                inside = inside && ry[u] >= 0.f && rx[u] >= 0.f && ry[u] <= (float)(hp.HH - 2) && rx[u] <= (float)(hp.HWd - 2);
+            }
             {   // the values are in registers (consumed above): request my next K block's into the same slots
                 const int ntap = last_in_slot ? tap + G - T : tap + G;
                 const int ncb = last_in_slot ? cb + 1 : cb;
@@ -521,10 +539,6 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                     prefetch_geom(tn, 0, ntap);
                 }
             }
-            const float ry = fy - (float)tl.hy0, rx = fx - (float)tl.hx0;      // top-left corner inside the halo?
-            const bool inside = ry >= 0.f && rx >= 0.f && ry <= (float)(hp.HH - 2) && rx <= (float)(hp.HWd - 2);
-            float w0 = (1.f - lh) * (1.f - lw) * m, w1 = (1.f - lh) * lw * m, w2 = lh * (1.f - lw) * m, w3 = lh * lw * m;
-
             if (ready_hs != hs) {
                 TP(const long long t0 = clock64();)
                 umma::mbar_wait(&bar_halo_full[hslot], (hs >> 1) & 1);
@@ -535,57 +549,74 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
 
             // Fast path: corner line L sits at L * 128 bytes of the slot; its 16-byte chunk c at (c ^ (L & 7)) * 16
             // (SWIZZLE_128B).  With P = line address | ((L & 7) << 4) the chunk address is P ^ (c << 4).
-            // Slow path (footprint leaves the staged patch): global gather with the reference's validity rules.
+            // Slow path (a footprint leaves the staged patch): global gather with the reference's validity rules.
             // The 32 sampled values are produced into REGISTERS before the A stage is awaited: a group owns one stage,
             // so whatever happens while it holds the stage is serial with the MMAs that consume it.  (First version:
             // gather + combine + store all under the stage, ~1500 cycles per K block and group on top of the MMA
             // turnaround.)  Now the stage is held for the hi / lo split and eight tcgen05.st only.
-            uint32_t P0 = 0, P1 = 0, P2 = 0, P3 = 0;
-            const float4 *g0 = nullptr, *g1 = nullptr, *g2 = nullptr, *g3 = nullptr;
-            if (inside) {
-                const int l0 = (int)ry * hp.HWd + (int)rx, l2 = l0 + hp.HWd;
-                const uint32_t p0 = halo + (uint32_t)l0 * 128, p2 = halo + (uint32_t)l2 * 128;
-                P0 = p0 | ((uint32_t)(l0 & 7) << 4); P1 = (p0 + 128) | ((uint32_t)((l0 + 1) & 7) << 4);
-                P2 = p2 | ((uint32_t)(l2 & 7) << 4); P3 = (p2 + 128) | ((uint32_t)((l2 + 1) & 7) << 4);
-            } else {
-                const Sample sm = make_sample(py, px, d.H, d.W);
-                w0 = sm.w[0] * m; w1 = sm.w[1] * m; w2 = sm.w[2] * m; w3 = sm.w[3] * m;
-                const float *x_b = p.x + (long)tl.b * d.HW * d.Cin + tl.grp * d.Cg + cb * 32;
-                g0 = reinterpret_cast<const float4 *>(x_b + (long)sm.i[0] * d.Cin);
-                g1 = reinterpret_cast<const float4 *>(x_b + (long)sm.i[1] * d.Cin);
-                g2 = reinterpret_cast<const float4 *>(x_b + (long)sm.i[2] * d.Cin);
-                g3 = reinterpret_cast<const float4 *>(x_b + (long)sm.i[3] * d.Cin);
-            }
+            const bool all_inside = __all_sync(0xffffffffu, inside);
             uint64_t v[16];                                   // 32 sampled channels as packed pairs
-            const uint64_t W0 = pack2(w0, w0), W1 = pack2(w1, w1), W2 = pack2(w2, w2), W3 = pack2(w3, w3);
-            if (__all_sync(0xffffffffu, inside)) {
-                // the whole warp reads from the staged patch (the common case): no branches in the loop; the four
-                // corner chunks of chunk c+1 are requested before chunk c is combined
-                float4 qb[2][4];
-                qb[0][0] = lds128(P0); qb[0][1] = lds128(P1); qb[0][2] = lds128(P2); qb[0][3] = lds128(P3);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int b = c & 1;
-                    if (c + 1 < 8) {
-                        const uint32_t x = (uint32_t)((c + 1) << 4);
-                        qb[b ^ 1][0] = lds128(P0 ^ x); qb[b ^ 1][1] = lds128(P1 ^ x);
-                        qb[b ^ 1][2] = lds128(P2 ^ x); qb[b ^ 1][3] = lds128(P3 ^ x);
+            for (int u = 0; u < SUB; ++u) {
+                constexpr int CH = 8 / SUB;                   // 16-byte chunks of the K row that sample u covers
+                const int c0 = u * CH;
+                float w0 = (1.f - lh[u]) * (1.f - lw[u]) * m[u], w1 = (1.f - lh[u]) * lw[u] * m[u];
+                float w2 = lh[u] * (1.f - lw[u]) * m[u], w3 = lh[u] * lw[u] * m[u];
+                if (all_inside) {
+                    // the whole warp reads from the staged patch (the common case): no branches in the loop; the four
+                    // corner chunks of chunk c+1 are requested before chunk c is combined
+                    const int l0 = (int)ry[u] * hp.HWd + (int)rx[u], l2 = l0 + hp.HWd;
+                    const uint32_t p0 = halo + (uint32_t)l0 * 128, p2 = halo + (uint32_t)l2 * 128;
+                    const uint32_t P0 = p0 | ((uint32_t)(l0 & 7) << 4), P1 = (p0 + 128) | ((uint32_t)((l0 + 1) & 7) << 4);
+                    const uint32_t P2 = p2 | ((uint32_t)(l2 & 7) << 4), P3 = (p2 + 128) | ((uint32_t)((l2 + 1) & 7) << 4);
+                    const uint64_t W0 = pack2(w0, w0), W1 = pack2(w1, w1), W2 = pack2(w2, w2), W3 = pack2(w3, w3);
+                    float4 qb[2][4];
+                    {
+                        const uint32_t x = (uint32_t)(c0 << 4);
+                        qb[0][0] = lds128(P0 ^ x); qb[0][1] = lds128(P1 ^ x); qb[0][2] = lds128(P2 ^ x); qb[0][3] = lds128(P3 ^ x);
                     }
-                    combine4(qb[b][0], qb[b][1], qb[b][2], qb[b][3], W0, W1, W2, W3, v[2 * c], v[2 * c + 1]);
-                }
-            } else {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float4 q0, q1, q2, q3;
+                    for (int c = 0; c < CH; ++c) {
+                        const int b = c & 1;
+                        if (c + 1 < CH) {
+                            const uint32_t x = (uint32_t)((c0 + c + 1) << 4);
+                            qb[b ^ 1][0] = lds128(P0 ^ x); qb[b ^ 1][1] = lds128(P1 ^ x);
+                            qb[b ^ 1][2] = lds128(P2 ^ x); qb[b ^ 1][3] = lds128(P3 ^ x);
+                        }
+                        combine4(qb[b][0], qb[b][1], qb[b][2], qb[b][3], W0, W1, W2, W3, v[2 * (c0 + c)], v[2 * (c0 + c) + 1]);
+                    }
+                } else {
+                    // per-lane: from the patch where my footprints are inside it, else from global memory
+                    uint32_t P0 = 0, P1 = 0, P2 = 0, P3 = 0;
+                    const float4 *g0 = nullptr, *g1 = nullptr, *g2 = nullptr, *g3 = nullptr;
                     if (inside) {
-                        const uint32_t x = (uint32_t)(c << 4);
-                        q0 = lds128(P0 ^ x); q1 = lds128(P1 ^ x); q2 = lds128(P2 ^ x); q3 = lds128(P3 ^ x);
+                        const int l0 = (int)ry[u] * hp.HWd + (int)rx[u], l2 = l0 + hp.HWd;
+                        const uint32_t p0 = halo + (uint32_t)l0 * 128, p2 = halo + (uint32_t)l2 * 128;
+                        P0 = p0 | ((uint32_t)(l0 & 7) << 4); P1 = (p0 + 128) | ((uint32_t)((l0 + 1) & 7) << 4);
+                        P2 = p2 | ((uint32_t)(l2 & 7) << 4); P3 = (p2 + 128) | ((uint32_t)((l2 + 1) & 7) << 4);
                     } else {
-                        q0 = __ldg(g0 + c); q1 = __ldg(g1 + c); q2 = __ldg(g2 + c); q3 = __ldg(g3 + c);
+                        const Sample sm = make_sample(py[u], px[u], d.H, d.W);
+                        w0 = sm.w[0] * m[u]; w1 = sm.w[1] * m[u]; w2 = sm.w[2] * m[u]; w3 = sm.w[3] * m[u];
+                        const float *x_b = p.x + (long)tl.b * d.HW * d.Cin + tl.grp * d.Cg + cb * 32;
+                        g0 = reinterpret_cast<const float4 *>(x_b + (long)sm.i[0] * d.Cin);
+                        g1 = reinterpret_cast<const float4 *>(x_b + (long)sm.i[1] * d.Cin);
+                        g2 = reinterpret_cast<const float4 *>(x_b + (long)sm.i[2] * d.Cin);
+                        g3 = reinterpret_cast<const float4 *>(x_b + (long)sm.i[3] * d.Cin);
                     }
-                    combine4(q0, q1, q2, q3, W0, W1, W2, W3, v[2 * c], v[2 * c + 1]);
+                    const uint64_t W0 = pack2(w0, w0), W1 = pack2(w1, w1), W2 = pack2(w2, w2), W3 = pack2(w3, w3);
+#pragma unroll
+                    for (int c = c0; c < c0 + CH; ++c) {
+                        float4 q0, q1, q2, q3;
+                        if (inside) {
+                            const uint32_t x = (uint32_t)(c << 4);
+                            q0 = lds128(P0 ^ x); q1 = lds128(P1 ^ x); q2 = lds128(P2 ^ x); q3 = lds128(P3 ^ x);
+                        } else {
+                            q0 = __ldg(g0 + c); q1 = __ldg(g1 + c); q2 = __ldg(g2 + c); q3 = __ldg(g3 + c);
+                        }
+                        combine4(q0, q1, q2, q3, W0, W1, W2, W3, v[2 * c], v[2 * c + 1]);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
             {
                 TP(const long long t0 = clock64();)
@@ -621,7 +652,7 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                     tap -= T; ++hs;
                     if (++cb == n_cb) { cb = 0; tl.t += (int)gridDim.x; if (tl.t < total) decode_tile(tl); }
                 }
-                tapo = s_tapoff[tap];
+                tapo = s_tapoff[phys(tap)];
             }
         }
         TP(if (hp.prof == 1 && blockIdx.x == 0 && lane == 0 && q == 0)
@@ -640,7 +671,8 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                     umma::mbar_wait_sleep(&bar_halo_empty[s], ((hs >> 1) & 1) ^ 1);
                     umma::mbar_expect_tx(&bar_halo_full[s], hp.lines * 128);
                     umma::tma_load_4d(halo0 + (size_t)s * hp.slot_bytes, &tm, it.grp * d.Cg + cb * 32,
-                                      it.tx * kTTW - d.pad - hp.margin_x, it.ty * kTTH - d.pad - hp.margin_y, it.b,
+                                      it.tx * kTTW * d.stride - d.pad - hp.margin_x,
+                                      it.ty * kTTH * d.stride - d.pad - hp.margin_y, it.b,
                                       &bar_halo_full[s]);
                 }
             }
@@ -664,7 +696,7 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                         umma::mbar_wait(&bar_empty[s], ((itc / S) & 1) ^ 1);
                         TP(if (hp.prof == 2 && blockIdx.x == 0 && itc < (uint32_t)kTraceKB) g_ttrace[itc][7] = clock64();)
                         umma::mbar_expect_tx(&bar_full[s], kBTile);
-                        umma::bulk_g2s(smem + (size_t)s * kBTile, src + (size_t)(tap * n_cb + cb) * kBTile, kBTile,
+                        umma::bulk_g2s(smem + (size_t)s * kBTile, src + (size_t)(phys(tap) * n_cb + cb) * kBTile, kBTile,
                                        &bar_full[s]);
                     }
             }
@@ -782,13 +814,13 @@ static size_t tail_bytes(const ConvParams &p, int BN) {
     return p.tail_wpack ? (size_t)(BN / 32) * 2 * p.tail_cout * 128 : 0;
 }
 
-template <int BN, bool DENSE, bool LEAN, int G, bool TAIL = false>
+template <int BN, bool DENSE, bool LEAN, int G, bool TAIL = false, int SUB = 1>
 static int tmem_launch_g(const DeformTmemParams &hp, const CUtensorMap &tm, cudaStream_t stream) {
     const size_t smem = (size_t)G * 2 * BN * 32 * 4 + 2 * (size_t)hp.slot_bytes + tail_bytes(hp.p, BN) + 1024;
-    cudaFuncSetAttribute(deform_tmem_kernel<BN, DENSE, LEAN, G, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(deform_tmem_kernel<BN, DENSE, LEAN, G, TAIL, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int rounds = ceil_div(hp.p.total_tiles, num_sms());
     const int grid = ceil_div(hp.p.total_tiles, rounds);
-    return launch_pdl(deform_tmem_kernel<BN, DENSE, LEAN, G, TAIL>, dim3(grid), dim3(TCfg<G>::kThreads), smem, stream, hp, tm);
+    return launch_pdl(deform_tmem_kernel<BN, DENSE, LEAN, G, TAIL, SUB>, dim3(grid), dim3(TCfg<G>::kThreads), smem, stream, hp, tm);
 }
 
 // the fused-tail instantiations exist for the 3-group pipeline, lean epilogue, BN = 32 / 64
@@ -822,7 +854,7 @@ static bool tmem_tail_ok(const ConvParams &p, int BN) {
 static int tmem_plan(const ConvParams &src, int BN, int margin_req, int groups, DeformTmemParams &hp, CUtensorMap &tm) {
     const MdcnDims &d = src.d;
     hp.p = src;
-    const size_t ring = (size_t)groups * 2 * BN * 32 * 4 + tail_bytes(src, BN);
+    const size_t ring = (size_t)groups * 2 * BN * 32 * 4 + tail_bytes(src, BN) + (src.offset && d.Cd == 16 ? 5 * 1024 : 0);   // (+ the second sample's geometry slots, static)
     // Halo plan.  The pitch (pixels per halo row) is rounded up to a multiple of 8 lines: a sample whose row index
     // jitters by one (sub-pixel offsets of either sign) then keeps its swizzle key (line & 7), so neighbouring
     // threads keep hitting different bank groups; the extra columns widen the horizontal margin.  Vertical margin:
@@ -832,9 +864,9 @@ static int tmem_plan(const ConvParams &src, int BN, int margin_req, int groups, 
     const int corner = margin_req > 0 || src.offset ? 1 : 0;      // +1 line / column for the bilinear corner
     int margin = margin_req, mx = 0;
     for (; margin >= 0; --margin) {
-        hp.HH = kTTH + (d.kh - 1) * d.dil + 2 * margin + corner;
-        const int wmin = kTTW + (d.kw - 1) * d.dil + 2 * margin + corner;
-        hp.HWd = pitch8 ? (wmin + 7) / 8 * 8 : wmin;
+        hp.HH = (kTTH - 1) * d.stride + 1 + (d.kh - 1) * d.dil + 2 * margin + corner;
+        const int wmin = (kTTW - 1) * d.stride + 1 + (d.kw - 1) * d.dil + 2 * margin + corner;
+        hp.HWd = (pitch8 && d.stride == 1) ? (wmin + 7) / 8 * 8 : wmin;
         mx = margin + (hp.HWd - wmin) / 2;
         hp.lines = hp.HH * hp.HWd;
         hp.slot_bytes = (hp.lines * 128 + 1023) & ~1023;
@@ -846,6 +878,7 @@ static int tmem_plan(const ConvParams &src, int BN, int margin_req, int groups, 
     hp.n_cb = d.Cg / 32;
     { const char *ep = getenv("AANET_HALO_PROF"); hp.prof = ep ? atoi(ep) : 0; }
     { const char *ep = getenv("AANET_MMA_SPIN"); hp.spin = ep ? atoi(ep) : 0; }
+    { const char *ep = getenv("AANET_TMEM_ROT"); hp.rot = ep ? atoi(ep) : 0; }
     ConvParams &p = hp.p;
     p.n_tiles_n = ceil_div(d.Og, BN);
     p.K = d.K * d.Cg;
@@ -866,7 +899,10 @@ static int tmem_plan(const ConvParams &src, int BN, int margin_req, int groups, 
 int deform_tmem_launch(const ConvParams &src, int BN, cudaStream_t stream) {
     { const char *e = getenv("AANET_DEFORM_TMEM"); if (e && e[0] == '0') return AANET_ERR_UNSUPPORTED; }   // A/B switch
     const MdcnDims &d = src.d;
-    if (d.stride != 1 || d.Cg % 32 || d.Cd % 32 || d.Cin > 64 * 32 || !aligned16(src.x)) return AANET_ERR_UNSUPPORTED;
+    // deformable groups of >= 32 channels (one bilinear sample per 32-channel K block) or of exactly 16 (two samples)
+    const bool sub2 = d.Cd == 16;
+    if (d.stride != 1 || d.Cg % 32 || (d.Cd % 32 && !sub2) || d.Cin > 64 * 32 || !aligned16(src.x)) return AANET_ERR_UNSUPPORTED;
+    if (sub2 && BN != 32) return AANET_ERR_UNSUPPORTED;      // instantiated for the 32-channel scale
     if (src.out_nchw || src.residual || d.Og % 16 || (d.Cout & 3) || src.act == ACT_OFFSET_MASK) return AANET_ERR_UNSUPPORTED;
     if (BN != 32 && BN != 64) return AANET_ERR_UNSUPPORTED;
     const bool tail = src.tail_wpack != nullptr;
@@ -878,6 +914,8 @@ int deform_tmem_launch(const ConvParams &src, int BN, cudaStream_t stream) {
     CUtensorMap tm;
     const int rc = tmem_plan(src, BN, em ? atoi(em) : 4, groups, hp, tm);
     if (rc) return rc;
+    if (sub2) return tail ? tmem_launch_g<32, false, true, 3, true, 2>(hp, tm, stream)
+                          : tmem_launch_g<32, false, true, 3, false, 2>(hp, tm, stream);
     if (tail) return tmem_launch_tail<false>(hp, tm, BN, stream);
     return BN == 64 ? tmem_launch_inst<64, false, true>(hp, tm, groups, stream)
                     : tmem_launch_inst<32, false, true>(hp, tm, groups, stream);
@@ -888,7 +926,7 @@ int deform_tmem_launch(const ConvParams &src, int BN, cudaStream_t stream) {
 int dense_tmem_launch(const ConvParams &src, int BN, cudaStream_t stream) {
     { const char *e = getenv("AANET_DENSE_TMEM"); if (e && e[0] == '0') return AANET_ERR_UNSUPPORTED; }   // A/B switch
     const MdcnDims &d = src.d;
-    if (d.stride != 1 || d.Cg % 32 || !aligned16(src.x) || src.residual || src.offset) return AANET_ERR_UNSUPPORTED;
+    if ((d.stride != 1 && d.stride != 2) || d.Cg % 32 || !aligned16(src.x) || src.residual || src.offset) return AANET_ERR_UNSUPPORTED;
     if (BN != 32 && BN != 48 && BN != 64) return AANET_ERR_UNSUPPORTED;
     const bool tail = src.tail_wpack != nullptr;
     if (tail && !tmem_tail_ok(src, BN)) return AANET_ERR_UNSUPPORTED;
@@ -914,7 +952,7 @@ bool tmem_tail_supported(const ConvParams &src, bool deform) {
     if (!src.tail_wpack || !tmem_tail_ok(src, BN) || d.stride != 1 || d.Cg % 32 || d.K < 3 || !aligned16(src.x)) return false;
     { const char *e = getenv(deform ? "AANET_DEFORM_TMEM" : "AANET_DENSE_TMEM"); if (e && e[0] == '0') return false; }
     { const char *e = getenv("AANET_TAIL_FUSION"); if (e && e[0] == '0') return false; }
-    if (deform && d.Cd % 32) return false;
+    if (deform && d.Cd % 32 && !(d.Cd == 16 && BN == 32)) return false;
     DeformTmemParams hp;
     CUtensorMap tm;
     return tmem_plan(src, BN, deform ? 4 : 0, 3, hp, tm) == AANET_OK;

@@ -68,6 +68,17 @@ class _Conv:
                     scale=self.scale, shift=self.shift, act=self.act, slope=self.slope, stride=self.stride,
                     pad=self.pad, dil=self.dil, groups=self.groups)
 
+    def tmem_eligible(self):
+        """Multi-tap convolution over 32-channel blocks (stride 1 or 2): runs as its own launch of the TMEM-A kernel
+        (TMA-staged input patch, no per-K-block L2 round trips) instead of inside a multi-problem engine launch."""
+        return (self.kh * self.kw >= 3 and self.stride in (1, 2) and (self._w.shape[1] % 32) == 0
+                and os.environ.get("AANET_DENSE_TMEM", "1") != "0" and os.environ.get("AANET_EXCHANGE_TMEM", "1") != "0")
+
+    def single(self, x):
+        """Own launch; the N tile is at least 32 wide so that narrow outputs (the 16-channel scale) qualify too."""
+        bn = max(32, ops.natural_bn(self.Cout // self.groups))
+        return ops.conv_batch([self.problem(x, bn)], bn=bn)[0]
+
     def as_tail(self, residual, act=None):
         """This (1x1) convolution as the fused tail of the preceding one (ops.conv_batch "tail")."""
         return dict(wpack=self.wpack, Cout=self.Cout, scale=self.scale, shift=self.shift, residual=residual,
@@ -256,12 +267,17 @@ class FusedAggregation:
                     for j, chain in enumerate(row):
                         t = xs[j]
                         for conv in chain[:-1]:
-                            t = conv(t)
+                            t = conv.single(t) if conv.tmem_eligible() else conv(t)
+                        if chain and chain[-1].tmem_eligible():
+                            t = chain[-1].single(t)                 # strided 3x3: TMEM-A kernel, own launch
+                            chain = ()
                         terms.append(t)
                         if chain:
                             last.append((chain[-1], t))
                             where.append(j)
-                    if len(last) > 1 and BATCH_EXCHANGE:
+                    if len(last) == 1:
+                        terms[where[0]] = last[0][0](last[0][1])
+                    elif len(last) > 1 and BATCH_EXCHANGE:
                         bn = max(ops.natural_bn(c.Cout // c.groups) for c, _ in last)
                         outs = ops.conv_batch([c.problem(t, bn) for c, t in last], bn=bn)
                         for j, o in zip(where, outs):

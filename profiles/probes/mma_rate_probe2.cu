@@ -5,6 +5,7 @@
 //   C  cta_group::1, M = 64
 //   D  cta_group::2, M = 256 (128 rows per CTA), B split N/2 per CTA, issued by the leader CTA
 //   E  cta_group::2, M = 128 (64 rows per CTA)
+//   F  as A, issued by an elected lane of a warp-uniform loop
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o mma_rate_probe2 mma_rate_probe2.cu
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -19,6 +20,46 @@ __device__ __forceinline__ void mma_tf32_2cta(uint32_t d_tmem, uint64_t a_desc, 
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+
+// mode F: the issuing warp runs warp-uniform code and one ELECTED lane issues (elect.sync): no compiler-generated
+// ELECT / BRA.U.ANY retry loop around every UTCHMMA (what `if (tid == 0)` produces)
+__global__ void __launch_bounds__(128)
+rate_elect_kernel(long long *out, int M, int N, int iters) {
+    extern __shared__ uint8_t raw[];
+    uint8_t *smem = raw + ((1024 - (smem_u32(raw) & 1023)) & 1023);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<float *>(smem)[i] = 0.f;
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc<512>(&s_tmem);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) {
+        const uint64_t a = make_desc_sw128(smem_u32(smem)), b = make_desc_sw128(smem_u32(smem + 16384));
+        const uint32_t id = make_idesc_tf32(M, N);
+        const uint32_t d = s_tmem;
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_tf32(d, a + 2 * k, b + 2 * k, id, 1);
+            }
+            __syncwarp();
+        }
+        const long long t1 = clock64();
+        if (elect_one()) tc_commit(&bar);
+        __syncwarp();
+        mbar_wait(&bar, 0);
+        const long long t2 = clock64();
+        if (blockIdx.x == 0 && tid == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc<512>(s_tmem); }
 }
 
 // modes A (n_issuers = 1), B (n_issuers = 2), C (M = 64)
@@ -125,6 +166,11 @@ int main() {
             rate1_kernel<<<grid, 128, 52 * 1024>>>(d_out, 128, N, iters, 1);
             if (report("A cta_group::1, one issuer", 128, N, grid, d_out, iters, 128)) return 1;
         }
+    cudaFuncSetAttribute(rate_elect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 52 * 1024);
+    for (int N : {32, 64, 96, 128, 192, 256}) {
+        rate_elect_kernel<<<148, 128, 52 * 1024>>>(d_out, 128, N, iters);
+        if (report("F cta_group::1, elected lane of a uniform warp", 128, N, 148, d_out, iters, 128)) return 1;
+    }
     for (int N : {32, 64, 128, 256}) {
         rate1_kernel<<<148, 128, 52 * 1024>>>(d_out, 128, N, iters, 2);
         // two issuers: per-issuer cycles per MMA; the SM retires 2 MMAs in that time

@@ -60,6 +60,9 @@ def _run(ops, x, off, msk, w, sc, sh, dg, dil, om_nchw=True):
     (1, 128, 128, 12, 20, 2, 2, 2.0, None),    # Cd = 64 (two channel blocks per deformable group), two N tiles
     (1, 128, 64, 9, 33, 4, 1, 1.5, None),      # dg = 4, dilation 1
     (1, 32, 32, 16, 16, 1, 2, 30.0, None),     # one channel block; offsets mostly outside the image
+    (1, 32, 32, 24, 52, 2, 2, 1.0, None),      # 16 channels per deformable group (the 1/6 scale): two samples per K block
+    (2, 32, 32, 19, 37, 2, 2, 6.0, 2),         # same, ragged tiles, batch 2, many samples outside the staged patch
+    (1, 64, 32, 12, 20, 4, 1, 1.5, None),      # 16-channel groups over two channel blocks
 ])
 @pytest.mark.parametrize("rows", [4, 8])
 def test_deform_halo_matches_oracle(deform_halo, cfg, rows):

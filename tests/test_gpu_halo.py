@@ -109,6 +109,8 @@ def test_halo_fused_executor_matches_gather_engine(halo):
     (2, 32, 33, 47, False, 1),        # one channel block, ragged tiles, batch 2, one K block in the tail
     (1, 64, 24, 52, True, 2),
     (3, 64, 9, 20, False, 1),         # more tiles than two per CTA never happens here; several images
+    (1, 32, 24, 52, True, 2),         # the 1/6 scale: 16 channels per deformable group (two samples per K block) + tail
+    (2, 32, 17, 35, True, 2),
 ])
 def test_fused_tail_matches_two_launches(cfg):
     """conv2 (+ bn2 + ReLU) with the bottleneck's trailing conv3 + bn3 + identity + ReLU fused into the same launch
@@ -145,3 +147,40 @@ def test_fused_tail_matches_two_launches(cfg):
         r3 = torch.relu(torch.nn.functional.conv2d(r2, w3.double()) * s3.view(1, -1, 1, 1) + h3.view(1, -1, 1, 1)
                         + idn.permute(0, 3, 1, 2))
         assert rel_err(npy(fused.permute(0, 3, 1, 2)), npy(r3)) < 1e-5
+
+
+@pytest.mark.parametrize("cfg", [
+    # B, Cin, Cout, H, W  -- the CSA down-sampling convolutions (aggregation.py:353-371): 3x3, stride 2, pad 1
+    (1, 64, 64, 128, 416),
+    (1, 64, 32, 24, 52),
+    (2, 64, 16, 17, 35),              # 16 outputs inside a 32-wide N tile, odd sizes, batch 2
+    (1, 32, 16, 64, 208),
+])
+def test_strided_dense_tmem_vs_float64(cfg):
+    """Stride-2 3x3 convolutions through the TMEM-A kernel (TMA-staged patch of every other pixel) against float64 torch
+    and against the round-1 gather engine."""
+    import aanet_b200.ops as ops
+    B, Ci, Co, H, W = cfg
+    torch.manual_seed(31)
+    x = torch.randn(B, H, W, Ci, device="cuda")
+    w = torch.randn(Co, Ci, 3, 3, device="cuda") / (Ci * 9) ** 0.5
+    sc, sh = torch.rand(Co, device="cuda") + 0.5, torch.randn(Co, device="cuda")
+    bn = max(32, ops.natural_bn(Co))
+    q = dict(x=x, wpack=ops.pack_conv_weight(w, 1, bn), Cout=Co, kh=3, kw=3, scale=sc, shift=sh, act=ops.ACT_LEAKY,
+             slope=0.2, stride=2, pad=1, dil=1, groups=1)
+    got = ops.conv_batch([q], bn=bn)[0]
+    ref = torch.nn.functional.leaky_relu(
+        torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), None, 2, 1) * sc.view(1, -1, 1, 1)
+        + sh.view(1, -1, 1, 1), 0.2)
+    assert got.shape == (B, ref.shape[2], ref.shape[3], Co)
+    assert rel_err(npy(got.permute(0, 3, 1, 2)), npy(ref)) < 1e-5
+    old = os.environ.get("AANET_DENSE_TMEM")
+    os.environ["AANET_DENSE_TMEM"] = "0"
+    try:
+        eng = ops.conv_batch([q], bn=bn)[0]
+    finally:
+        if old is None:
+            os.environ.pop("AANET_DENSE_TMEM", None)
+        else:
+            os.environ["AANET_DENSE_TMEM"] = old
+    assert rel_err(npy(got), npy(eng)) < 1e-5
