@@ -5,11 +5,19 @@ half of every aggregation module.  The 1/6 and 1/12 scale kernels are launch/lat
 on 148 SMs), so running them next to the 1/3 scale work hides them almost completely.  The pattern is
 plain event fork/join, which CUDA-graph capture records as parallel branches.
 
+Every kernel of this path takes a whole SM per CTA (150-220 KB of shared memory, tensor memory), so a stage costs about
+(sum over its kernels of CTAs x duration) / 148 however the branches are ordered: measured in round 2, enqueueing the
+1/3-scale branch first (AANET_FORK_ORDER=1), giving it a high-priority stream, or running the CSA stage as a task graph
+with one stream per exchange chain all came out 1-6 % SLOWER than this plain fork (1185 pairs/s) -- the hardware block
+scheduler packs the small kernels into the gaps of the large ones best when they are enqueued first.
+
 Allocator note: a tensor produced on a side stream and consumed on the main stream (or vice versa) must not
 be freed while the other stream may still touch it.  Callers keep every intermediate alive until the join
 that ends their forward (see FusedAggregation.__call__), so blocks only return to their pools after all
 consumers were enqueued and the next fork orders any reuse behind them.
 """
+import os
+
 import torch
 
 _side = {}
@@ -23,6 +31,10 @@ def side_streams(device, n):
     return pool[:n]
 
 
+# A/B switch: AANET_FORK_ORDER=1 enqueues the main branch before the side branches
+LEAD_FIRST = os.environ.get("AANET_FORK_ORDER", "0") == "1"
+
+
 def fork_join(device, fns):
     """Run fns[0] on the current stream and fns[1:] on side streams; returns their results in order."""
     if len(fns) == 1:
@@ -32,6 +44,8 @@ def fork_join(device, fns):
     start.record(main)
     results = [None] * len(fns)
     done = []
+    if LEAD_FIRST:
+        results[0] = fns[0]()
     for i, (fn, s) in enumerate(zip(fns[1:], side_streams(device, len(fns) - 1)), 1):
         s.wait_event(start)
         with torch.cuda.stream(s):
@@ -39,7 +53,8 @@ def fork_join(device, fns):
             e = torch.cuda.Event()
             e.record(s)
         done.append(e)
-    results[0] = fns[0]()
+    if not LEAD_FIRST:
+        results[0] = fns[0]()
     for e in done:
         main.wait_event(e)
     return results
