@@ -55,6 +55,8 @@ struct DeformTmemParams {
     int HH, HWd, lines, slot_bytes;    // halo box (rows, pixels per row), lines = HH * HWd, bytes rounded to 1024
     int margin_y, margin_x, n_cb, prof;   // pixels of offset the halo covers above/below and left/right
     int spin;                             // experiment: the MMA thread polls its barriers instead of sleeping on them
+    int sb;                               // weight-ring slots: S (a block is requested when its stage frees) or 2 S
+                                          // (requested one use of the stage earlier: hides the ~1500-cycle L2 fetch)
     int rot;                              // CTA b walks the taps of a channel block starting at tap b % T: the CTAs of a
                                           // wave then fetch different weight blocks at any one time (L2 hot spot)
 };
@@ -180,7 +182,11 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
     static_assert(2 * BN <= 128, "accumulator stride is 128 columns");
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_halo_full[2], bar_halo_empty[2];
-    __shared__ __align__(8) uint64_t bar_full[S], bar_empty[S];   // full: 4 producer warps + the weight block's bytes
+    // Stage barriers come in PAIRS, indexed [stage + S * (use & 1)]: use p of stage s signals full / empty barrier
+    // (s, p & 1), whose own phase is p >> 1.  One wait and one commit per K block for the MMA warp as before, but a
+    // barrier now completes every second use of its stage, so the weight loader can wait for use p - 2 (and request
+    // the block of use p into the spare slot (s, p & 1) of a 2 S-deep ring) without the parity test aliasing.
+    __shared__ __align__(8) uint64_t bar_full[2 * S], bar_empty[2 * S];   // full: 4 producer warps + the weight block's bytes
     __shared__ __align__(8) uint64_t bar_acc_full[2], bar_acc_empty[2];
     __shared__ __align__(8) uint64_t bar_y2[2], bar_acc3_full, bar_acc3_empty, bar_tailw;      // TAIL only
     __shared__ uint32_t s_tmem;
@@ -196,7 +202,7 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
     const MdcnDims &d = p.d;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t *smem = smem_raw + ((1024 - (umma::smem_u32(smem_raw) & 1023)) & 1023);
-    uint8_t *halo0 = smem + (size_t)S * kBTile;               // two halo slots behind the weight ring
+    uint8_t *halo0 = smem + (size_t)hp.sb * kBTile;           // two halo slots behind the weight ring
     uint8_t *tailw = halo0 + 2 * (size_t)hp.slot_bytes;       // TAIL: resident packed weights of the 1x1 convolution
     if (tid < d.K) s_tapoff[tid] = make_int2((tid / d.kw) * d.dil - d.pad, (tid % d.kw) * d.dil - d.pad);
     if (!DENSE && tid < 64) s_dgk[tid] = ((tid * 32) / max(d.Cd, 1)) * d.K;     // SUB == 2: the block's second group follows at + K
@@ -209,7 +215,7 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
             umma::mbar_init(&bar_halo_full[s], 1);            // expect_tx + TMA bytes
             umma::mbar_init(&bar_halo_empty[s], kTProdWarps); // every producer warp, after its last tap of the slot
         }
-        for (int s = 0; s < S; ++s) {
+        for (int s = 0; s < 2 * S; ++s) {
             umma::mbar_init(&bar_full[s], 5);                 // the four warps of the filling group + arrive.expect_tx of
                                                               // the weight loader: ONE wait per K block for the MMA thread
                                                               // (a barrier operation costs that thread ~100 cycles; a
@@ -449,7 +455,8 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
         Tile tl;
         tl.t = (int)blockIdx.x;
         int cb = 0, tap = grpi;                               // G <= T: the group's first K block is tap grpi of block 0
-        uint32_t hs = 0u, ph = 0u;                            // halo slot sequence number; parity of my stage's use count
+        uint32_t hs = 0u;                                     // halo slot sequence number
+        int use = 0;                                          // how often my stage has been filled (see bar_full / bar_empty)
         TP(uint32_t it_seq = grpi;)
         const int s = grpi;                                   // S == G: group g always refills A stage g
         if (tl.t < total) { decode_tile(tl); prefetch_geom(tl, cb, tap); }
@@ -478,7 +485,8 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                 float4 qd[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) qd[c] = lds128(P0 ^ (uint32_t)(c << 4));
-                umma::mbar_wait(&bar_empty[s], ph ^ 1);
+                // previous use of my stage retired?  (use - 1 = -1 on the first pass: parity 1 of a fresh barrier passes)
+                umma::mbar_wait(&bar_empty[s + S * ((use - 1) & 1)], (uint32_t)(((use - 1) >> 1) & 1));
                 TP(const bool tr = hp.prof == 2 && blockIdx.x == 0 && q == 0 && lane == 0 && it_seq < (uint32_t)kTraceKB;
                    if (tr) g_ttrace[it_seq][0] = clock64();)
                 umma::tc_fence_after();
@@ -498,12 +506,12 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                 umma::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    umma::mbar_arrive(&bar_full[s]);
+                    umma::mbar_arrive(&bar_full[s + S * (use & 1)]);
                     if (last_in_slot) umma::mbar_arrive(&bar_halo_empty[hslot]);
                 }
                 TP(if (tr) g_ttrace[it_seq][3] = clock64();)
                 {   // step to my next K block
-                    tap += G; ph ^= 1u; TP(it_seq += G;)
+                    tap += G; ++use; TP(it_seq += G;)
                     if (tap >= T) {
                         tap -= T; ++hs;
                         if (++cb == n_cb) { cb = 0; tl.t += (int)gridDim.x; if (tl.t < total) decode_tile(tl); }
@@ -620,7 +628,8 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
             }
             {
                 TP(const long long t0 = clock64();)
-                umma::mbar_wait(&bar_empty[s], ph ^ 1);       // the MMAs that read this A stage have retired
+                // the MMAs that read this A stage (its previous use) have retired
+                umma::mbar_wait(&bar_empty[s + S * ((use - 1) & 1)], (uint32_t)(((use - 1) >> 1) & 1));
                 TP(c_wait_stage += clock64() - t0;)
             }
             TP(const bool tr = hp.prof == 2 && blockIdx.x == 0 && q == 0 && lane == 0 && it_seq < (uint32_t)kTraceKB;
@@ -641,13 +650,13 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
             umma::tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                umma::mbar_arrive(&bar_full[s]);
+                umma::mbar_arrive(&bar_full[s + S * (use & 1)]);
                 // last K block of this group inside the halo slot: this warp has read everything it needs from it
                 if (last_in_slot) umma::mbar_arrive(&bar_halo_empty[hslot]);
             }
             TP(if (tr) g_ttrace[it_seq][3] = clock64();)
             {   // step to my next K block
-                tap += G; ph ^= 1u; TP(it_seq += G;)
+                tap += G; ++use; TP(it_seq += G;)
                 if (tap >= T) {
                     tap -= T; ++hs;
                     if (++cb == n_cb) { cb = 0; tl.t += (int)gridDim.x; if (tl.t < total) decode_tile(tl); }
@@ -685,19 +694,25 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                 umma::mbar_expect_tx(&bar_tailw, bytes);
                 umma::bulk_g2s(tailw, p.tail_wpack, bytes, &bar_tailw);
             }
-            uint32_t itc = 0;
+            // K block i = use u of stage s.  Its weight block goes to ring slot (s, u & 1) [2 S slots] or s [S slots]
+            // and may be requested as soon as the slot's previous block has been consumed: use u - 2 / u - 1.
+            TP(uint32_t itc = 0;)
+            int s = 0, use = 0;
+            const bool deep = hp.sb == 2 * S;
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 const TItem it = t_item(p, t);
                 const uint8_t *src = reinterpret_cast<const uint8_t *>(p.wpack) +
                                      (size_t)(it.grp * p.n_tiles_n + it.nt) * p.KB * kBTile;
                 for (int cb = 0; cb < n_cb; ++cb)
-                    for (int tap = 0; tap < T; ++tap, ++itc) {
-                        const int s = itc % S;
-                        umma::mbar_wait(&bar_empty[s], ((itc / S) & 1) ^ 1);
-                        TP(if (hp.prof == 2 && blockIdx.x == 0 && itc < (uint32_t)kTraceKB) g_ttrace[itc][7] = clock64();)
-                        umma::mbar_expect_tx(&bar_full[s], kBTile);
-                        umma::bulk_g2s(smem + (size_t)s * kBTile, src + (size_t)(phys(tap) * n_cb + cb) * kBTile, kBTile,
-                                       &bar_full[s]);
+                    for (int tap = 0; tap < T; ++tap) {
+                        const int prev = deep ? use - 2 : use - 1;           // negative: parity 1 of a fresh barrier passes
+                        umma::mbar_wait(&bar_empty[s + S * (prev & 1)], (uint32_t)((prev >> 1) & 1));
+                        TP(if (hp.prof == 2 && blockIdx.x == 0 && itc < (uint32_t)kTraceKB) g_ttrace[itc][7] = clock64(); ++itc;)
+                        uint64_t *full = &bar_full[s + S * (use & 1)];
+                        uint8_t *dst = smem + (size_t)(deep ? s + S * (use & 1) : s) * kBTile;
+                        umma::mbar_expect_tx(full, kBTile);
+                        umma::bulk_g2s(dst, src + (size_t)(phys(tap) * n_cb + cb) * kBTile, kBTile, full);
+                        if (++s == S) { s = 0; ++use; }
                     }
             }
         }
@@ -744,8 +759,9 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
             // executes between two K blocks is time the pipe drains (trace of the first version: 490 of 980 cycles per
             // K block).  Hence ONE barrier per stage (A arrivals + weight bytes), a wrapping stage counter instead of
             // % and /, no instrumentation unless built for it.
-            uint32_t stage = 0, phase = 0;
+            uint32_t stage = 0, use = 0;                      // K block = use `use` of stage `stage` (see bar_full)
             const uint32_t b_base = umma::smem_u32(smem);
+            const uint32_t deep = hp.sb == 2 * S ? (uint32_t)S : 0u;
             for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
                 const int a = ti & 1;
                 if (!TAIL) {    // TAIL: tile i-2's tail MMAs (which follow its activation pass) precede this tile in the pipe
@@ -757,14 +773,14 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
 #pragma unroll 1
                 for (int kb = 0; kb < nkb; ++kb) {
                     TP(const bool tr = l0 && hp.prof == 2 && blockIdx.x == 0 && itc < (uint32_t)kTraceKB;)
-                    if (hp.spin == 1) umma::mbar_wait(&bar_full[stage], phase);
-                    else if (hp.spin == 2) { if (lane == 0) umma::mbar_wait(&bar_full[stage], phase); __syncwarp(); }
-                    else umma::mbar_wait_sleep(&bar_full[stage], phase);
+                    const uint32_t bi = stage + S * (use & 1u);       // barrier pair member of this use
+                    if (hp.spin == 1) umma::mbar_wait(&bar_full[bi], (use >> 1) & 1u);
+                    else umma::mbar_wait_sleep(&bar_full[bi], (use >> 1) & 1u);
                     umma::tc_fence_after();
                     TPROF(c_a);
                     TP(if (tr) g_ttrace[itc][4] = g_ttrace[itc][5] = t0;)
                     const uint32_t a_col = tmem_base + kTACol + stage * kTAStageCols;
-                    const uint64_t b_hi = umma::make_desc_sw128(b_base + stage * (uint32_t)kBTile);
+                    const uint64_t b_hi = umma::make_desc_sw128(b_base + (stage + deep * (use & 1u)) * (uint32_t)kBTile);
                     if (umma::elect_one()) {
                         mma_tf32_ts(d_tmem, a_col, b_hi, idesc2, kb != 0);
                         mma_tf32_ts(d_tmem, a_col + 32, b_hi, idesc, 1);
@@ -773,12 +789,12 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                             mma_tf32_ts(d_tmem, a_col + k * 8, umma::desc_advance(b_hi, k * 32), idesc2, 1);
                             mma_tf32_ts(d_tmem, a_col + 32 + k * 8, umma::desc_advance(b_hi, k * 32), idesc, 1);
                         }
-                        umma::tc_commit(&bar_empty[stage]);
+                        umma::tc_commit(&bar_empty[bi]);
                     }
                     __syncwarp();
                     TPROF(c_issue);
                     TP(if (tr) g_ttrace[itc][6] = t0; ++itc;)
-                    if (++stage == S) { stage = 0; phase ^= 1; }
+                    if (++stage == S) { stage = 0; ++use; }
                 }
                 if (umma::elect_one()) umma::tc_commit(&bar_acc_full[a]);
                 __syncwarp();
@@ -816,7 +832,7 @@ static size_t tail_bytes(const ConvParams &p, int BN) {
 
 template <int BN, bool DENSE, bool LEAN, int G, bool TAIL = false, int SUB = 1>
 static int tmem_launch_g(const DeformTmemParams &hp, const CUtensorMap &tm, cudaStream_t stream) {
-    const size_t smem = (size_t)G * 2 * BN * 32 * 4 + 2 * (size_t)hp.slot_bytes + tail_bytes(hp.p, BN) + 1024;
+    const size_t smem = (size_t)hp.sb * 2 * BN * 32 * 4 + 2 * (size_t)hp.slot_bytes + tail_bytes(hp.p, BN) + 1024;
     cudaFuncSetAttribute(deform_tmem_kernel<BN, DENSE, LEAN, G, TAIL, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int rounds = ceil_div(hp.p.total_tiles, num_sms());
     const int grid = ceil_div(hp.p.total_tiles, rounds);
@@ -875,6 +891,13 @@ static int tmem_plan(const ConvParams &src, int BN, int margin_req, int groups, 
     if (margin < 0) return AANET_ERR_UNSUPPORTED;
     hp.margin_y = margin;
     hp.margin_x = src.offset ? mx : 0;
+    {   // weight ring: twice as deep where the patch slots leave room (the dense layers; the deformable layer's margin
+        // is worth more than the ring depth).  AANET_TMEM_DEEP=0: A/B switch.
+        const char *ed = getenv("AANET_TMEM_DEEP");
+        const size_t extra = (size_t)groups * 2 * BN * 32 * 4;
+        hp.sb = groups;
+        if (!(ed && ed[0] == '0') && ring + extra + 2 * (size_t)hp.slot_bytes <= (size_t)kTSmemBudget) hp.sb = 2 * groups;
+    }
     hp.n_cb = d.Cg / 32;
     { const char *ep = getenv("AANET_HALO_PROF"); hp.prof = ep ? atoi(ep) : 0; }
     { const char *ep = getenv("AANET_MMA_SPIN"); hp.spin = ep ? atoi(ep) : 0; }

@@ -462,6 +462,12 @@ def run_gpu(args):
                     "tensor_pipe_note": "model = 3 MMAs per logical product (hi*hi, hi*lo, lo*hi) at the TF32 peak / "
                                         "live launch time; ncu = sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed "
                                         "of the committed capture",
+                    # tensor-pipe floor of THIS launch from the measured instruction times (profiles/probes/
+                    # mma_rate_probe2.cu, elected-lane issue: M = 128 kind::tf32 K = 8 takes 64 cycles at N = 128 and
+                    # 48 at N = 64): per 128-pixel tile 72 K steps x (N = 128 + N = 64) + the 1x1 tail's 8 x 3 N = 64
+                    # MMAs, 3 tiles per CTA (416 tiles on 148 SMs), at the SM clock sampled during the run
+                    "mma_floor_us": 3 * (72 * (64 + 48) + (8 * 3 * 48 if "tail" in k_what else 0))
+                                    / (((clocks or {}).get("sm_mhz") or 1965.0) * 1e6) * 1e6,
                     "us_per_launch": k_ms * 1e3, "algorithmic_mb": k_bytes / 1e6,
                     "hbm_frac_if_memory_bound": k_bytes / (k_ms * 1e-3) / 1e9 / hbm,
                     "peak_source": peak_src + "; TF32 dense taken as bf16_tflops/2 (burst, kernel timed alone); "
