@@ -62,6 +62,92 @@ rate_elect_kernel(long long *out, int M, int N, int iters) {
     if (warp == 0) { tc_fence_after(); tmem_dealloc<512>(s_tmem); }
 }
 
+// mode T: as F with the A operand in TENSOR MEMORY (the TMEM-A kernels' form), single N and the kernels' alternating
+// N = 2 BN / N = BN pair
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__global__ void __launch_bounds__(128)
+rate_ts_kernel(long long *out, int N, int N2, int iters) {
+    extern __shared__ uint8_t raw[];
+    uint8_t *smem = raw + ((1024 - (smem_u32(raw) & 1023)) & 1023);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<float *>(smem)[i] = 0.f;
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc<512>(&s_tmem);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) {
+        const uint64_t b = make_desc_sw128(smem_u32(smem + 16384));
+        const uint32_t id = make_idesc_tf32(128, N), id2 = make_idesc_tf32(128, N2);
+        const uint32_t d = s_tmem, a = s_tmem + 256;
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    mma_tf32_ts(d, a + k * 8, b + 2 * k, id, 1);
+                    if (N2) mma_tf32_ts(d, a + 32 + k * 8, b + 2 * k, id2, 1);
+                }
+            }
+            __syncwarp();
+        }
+        const long long t1 = clock64();
+        if (elect_one()) tc_commit(&bar);
+        __syncwarp();
+        mbar_wait(&bar, 0);
+        const long long t2 = clock64();
+        if (blockIdx.x == 0 && tid == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc<512>(s_tmem); }
+}
+
+// mode Q: depth of the tensor pipe's instruction queue -- cycles the issuing lane needs to get n MMAs (N = 256, 128
+// cycles of pipe time each) accepted, starting from an idle pipe
+__global__ void __launch_bounds__(128)
+queue_kernel(long long *out, int n) {
+    extern __shared__ uint8_t raw[];
+    uint8_t *smem = raw + ((1024 - (smem_u32(raw) & 1023)) & 1023);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<float *>(smem)[i] = 0.f;
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    if (warp == 0) tmem_alloc<512>(&s_tmem);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) {
+        const uint64_t a = make_desc_sw128(smem_u32(smem)), b = make_desc_sw128(smem_u32(smem + 16384));
+        const uint32_t id = make_idesc_tf32(128, 256);
+        const uint32_t d = s_tmem;
+        long long t0 = 0, t1 = 0;
+        if (elect_one()) {
+            t0 = clock64();
+            for (int k = 0; k < n; ++k) mma_tf32(d, a, b, id, 1);
+            t1 = clock64();
+            tc_commit(&bar);
+        }
+        __syncwarp();
+        mbar_wait(&bar, 0);
+        const long long t2 = clock64();
+        if (blockIdx.x == 0 && t1 != 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc<512>(s_tmem); }
+}
+
 // modes A (n_issuers = 1), B (n_issuers = 2), C (M = 64)
 __global__ void __launch_bounds__(128)
 rate1_kernel(long long *out, int M, int N, int iters, int n_issuers) {
@@ -166,6 +252,29 @@ int main() {
             rate1_kernel<<<grid, 128, 52 * 1024>>>(d_out, 128, N, iters, 1);
             if (report("A cta_group::1, one issuer", 128, N, grid, d_out, iters, 128)) return 1;
         }
+    cudaFuncSetAttribute(rate_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 52 * 1024);
+    for (int N : {32, 64, 128, 192}) {
+        long long h[2];
+        rate_ts_kernel<<<148, 128, 52 * 1024>>>(d_out, N, 0, iters);
+        if (cudaDeviceSynchronize() != cudaSuccess) { printf("ts probe failed\n"); return 1; }
+        cudaMemcpy(h, d_out, 16, cudaMemcpyDeviceToHost);
+        printf("T A in tensor memory, elected lane                M=128 N=%3d: %.1f cyc/MMA\n", N, (double)h[1] / (iters * 4.0));
+    }
+    for (int N : {32, 64}) {
+        long long h[2];
+        rate_ts_kernel<<<148, 128, 52 * 1024>>>(d_out, 2 * N, N, iters);
+        if (cudaDeviceSynchronize() != cudaSuccess) { printf("ts probe failed\n"); return 1; }
+        cudaMemcpy(h, d_out, 16, cudaMemcpyDeviceToHost);
+        printf("T A in tensor memory, the kernels' K step (N=%3d then N=%3d): %.1f cycles per K step of 8\n", 2 * N, N, (double)h[1] / (iters * 4.0));
+    }
+    cudaFuncSetAttribute(queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 52 * 1024);
+    for (int n : {1, 2, 3, 4, 6, 8, 12, 16, 24, 32}) {
+        long long h[2];
+        queue_kernel<<<1, 128, 52 * 1024>>>(d_out, n);
+        if (cudaDeviceSynchronize() != cudaSuccess) { printf("queue probe failed\n"); return 1; }
+        cudaMemcpy(h, d_out, 16, cudaMemcpyDeviceToHost);
+        printf("Q issue of %2d MMAs (N = 256, 128 cyc each) from an idle pipe: %5lld cycles until accepted, %5lld until retired\n", n, h[0], h[1]);
+    }
     cudaFuncSetAttribute(rate_elect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 52 * 1024);
     for (int N : {32, 64, 96, 128, 192, 256}) {
         rate_elect_kernel<<<148, 128, 52 * 1024>>>(d_out, 128, N, iters);
