@@ -5,7 +5,10 @@
 
 namespace aanet {
 
-enum ConvAct { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_OFFSET_MASK = 3 };
+// ACT_SOFTARGMIN: the epilogue reduces the tile's output channels (= disparity candidates, one N tile) to the
+// soft-argmin disparity sum_d d * softmax(out)[d] (nets/estimation.py:19-28) and writes ONE float per pixel to `out`
+// ([B][P]): the final 1x1 convolution of the aggregation and DisparityEstimation in one launch.
+enum ConvAct { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_OFFSET_MASK = 3, ACT_SOFTARGMIN = 4 };
 
 constexpr int kMaxProblems = 3;   // == AANET_CONV_MAX_BATCH
 

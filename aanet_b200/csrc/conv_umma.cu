@@ -116,7 +116,7 @@ int conv_umma_launch_batch(const ConvParams *probs, int n, bool deform, int bn, 
     if (!BN)
         for (int i = 0; i < n; ++i) BN = BN > conv_umma_pick_bn(probs[i].d.Og) ? BN : conv_umma_pick_bn(probs[i].d.Og);
     if (!bn_valid(BN)) return AANET_ERR_UNSUPPORTED;
-    if (n == 1 && !deform) {        // stride-1 dense layers with 32-channel blocks: operands straight from a TMA halo
+    if (n == 1 && !deform && probs[0].act != ACT_SOFTARGMIN) {   // dense layers with 32-channel blocks: operands from a TMA halo
         int rc = dense_tmem_launch(probs[0], BN, stream);
         if (rc != AANET_ERR_UNSUPPORTED) return rc;
         rc = conv_halo_launch(probs[0], BN, stream);

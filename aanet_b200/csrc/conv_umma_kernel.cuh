@@ -503,6 +503,7 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
             umma::mbar_wait_sleep(&bar_acc_full[a], (ti >> 1) & 1);
             umma::tc_fence_after();
             PROF_ADD(3);                                   // slot 3: epilogue waiting for an accumulator
+            float sm_m = -INFINITY, sm_s = 0.f, sm_w = 0.f;   // ACT_SOFTARGMIN: running max / sum / disparity-weighted sum
 #pragma unroll 1
             for (int n0 = 0; n0 < BN; n0 += 16) {
                 const bool live = p_ok && n0 < n_valid;
@@ -557,6 +558,22 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
                         if (o_base + n0 + i >= p.n_offset_ch) acc[i] = __fdividef(p.mask_scale, 1.f + __expf(-acc[i]));
+                } else if (!LEAN && p.act == ACT_SOFTARGMIN) {
+                    // online softmax over this thread's pixel (same arithmetic as softargmin_fwd_kernel: __expf of the
+                    // max-shifted value); channel o = disparity candidate o
+                    float cm = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (n0 + i < n_valid) cm = fmaxf(cm, acc[i]);
+                    const float nm = fmaxf(sm_m, cm), r = __expf(sm_m - nm);
+                    sm_s *= r; sm_w *= r; sm_m = nm;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (n0 + i < n_valid) {
+                            const float e = __expf(acc[i] - nm);
+                            sm_s += e; sm_w = fmaf(e, (float)(o_base + n0 + i), sm_w);
+                        }
+                    continue;
                 }
                 if (full) {
                     float4 *dst = reinterpret_cast<float4 *>(p.out + pix_g * d.Cout + o_base + n0);
@@ -574,6 +591,7 @@ conv_umma_kernel(const __grid_constant__ ConvBatch B) {
                         if (n0 + i < n_valid) dst[i] = acc[i];
                 }
             }
+            if (!LEAN && p.act == ACT_SOFTARGMIN && p_ok) p.out[pix_g] = __fdividef(sm_w, sm_s);
             umma::tc_fence_before();
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(&bar_acc_empty[a]);
@@ -703,7 +721,7 @@ static int launch_one(const ConvBatch &batch, cudaStream_t stream) {
     for (int i = 0; i < batch.n; ++i) {
         const ConvParams &p = batch.pr[i];
         res |= p.residual != nullptr;
-        lean &= !p.out_nchw && p.act != ACT_OFFSET_MASK && p.d.Og % 16 == 0 && (p.d.Cout & 3) == 0;
+        lean &= !p.out_nchw && p.act != ACT_OFFSET_MASK && p.act != ACT_SOFTARGMIN && p.d.Og % 16 == 0 && (p.d.Cout & 3) == 0;
     }
     if (batch.n > 1)
         return res ? launch_lean<BN, MODE, true, true>(batch, lean, stream)

@@ -142,7 +142,9 @@ extern "C" int aanet_nhwc_to_nchw(const float *src, float *dst, int B, int C, in
 static int problem_from_desc(const aanet_conv_desc &c, bool deform, ConvParams &p) {
     if (!c.x || !c.wpack || !c.out) return AANET_ERR_NULL;
     if ((c.scale == nullptr) != (c.shift == nullptr)) return AANET_ERR_NULL;
-    if (c.act < ACT_NONE || c.act > ACT_OFFSET_MASK) return AANET_ERR_UNSUPPORTED;
+    if (c.act < ACT_NONE || c.act > ACT_SOFTARGMIN) return AANET_ERR_UNSUPPORTED;
+    // soft-argmin epilogue: every candidate in one N tile of a dense, ungrouped problem; `out` is [B][P]
+    if (c.act == ACT_SOFTARGMIN && (deform || c.groups != 1 || c.Cout > 64 || c.residual || c.tail_wpack)) return AANET_ERR_UNSUPPORTED;
     MdcnDims d;
     const int rc = mdcn_make_dims(d, c.B, c.Cin, c.H, c.W, c.Cout, c.kh, c.kw, c.stride, c.pad, c.dil, c.groups,
                                   deform ? c.dg : 1);

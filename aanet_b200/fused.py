@@ -229,7 +229,14 @@ class FusedAggregation:
             conv.refresh()
         self.key = _state_key(agg)
 
-    def __call__(self, cost_volume, nhwc=False):
+    def disparity_fusable(self):
+        """Final 1x1 convolution + soft-argmin as one launch (ops.ACT_SOFTARGMIN): plain 1x1 convs whose disparity
+        candidates fit one N tile.  AANET_FUSE_SOFTARGMIN=0: A/B switch."""
+        return (os.environ.get("AANET_FUSE_SOFTARGMIN", "1") != "0" and
+                all(c.kh == 1 and c.kw == 1 and c.groups == 1 and c.Cout <= 64 and c.stride == 1 and c.pad == 0
+                    for c in self.final))
+
+    def __call__(self, cost_volume, nhwc=False, disparity=False):
         """cost_volume: the pyramid of volumes, [B,D,H,W] each -- or already channels-last [B,H,W,D] (nhwc=True,
         ops.correlation_nhwc), which saves the three layout kernels.
 
@@ -288,10 +295,17 @@ class FusedAggregation:
                     return ops.csa_fuse_nhwc(terms, slope)
                 return go
             xs = fork_join(dev, [fuse_row(row) for row in fuse])
+        if disparity:
+            # DisparityEstimation (similarity volume: softmax over the candidates, estimation.py:19-28) in the epilogue of
+            # the final 1x1: the aggregated volume is never written
+            return fork_join(dev, [(lambda s=s, conv=conv: conv(xs[s], act=ops.ACT_SOFTARGMIN))
+                                   for s, conv in enumerate(self.final)])
         return fork_join(dev, [(lambda s=s, conv=conv: conv(xs[s], out_nchw=True)) for s, conv in enumerate(self.final)])
 
 
-def run(agg, cost_volume, nhwc=False):
+def run(agg, cost_volume, nhwc=False, disparity=False):
+    """disparity=True: return soft-argmin disparities [B,H,W] (similarity volumes) instead of the aggregated volumes
+    when the executor can fuse them (FusedAggregation.disparity_fusable), else None -- the caller then asks again."""
     fused = getattr(agg, "_aanet_fused", None)
     if fused is None or fused.shapes != _shape_key(agg):
         fused = FusedAggregation(agg)
@@ -303,4 +317,6 @@ def run(agg, cost_volume, nhwc=False):
             raise RuntimeError("aanet_b200.fused: weights changed since the last eager run; run one eager forward "
                                "before capturing (the re-pack must not become part of the graph)")
         fused.refresh(agg)
-    return fused(cost_volume, nhwc)
+    if disparity and not fused.disparity_fusable():
+        return None
+    return fused(cost_volume, nhwc, disparity)

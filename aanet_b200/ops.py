@@ -358,6 +358,7 @@ def conv2d_fused(x, weight, bias=None, scale=None, shift=None, residual=None, ac
 
 # ------------------------------------------------------------------------------------ channels-last engine
 ACT_OFFSET_MASK = 3
+ACT_SOFTARGMIN = 4      # conv_batch: the epilogue reduces the output channels to the soft-argmin disparity, out [B,Ho,Wo]
 
 
 def nchw_to_nhwc(x):
@@ -441,6 +442,8 @@ def _fill_desc(d, q, out):
     tail = q.get("tail")
     c_out = tail["Cout"] if tail else q["Cout"]
     oshape = (B, c_out, Ho, Wo) if q.get("out_nchw") else (B, Ho, Wo, c_out)
+    if int(q.get("act", ACT_NONE)) == ACT_SOFTARGMIN:
+        oshape = (B, Ho, Wo)
     om = q.get("offmask")
     for nm in ("bias", "scale", "shift"):
         _cl(q.get(nm), nm, dev, (q["Cout"],))

@@ -62,6 +62,10 @@ class HotPath(nn.Module):
             cost = fork_join(left_pyramid[0].device,
                              [(lambda l=l, r=r, d=d: ops.correlation_nhwc(l, r, d))
                               for l, r, d in zip(left_pyramid, right_pyramid, D)])
+            if self.disparity_estimation.match_similarity:
+                disp = fused.run(agg_mod, cost, nhwc=True, disparity=True)
+                if disp is not None:
+                    return list(reversed(disp))
             agg = fused.run(agg_mod, cost, nhwc=True)
         else:
             with exact_fp32():

@@ -197,7 +197,9 @@ typedef struct aanet_conv_desc {
     const float *offmask;    /* DEFORM: [B][Ho*Wo][om_channels] */
     int om_channels;
     int B, Cin, H, W, Cout, kh, kw, stride, pad, dil, groups, dg;
-    int act;                 /* 0 none, 1 ReLU, 2 LeakyReLU(slope), 3 offset/mask head */
+    int act;                 /* 0 none, 1 ReLU, 2 LeakyReLU(slope), 3 offset/mask head, 4 soft-argmin over the output
+                              * channels (nets/estimation.py:19-28 fused into the final 1x1, nets/aggregation.py:443-450):
+                              * `out` is then [B][Ho*Wo], one disparity per pixel; dense, groups == 1, Cout <= 64 */
     float slope;
     int n_offset_ch;         /* act == 3 */
     float mask_scale;        /* act == 3 */

@@ -16,7 +16,10 @@ timeout 600 python profiles/full_model.py --variant dropin --weights $W > $O/z_f
 timeout 300 python profiles/profile_step.py --steps 3 > $O/z_plain.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches_r02.csv python profiles/profile_step.py --steps 3 > $O/z_ncu1.log 2>&1
 # full capture of the kernels of step 3
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"deform_tmem|conv_umma_kernel|corr_tma|csa_fuse|softargmin" -s 190 -c 60 -o /tmp/step_r02 python profiles/profile_step.py --steps 3 > $O/z_ncu2.log 2>&1
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"deform_tmem|conv_umma_kernel|corr_tma|csa_fuse|softargmin" -s 228 -c 84 -o /tmp/step_r02 python profiles/profile_step.py --steps 3 > $O/z_ncu2.log 2>&1
 ncu -i /tmp/step_r02.ncu-rep --page raw --csv > $O/step_r02_raw.csv 2>/dev/null
 ls -la /tmp/step_r02.ncu-rep $O/step_r02_raw.csv; du -sh $O
+timeout 200 python profiles/timeline.py --graph > $O/timeline_graph_final.txt 2>/dev/null
+TRACE=0 PIPE=1 timeout 200 python profiles/tmem_trace.py > $O/tmem_kernels_final.log 2>&1
+AANET_B200_LIB=$PWD/aanet_b200/lib/libaanet_b200_base.so TRACE=0 PIPE=1 timeout 200 python profiles/tmem_trace.py > $O/tmem_kernels_a56f909.log 2>&1
 head -c 500 $O/z_bench.json

@@ -396,3 +396,33 @@ def test_fused_executor_peak_memory():
     print("peak extra memory: %.2f volumes of the 1/3-scale size" % peak)
     assert out[0].shape == (B, D0, H, W)
     assert peak < 8.0
+
+
+def test_fused_softargmin_epilogue_matches_separate_kernels():
+    """HotPath with the final 1x1 convolution + soft-argmin in one launch (ops.ACT_SOFTARGMIN) against the final
+    convolution followed by the soft-argmin kernel: <= 1e-4 px (both are fp32 online softmaxes), and both against the
+    CPU port within the path's 1e-3 px."""
+    import os
+    from aanet_b200.pipeline import HotPath
+    torch.manual_seed(5)
+    hp = HotPath(96, num_deform_blocks=1, num_fusions=2).cuda().eval()
+    for name, m in hp.named_modules():
+        if name.endswith("offset_conv"):
+            torch.nn.init.normal_(m.weight, std=0.05)
+    L = [torch.relu(torch.randn(2, 32, 48 // 2 ** s, 96 // 2 ** s, device="cuda")) for s in range(3)]
+    R = [torch.relu(torch.randn(2, 32, 48 // 2 ** s, 96 // 2 ** s, device="cuda")) for s in range(3)]
+    old = os.environ.get("AANET_FUSE_SOFTARGMIN")
+    try:
+        os.environ["AANET_FUSE_SOFTARGMIN"] = "1"
+        with torch.no_grad():
+            fused_d = hp(L, R)
+        os.environ["AANET_FUSE_SOFTARGMIN"] = "0"
+        with torch.no_grad():
+            two = hp(L, R)
+    finally:
+        if old is None:
+            os.environ.pop("AANET_FUSE_SOFTARGMIN", None)
+        else:
+            os.environ["AANET_FUSE_SOFTARGMIN"] = old
+    assert len(fused_d) == len(two) == 1 and fused_d[0].shape == two[0].shape == (2, 48, 96)
+    assert float((fused_d[0] - two[0]).abs().max()) < 1e-4
