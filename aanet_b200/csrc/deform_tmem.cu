@@ -213,7 +213,9 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
             umma::mbar_init(&bar_halo_full[s], 1);            // expect_tx + TMA bytes
-            umma::mbar_init(&bar_halo_empty[s], kTProdWarps); // every producer warp, after its last tap of the slot
+            // every producer warp that reads the slot, after its last tap of it (fewer taps than groups, i.e. the 1x1
+            // convolutions: only T of the G groups touch a slot)
+            umma::mbar_init(&bar_halo_empty[s], 4 * (T < G ? T : G));
         }
         for (int s = 0; s < 2 * S; ++s) {
             umma::mbar_init(&bar_full[s], 5);                 // the four warps of the filling group + arrive.expect_tx of
@@ -454,8 +456,12 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
 
         Tile tl;
         tl.t = (int)blockIdx.x;
-        int cb = 0, tap = grpi;                               // G <= T: the group's first K block is tap grpi of block 0
+        int cb = 0, tap = grpi;                               // the group's first K block: tap grpi of block 0 ...
         uint32_t hs = 0u;                                     // halo slot sequence number
+        while (tap >= T) {                                    // ... or, with fewer taps than groups, a later block / tile
+            tap -= T; ++hs;
+            if (++cb == n_cb) { cb = 0; tl.t += (int)gridDim.x; }
+        }
         int use = 0;                                          // how often my stage has been filled (see bar_full / bar_empty)
         TP(uint32_t it_seq = grpi;)
         const int s = grpi;                                   // S == G: group g always refills A stage g
@@ -512,10 +518,12 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                 TP(if (tr) g_ttrace[it_seq][3] = clock64();)
                 {   // step to my next K block
                     tap += G; ++use; TP(it_seq += G;)
-                    if (tap >= T) {
+                    bool moved = false;
+                    while (tap >= T) {                        // (several wraps when a block has fewer taps than groups)
                         tap -= T; ++hs;
-                        if (++cb == n_cb) { cb = 0; tl.t += (int)gridDim.x; if (tl.t < total) decode_tile(tl); }
+                        if (++cb == n_cb) { cb = 0; tl.t += (int)gridDim.x; moved = true; }
                     }
+                    if (moved && tl.t < total) decode_tile(tl);
                     tapo = s_tapoff[phys(tap)];
                 }
                 continue;
@@ -954,7 +962,8 @@ int dense_tmem_launch(const ConvParams &src, int BN, cudaStream_t stream) {
     const bool tail = src.tail_wpack != nullptr;
     if (tail && !tmem_tail_ok(src, BN)) return AANET_ERR_UNSUPPORTED;
     const int groups = tail ? 3 : tmem_groups(true);
-    if (d.K < groups) return AANET_ERR_UNSUPPORTED;
+    // (fewer taps than producer groups -- the 1x1 convolutions -- are fine: the groups then skip halo slots)
+    if (tail && d.K < groups) return AANET_ERR_UNSUPPORTED;
     DeformTmemParams hp;
     CUtensorMap tm;
     const int rc = tmem_plan(src, BN, 0, groups, hp, tm);

@@ -184,3 +184,38 @@ def test_strided_dense_tmem_vs_float64(cfg):
         else:
             os.environ["AANET_DENSE_TMEM"] = old
     assert rel_err(npy(got), npy(eng)) < 1e-5
+
+
+@pytest.mark.parametrize("cfg", [
+    # B, Cin, Cout, H, W, out_nchw
+    (1, 64, 64, 128, 416, False),     # conv1 of the bottlenecks at the 1/3 scale
+    (2, 32, 32, 33, 47, False),       # one channel block, ragged tiles, batch 2
+    (1, 64, 32, 24, 52, True),        # NCHW output (non-lean epilogue)
+    (1, 128, 64, 9, 20, False),       # four channel blocks
+])
+def test_pointwise_dense_tmem_vs_float64(cfg):
+    """1x1 convolutions through the TMEM-A kernel (fewer taps than producer groups: the groups skip patch slots)
+    against float64 torch and against the round-1 engine."""
+    import aanet_b200.ops as ops
+    B, Ci, Co, H, W, nchw = cfg
+    torch.manual_seed(37)
+    x = torch.randn(B, H, W, Ci, device="cuda")
+    w = torch.randn(Co, Ci, 1, 1, device="cuda") / Ci ** 0.5
+    sc, sh = torch.rand(Co, device="cuda") + 0.5, torch.randn(Co, device="cuda")
+    wp = ops.pack_conv_weight(w)
+    call = lambda: ops.conv2d_nhwc(x, wp, Co, 1, 1, None, sc, sh, None, ops.ACT_RELU, 0.0, 1, 0, 1, 1, out_nchw=nchw)
+    got = call()
+    ref = torch.relu(torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double()) * sc.view(1, -1, 1, 1)
+                     + sh.view(1, -1, 1, 1))
+    g = got if nchw else got.permute(0, 3, 1, 2)
+    assert rel_err(npy(g), npy(ref)) < 1e-5
+    old = os.environ.get("AANET_DENSE_TMEM")
+    os.environ["AANET_DENSE_TMEM"] = "0"
+    try:
+        eng = call()
+    finally:
+        if old is None:
+            os.environ.pop("AANET_DENSE_TMEM", None)
+        else:
+            os.environ["AANET_DENSE_TMEM"] = old
+    assert rel_err(npy(got), npy(eng)) < 1e-5
