@@ -213,9 +213,11 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
             umma::mbar_init(&bar_halo_full[s], 1);            // expect_tx + TMA bytes
-            // every producer warp that reads the slot, after its last tap of it (fewer taps than groups, i.e. the 1x1
-            // convolutions: only T of the G groups touch a slot)
-            umma::mbar_init(&bar_halo_empty[s], 4 * (T < G ? T : G));
+            // every producer warp, after its last tap of the slot -- or, with fewer taps than groups (the 1x1
+            // convolutions), when it passes a slot it has no tap in: all groups then see every phase of both slot
+            // barriers in order, so a parity wait can never alias (a group that SKIPPED slots would test phase n of a
+            // barrier that is still in phase n - 2: found the hard way)
+            umma::mbar_init(&bar_halo_empty[s], kTProdWarps);
         }
         for (int s = 0; s < 2 * S; ++s) {
             umma::mbar_init(&bar_full[s], 5);                 // the four warps of the filling group + arrive.expect_tx of
@@ -458,7 +460,16 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
         tl.t = (int)blockIdx.x;
         int cb = 0, tap = grpi;                               // the group's first K block: tap grpi of block 0 ...
         uint32_t hs = 0u;                                     // halo slot sequence number
+        int n_my = 0;                                         // halo slots this CTA walks = its tiles x channel blocks
+        for (int t = blockIdx.x; t < total; t += gridDim.x) n_my += n_cb;
+        auto pass_slot = [&](uint32_t h) {                    // a slot I have no tap in: see it filled, release it
+            if ((int)h >= n_my) return;
+            umma::mbar_wait(&bar_halo_full[h & 1], (h >> 1) & 1);
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(&bar_halo_empty[h & 1]);
+        };
         while (tap >= T) {                                    // ... or, with fewer taps than groups, a later block / tile
+            pass_slot(hs);
             tap -= T; ++hs;
             if (++cb == n_cb) { cb = 0; tl.t += (int)gridDim.x; }
         }
@@ -518,8 +529,10 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                 TP(if (tr) g_ttrace[it_seq][3] = clock64();)
                 {   // step to my next K block
                     tap += G; ++use; TP(it_seq += G;)
-                    bool moved = false;
+                    bool moved = false, mine = true;
                     while (tap >= T) {                        // (several wraps when a block has fewer taps than groups)
+                        if (!mine) pass_slot(hs);             // the slot just left was mine only on the first wrap
+                        mine = false;
                         tap -= T; ++hs;
                         if (++cb == n_cb) { cb = 0; tl.t += (int)gridDim.x; moved = true; }
                     }
