@@ -62,6 +62,9 @@ int deform_tmem_launch(const ConvParams &p, int BN, cudaStream_t stream);
 int dense_tmem_launch(const ConvParams &p, int BN, cudaStream_t stream);
 // can the (main + fused 1x1 tail) problem run as one TMEM-kernel launch?
 bool tmem_tail_supported(const ConvParams &p, bool deform);
+// CSA resize-and-sum + LeakyReLU as the A producer of the following 1x1 convolution (deform_tmem.cu, FUSE)
+int csa_conv1_tmem_launch(const float *const *terms, const int *th, const int *tw, int n_terms, float slope,
+                          float *fused_out, const ConvParams &conv, cudaStream_t stream);
 
 bool conv_umma_supported(const MdcnDims &d, bool deform);
 int conv_umma_pick_bn(int Og);

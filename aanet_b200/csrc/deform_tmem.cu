@@ -50,8 +50,24 @@ template <int G> struct TCfg {
 constexpr int kTSmemBudget = 219 * 1024;   // dynamic; + 1 KB alignment slack + ~6.5 KB static (barriers, tables, geometry slots) <= 227 KB
 constexpr int kTAcc3Col = 448;           // TAIL: accumulator of the fused 1x1 convolution (<= 64 columns)
 
+// FUSE: the 1x1 convolution's input does not exist in memory -- it is the cross-scale sum of the CSA stage,
+//   x[p, c] = LeakyReLU( sum_k resize_k(term_k)[p, c] )        (nets/aggregation.py:387-400)
+// produced by the A producers from TMA-staged tiles / bilinear source patches of the terms and written out once (it
+// is the next bottleneck's identity) while it goes into tensor memory as the operand of conv1 (deform.py:164-170).
+constexpr int kFuseMaxTerms = 3;
+struct FuseGeom {
+    int n;                                   // 0: not a fused launch
+    int th[kFuseMaxTerms], tw[kFuseMaxTerms];   // term sizes; (H, W): same-size term, else bilinear up-sampling source
+    int ph[kFuseMaxTerms], pw[kFuseMaxTerms];   // TMA box of term k in lines: the tile (8 x 16) or the source patch
+    int off[kFuseMaxTerms];                  // byte offset of term k's region inside a halo slot (1024-aligned)
+    int bytes;                               // sum of the boxes
+    float slope;
+    float *out;                              // the sum, channels-last [B][H*W][C]
+};
+
 struct DeformTmemParams {
     ConvParams p;
+    FuseGeom fz;
     int HH, HWd, lines, slot_bytes;    // halo box (rows, pixels per row), lines = HH * HWd, bytes rounded to 1024
     int margin_y, margin_x, n_cb, prof;   // pixels of offset the halo covers above/below and left/right
     int spin;                             // experiment: the MMA thread polls its barriers instead of sleeping on them
@@ -173,9 +189,20 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 // MMA order D(0) D(1) C(0) D(2) C(1) ... so the activation pass of tile i runs under the main loop of tile i + 1.
 // SUB = deformable groups per 32-channel K block: 1 (>= 32 channels per deformable group) or 2 (16 channels per group,
 // the 1/6 scale of the pyramid: a thread then takes two bilinear samples per K block, one per half of its row).
-template <int BN, bool DENSE, bool LEAN, int G, bool TAIL = false, int SUB = 1>
+// ATen area_pixel_compute_source_index + guard (float arithmetic), as csa_fuse.cu
+__device__ __forceinline__ void fuse_src_index(int dst, int in, float scale, int &i0, int &i1, float &l0, float &l1) {
+    float src = scale * ((float)dst + 0.5f) - 0.5f;
+    src = src < 0.f ? 0.f : src;
+    i0 = min((int)src, in - 1);
+    i1 = i0 + (i0 < in - 1 ? 1 : 0);
+    l1 = src - (float)i0;
+    l0 = 1.f - l1;
+}
+
+template <int BN, bool DENSE, bool LEAN, int G, bool TAIL = false, int SUB = 1, bool FUSE = false>
 __global__ void __launch_bounds__(TCfg<G>::kThreads, 1)
-deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_constant__ CUtensorMap tm) {
+deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_constant__ CUtensorMap tm,
+                   const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2) {
     constexpr int S = G, kTGroups = G, kTProdWarps = TCfg<G>::kProdWarps, kTTmaWarp = TCfg<G>::kTmaWarp,
                   kTLoadWarp = TCfg<G>::kLoadWarp, kTMmaWarp = TCfg<G>::kMmaWarp;
     constexpr int kBTile = 2 * BN * 32 * 4;                   // [B_hi | B_lo] of one K block
@@ -497,11 +524,65 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                 const uint32_t a_col = tmem_base + ((uint32_t)(q * 32) << 16) + kTACol + s * kTAStageCols;
                 // (stride 2, the CSA down-sampling convs: neighbouring pixels read every other line -> 2-way bank
                 // conflicts on 8 loads per K block, irrelevant next to the L2 round trips of the gather engine)
+                float4 qd[8];
+                if (FUSE) {
+                    // my pixel's 32 channels of the cross-scale sum: same-size terms are a line of their tile box,
+                    // up-sampled terms four corner lines of their source patch (weights as csa_fuse.cu: products of
+                    // the row and column weights, corners in the order 00 01 10 11, terms added in order)
+                    const FuseGeom &fz = hp.fz;
+#pragma unroll
+                    for (int k = 0; k < kFuseMaxTerms; ++k) {
+                        if (k >= fz.n) break;
+                        const uint32_t reg = halo + (uint32_t)fz.off[k];
+                        if (fz.th[k] == d.H && fz.tw[k] == d.W) {
+                            const uint32_t P = (reg + (uint32_t)row * 128) | ((uint32_t)(row & 7) << 4);
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const float4 v = lds128(P ^ (uint32_t)(c << 4));
+                                if (k == 0) qd[c] = v;
+                                else { qd[c].x += v.x; qd[c].y += v.y; qd[c].z += v.z; qd[c].w += v.w; }
+                            }
+                        } else {
+                            const float shh = (float)fz.th[k] / (float)d.H, sww = (float)fz.tw[k] / (float)d.W;
+                            int h0, h1, x0, x1, r_lo, c_lo, t_; float a0, a1, b0, b1, u0, u1;
+                            fuse_src_index(tl.oh, fz.th[k], shh, h0, h1, a0, a1);
+                            fuse_src_index(tl.ow, fz.tw[k], sww, x0, x1, b0, b1);
+                            fuse_src_index(tl.hy0, fz.th[k], shh, r_lo, t_, u0, u1);      // patch origin (pad = 0: hy0 = tile row 0)
+                            fuse_src_index(tl.hx0, fz.tw[k], sww, c_lo, t_, u0, u1);
+                            const int l00 = (h0 - r_lo) * fz.pw[k] + (x0 - c_lo), l01 = (h0 - r_lo) * fz.pw[k] + (x1 - c_lo);
+                            const int l10 = (h1 - r_lo) * fz.pw[k] + (x0 - c_lo), l11 = (h1 - r_lo) * fz.pw[k] + (x1 - c_lo);
+                            const uint32_t P00 = (reg + (uint32_t)l00 * 128) | ((uint32_t)(l00 & 7) << 4);
+                            const uint32_t P01 = (reg + (uint32_t)l01 * 128) | ((uint32_t)(l01 & 7) << 4);
+                            const uint32_t P10 = (reg + (uint32_t)l10 * 128) | ((uint32_t)(l10 & 7) << 4);
+                            const uint32_t P11 = (reg + (uint32_t)l11 * 128) | ((uint32_t)(l11 & 7) << 4);
+                            const float w00 = a0 * b0, w01 = a0 * b1, w10 = a1 * b0, w11 = a1 * b1;
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const uint32_t x = (uint32_t)(c << 4);
+                                const float4 v00 = lds128(P00 ^ x), v01 = lds128(P01 ^ x), v10 = lds128(P10 ^ x), v11 = lds128(P11 ^ x);
+                                float4 v;
+                                v.x = w00 * v00.x + w01 * v01.x + w10 * v10.x + w11 * v11.x;
+                                v.y = w00 * v00.y + w01 * v01.y + w10 * v10.y + w11 * v11.y;
+                                v.z = w00 * v00.z + w01 * v01.z + w10 * v10.z + w11 * v11.z;
+                                v.w = w00 * v00.w + w01 * v01.w + w10 * v10.w + w11 * v11.w;
+                                if (k == 0) qd[c] = v;
+                                else { qd[c].x += v.x; qd[c].y += v.y; qd[c].z += v.z; qd[c].w += v.w; }
+                            }
+                        }
+                    }
+                    float4 *dst = reinterpret_cast<float4 *>(fz.out + ((long)tl.b * d.HW + (long)tl.oh * d.W + tl.ow) * d.Cin + cb * 32);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        qd[c].x = qd[c].x > 0.f ? qd[c].x : qd[c].x * fz.slope; qd[c].y = qd[c].y > 0.f ? qd[c].y : qd[c].y * fz.slope;
+                        qd[c].z = qd[c].z > 0.f ? qd[c].z : qd[c].z * fz.slope; qd[c].w = qd[c].w > 0.f ? qd[c].w : qd[c].w * fz.slope;
+                        if (tl.ok) dst[c] = qd[c];
+                    }
+                } else {
                 const int l0 = (tl.oh * d.stride + tapo.x - tl.hy0) * hp.HWd + (tl.ow * d.stride + tapo.y - tl.hx0);
                 const uint32_t P0 = (halo + (uint32_t)l0 * 128) | ((uint32_t)(l0 & 7) << 4);
-                float4 qd[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) qd[c] = lds128(P0 ^ (uint32_t)(c << 4));
+                }
                 // previous use of my stage retired?  (use - 1 = -1 on the first pass: parity 1 of a fresh barrier passes)
                 umma::mbar_wait(&bar_empty[s + S * ((use - 1) & 1)], (uint32_t)(((use - 1) >> 1) & 1));
                 TP(const bool tr = hp.prof == 2 && blockIdx.x == 0 && q == 0 && lane == 0 && it_seq < (uint32_t)kTraceKB;
@@ -699,6 +780,22 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                 for (int cb = 0; cb < n_cb; ++cb, ++hs) {
                     const int s = hs & 1;
                     umma::mbar_wait_sleep(&bar_halo_empty[s], ((hs >> 1) & 1) ^ 1);
+                    if (FUSE) {
+                        const FuseGeom &fz = hp.fz;
+                        umma::mbar_expect_tx(&bar_halo_full[s], fz.bytes);
+                        for (int k = 0; k < fz.n; ++k) {
+                            const CUtensorMap *tk = k == 0 ? &tm : k == 1 ? &tm1 : &tm2;
+                            int x0 = it.tx * kTTW, y0 = it.ty * kTTH;
+                            if (fz.th[k] != d.H || fz.tw[k] != d.W) {      // first source row / column of the patch
+                                int i1; float l0, l1;
+                                fuse_src_index(it.ty * kTTH, fz.th[k], (float)fz.th[k] / (float)d.H, y0, i1, l0, l1);
+                                fuse_src_index(it.tx * kTTW, fz.tw[k], (float)fz.tw[k] / (float)d.W, x0, i1, l0, l1);
+                            }
+                            umma::tma_load_4d(halo0 + (size_t)s * hp.slot_bytes + fz.off[k], tk, cb * 32, x0, y0, it.b,
+                                              &bar_halo_full[s]);
+                        }
+                        continue;
+                    }
                     umma::mbar_expect_tx(&bar_halo_full[s], hp.lines * 128);
                     umma::tma_load_4d(halo0 + (size_t)s * hp.slot_bytes, &tm, it.grp * d.Cg + cb * 32,
                                       it.tx * kTTW * d.stride - d.pad - hp.margin_x,
@@ -851,13 +948,15 @@ static size_t tail_bytes(const ConvParams &p, int BN) {
     return p.tail_wpack ? (size_t)(BN / 32) * 2 * p.tail_cout * 128 : 0;
 }
 
-template <int BN, bool DENSE, bool LEAN, int G, bool TAIL = false, int SUB = 1>
-static int tmem_launch_g(const DeformTmemParams &hp, const CUtensorMap &tm, cudaStream_t stream) {
+template <int BN, bool DENSE, bool LEAN, int G, bool TAIL = false, int SUB = 1, bool FUSE = false>
+static int tmem_launch_g(const DeformTmemParams &hp, const CUtensorMap &tm, cudaStream_t stream,
+                         const CUtensorMap *tm1 = nullptr, const CUtensorMap *tm2 = nullptr) {
     const size_t smem = (size_t)hp.sb * 2 * BN * 32 * 4 + 2 * (size_t)hp.slot_bytes + tail_bytes(hp.p, BN) + 1024;
-    cudaFuncSetAttribute(deform_tmem_kernel<BN, DENSE, LEAN, G, TAIL, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(deform_tmem_kernel<BN, DENSE, LEAN, G, TAIL, SUB, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int rounds = ceil_div(hp.p.total_tiles, num_sms());
     const int grid = ceil_div(hp.p.total_tiles, rounds);
-    return launch_pdl(deform_tmem_kernel<BN, DENSE, LEAN, G, TAIL, SUB>, dim3(grid), dim3(TCfg<G>::kThreads), smem, stream, hp, tm);
+    return launch_pdl(deform_tmem_kernel<BN, DENSE, LEAN, G, TAIL, SUB, FUSE>, dim3(grid), dim3(TCfg<G>::kThreads), smem, stream, hp,
+                      tm, tm1 ? *tm1 : tm, tm2 ? *tm2 : tm);
 }
 
 // the fused-tail instantiations exist for the 3-group pipeline, lean epilogue, BN = 32 / 64
@@ -891,6 +990,7 @@ static bool tmem_tail_ok(const ConvParams &p, int BN) {
 static int tmem_plan(const ConvParams &src, int BN, int margin_req, int groups, DeformTmemParams &hp, CUtensorMap &tm) {
     const MdcnDims &d = src.d;
     hp.p = src;
+    hp.fz = FuseGeom{};
     const size_t ring = (size_t)groups * 2 * BN * 32 * 4 + tail_bytes(src, BN) + (src.offset && d.Cd == 16 ? 5 * 1024 : 0);   // (+ the second sample's geometry slots, static)
     // Halo plan.  The pitch (pixels per halo row) is rounded up to a multiple of 8 lines: a sample whose row index
     // jitters by one (sub-pixel offsets of either sign) then keeps its swizzle key (line & 7), so neighbouring
@@ -1001,6 +1101,59 @@ bool tmem_tail_supported(const ConvParams &src, bool deform) {
     DeformTmemParams hp;
     CUtensorMap tm;
     return tmem_plan(src, BN, deform ? 4 : 0, 3, hp, tm) == AANET_OK;
+}
+
+// CSA resize-and-sum + LeakyReLU fused into the next bottleneck's conv1 (1x1 + bn1 + ReLU): `terms` are channels-last
+// [B][th][tw][C] tensors, each either (H, W)-sized or smaller (bilinear, align_corners = False); the sum goes to
+// fused_out [B][H*W][C] and conv1 of it to conv.out.  conv: a ConvParams of the 1x1 convolution (x unused).
+int csa_conv1_tmem_launch(const float *const *terms, const int *th, const int *tw, int n_terms, float slope,
+                          float *fused_out, const ConvParams &conv, cudaStream_t stream) {
+    const MdcnDims &d = conv.d;
+    if (n_terms < 1 || n_terms > kFuseMaxTerms || d.K != 1 || d.stride != 1 || d.pad != 0 || d.groups != 1) return AANET_ERR_UNSUPPORTED;
+    if (d.Cin % 32 || d.Cin > 64 * 32 || (d.Cout != 32 && d.Cout != 64) || conv.out_nchw || conv.residual || conv.tail_wpack ||
+        conv.act == ACT_OFFSET_MASK || conv.act == ACT_SOFTARGMIN || !fused_out)
+        return AANET_ERR_UNSUPPORTED;
+    DeformTmemParams hp;
+    hp.p = conv;
+    hp.p.x = terms[0];
+    FuseGeom &fz = hp.fz;
+    fz = FuseGeom{};
+    fz.n = n_terms; fz.slope = slope; fz.out = fused_out;
+    CUtensorMap tms[kFuseMaxTerms];
+    int off = 0;
+    for (int k = 0; k < n_terms; ++k) {
+        if (!terms[k] || !aligned16(terms[k]) || th[k] <= 0 || tw[k] <= 0 || th[k] > d.H || tw[k] > d.W) return AANET_ERR_UNSUPPORTED;
+        const bool same = th[k] == d.H && tw[k] == d.W;
+        if (!same && (th[k] == d.H || tw[k] == d.W)) return AANET_ERR_UNSUPPORTED;      // both axes resized, or none
+        fz.th[k] = th[k]; fz.tw[k] = tw[k];
+        // bilinear footprint of kTTH (kTTW) consecutive destination pixels: span * scale + both neighbours
+        fz.ph[k] = same ? kTTH : (int)((long)(kTTH - 1) * th[k] / d.H) + 3;
+        fz.pw[k] = same ? kTTW : (int)((long)(kTTW - 1) * tw[k] / d.W) + 3;
+        fz.off[k] = off;
+        fz.bytes += fz.ph[k] * fz.pw[k] * 128;
+        off += (fz.ph[k] * fz.pw[k] * 128 + 1023) & ~1023;
+        const uint64_t dims[4] = {(uint64_t)d.Cin, (uint64_t)tw[k], (uint64_t)th[k], (uint64_t)d.B};
+        const uint64_t strides[3] = {(uint64_t)d.Cin * 4, (uint64_t)tw[k] * d.Cin * 4, (uint64_t)th[k] * tw[k] * d.Cin * 4};
+        const uint32_t box[4] = {32, (uint32_t)fz.pw[k], (uint32_t)fz.ph[k], 1};
+        const int rc = make_tensor_map_f32(&tms[k], terms[k], 4, dims, strides, box, 1);
+        if (rc) return rc;
+    }
+    const int BN = d.Cout;
+    hp.HH = kTTH; hp.HWd = kTTW; hp.lines = kTTH * kTTW; hp.slot_bytes = off;
+    hp.margin_y = hp.margin_x = 0; hp.n_cb = d.Cin / 32;
+    hp.prof = 0; hp.spin = 0; hp.rot = 0; hp.sb = 3;
+    if ((size_t)3 * 2 * BN * 32 * 4 + 2 * (size_t)off > (size_t)kTSmemBudget) return AANET_ERR_UNSUPPORTED;
+    ConvParams &p = hp.p;
+    p.n_tiles_n = 1;
+    p.K = d.Cin; p.KB = p.K / 32;
+    p.tiles_x = ceil_div(d.W, kTTW);
+    p.tiles_per_img = p.tiles_x * ceil_div(d.H, kTTH);
+    p.n_ptiles = d.B * p.tiles_per_img;
+    if ((long)p.n_ptiles > 0x3fffffffL) return AANET_ERR_UNSUPPORTED;
+    p.total_tiles = p.n_ptiles;
+    const CUtensorMap *t1 = n_terms > 1 ? &tms[1] : nullptr, *t2 = n_terms > 2 ? &tms[2] : nullptr;
+    return BN == 64 ? tmem_launch_g<64, true, true, 3, false, 1, true>(hp, tms[0], stream, t1, t2)
+                    : tmem_launch_g<32, true, true, 3, false, 1, true>(hp, tms[0], stream, t1, t2);
 }
 
 }  // namespace aanet

@@ -158,8 +158,15 @@ class _Bottleneck:
             self._tail[key] = ok
         return self._tail[key]
 
-    def __call__(self, x):
-        y1 = self.c1(x)
+    def conv1_fusable(self):
+        """conv1 as the consumer of the fused CSA sum (ops.csa_conv1_nhwc): plain 1x1 + bn1 + ReLU."""
+        c = self.c1
+        return (c.kh == 1 and c.kw == 1 and c.stride == 1 and c.pad == 0 and c.groups == 1 and c.bias is None
+                and c.act == ops.ACT_RELU and c.Cout in (32, 64))
+
+    def __call__(self, x, y1=None):
+        if y1 is None:                      # (else: conv1 was computed by the CSA launch that produced x)
+            y1 = self.c1(x)
         if self._tail_ok(y1):
             return self.c2(y1, tail=self.c3.as_tail(x))          # conv2 (+ bn2 + ReLU) and conv3 + bn3 + x + ReLU: one launch
         return self.c3(self.c2(y1), residual=x)
@@ -248,10 +255,10 @@ class FusedAggregation:
         ~6 volumes of the 1/3-scale size per pair instead of the ~70 a keep-everything plan holds."""
         dev = cost_volume[0].device
 
-        def branch(blocks, x):
+        def branch(blocks, x, y1=None):
             def go():
-                y = x
-                for blk in blocks:
+                y = blocks[0](x, y1)
+                for blk in blocks[1:]:
                     y = blk(y)
                 return y
             return go
@@ -260,13 +267,16 @@ class FusedAggregation:
             xs = list(cost_volume)
         else:
             xs = fork_join(dev, [(lambda c=c: ops.nchw_to_nhwc(c)) for c in cost_volume])
-        for branches, fuse, slope in self.stages:
+        pre = [None] * len(xs)                  # conv1 outputs of the next stage, where the CSA launch produced them
+        for si, (branches, fuse, slope) in enumerate(self.stages):
             # ISA: the scales are independent -> one stream each
-            xs = fork_join(dev, [branch(blocks, xs[s]) for s, blocks in enumerate(branches)])
+            xs = fork_join(dev, [branch(blocks, xs[s], pre[s]) for s, blocks in enumerate(branches)])
+            pre = [None] * len(xs)
             if fuse is None:
                 continue
+            nxt = self.stages[si + 1][0] if si + 1 < len(self.stages) else None
             # CSA: output scale i needs every input scale; the output scales are independent
-            def fuse_row(row, xs=xs):
+            def fuse_row(i, row, xs=xs, nxt=nxt):
                 def go():
                     # the last conv of every exchange chain of this row in ONE multi-problem launch (they are
                     # independent and all produce this row's channel count); longer chains run their head first
@@ -292,9 +302,15 @@ class FusedAggregation:
                     else:
                         for j, (c, t) in zip(where, last):
                             terms[j] = c(t)
-                    return ops.csa_fuse_nhwc(terms, slope)
+                    if nxt is not None and i < len(nxt) and nxt[i][0].conv1_fusable() and \
+                            ops.csa_conv1_supported(terms, nxt[i][0].c1.Cout):
+                        c1 = nxt[i][0].c1           # the next module's conv1 consumes the sum inside the same launch
+                        return ops.csa_conv1_nhwc(terms, slope, c1.wpack, c1.Cout, c1.scale, c1.shift, c1.act)
+                    return ops.csa_fuse_nhwc(terms, slope), None
                 return go
-            xs = fork_join(dev, [fuse_row(row) for row in fuse])
+            got = fork_join(dev, [fuse_row(i, row) for i, row in enumerate(fuse)])
+            xs, pre = [g[0] for g in got], [g[1] for g in got]
+            pre += [None] * (len(branches) - len(pre))
         if disparity:
             # DisparityEstimation (similarity volume: softmax over the candidates, estimation.py:19-28) in the epilogue of
             # the final 1x1: the aggregated volume is never written

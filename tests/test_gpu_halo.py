@@ -219,3 +219,34 @@ def test_pointwise_dense_tmem_vs_float64(cfg):
         else:
             os.environ["AANET_DENSE_TMEM"] = old
     assert rel_err(npy(got), npy(eng)) < 1e-5
+
+
+@pytest.mark.parametrize("cfg", [
+    # B, C, Cout, H, W, term sizes (first = output size)
+    (1, 64, 64, 128, 416, [(128, 416), (64, 208), (32, 104)]),     # CSA row 0 of config 2 + conv1 of the next module
+    (2, 32, 32, 33, 47, [(33, 47), (33, 47), (17, 24)]),            # row 1 pattern (two same-size terms), odd sizes
+    (1, 64, 64, 24, 52, [(24, 52), (12, 26)]),
+    (1, 64, 32, 20, 40, [(20, 40), (7, 13), (3, 5)]),              # odd ratios
+])
+def test_csa_conv1_matches_two_launches(cfg):
+    """Resize-and-sum + LeakyReLU produced inside the 1x1 convolution's launch (ops.csa_conv1_nhwc) against
+    csa_fuse_nhwc followed by conv2d_nhwc, and the sum against the C oracle's resize rule through csa_fuse_nhwc
+    (tests/test_gpu_parity.py pins that one to the oracle)."""
+    import aanet_b200.ops as ops
+    B, C, Co, H, W, sizes = cfg
+    torch.manual_seed(41)
+    terms = [torch.randn(B, h, w, C, device="cuda") for h, w in sizes]
+    w1 = torch.randn(Co, C, 1, 1, device="cuda") / C ** 0.5
+    sc, sh = torch.rand(Co, device="cuda") + 0.5, torch.randn(Co, device="cuda")
+    wp = ops.pack_conv_weight(w1)
+    os.environ["AANET_CSA_CONV1"] = "1"          # opt-in (measured slower inside the pipeline, see DESIGN 4c)
+    try:
+        assert ops.csa_conv1_supported(terms, Co)
+    finally:
+        os.environ.pop("AANET_CSA_CONV1", None)
+    fused, y1 = ops.csa_conv1_nhwc(terms, 0.2, wp, Co, sc, sh, ops.ACT_RELU)
+    ref_sum = ops.csa_fuse_nhwc(terms, 0.2)
+    ref_y1 = ops.conv2d_nhwc(ref_sum, wp, Co, 1, 1, None, sc, sh, None, ops.ACT_RELU, 0.0, 1, 0, 1, 1)
+    assert fused.shape == ref_sum.shape and y1.shape == ref_y1.shape
+    assert rel_err(npy(fused), npy(ref_sum)) < 1e-6
+    assert rel_err(npy(y1), npy(ref_y1)) < 1e-5

@@ -426,3 +426,31 @@ def test_fused_softargmin_epilogue_matches_separate_kernels():
             os.environ["AANET_FUSE_SOFTARGMIN"] = old
     assert len(fused_d) == len(two) == 1 and fused_d[0].shape == two[0].shape == (2, 48, 96)
     assert float((fused_d[0] - two[0]).abs().max()) < 1e-4
+
+
+def test_csa_conv1_executor_path_matches_default():
+    """The opt-in executor path that produces the CSA sum inside the next module's conv1 launch
+    (AANET_CSA_CONV1=1, ops.csa_conv1_nhwc) against the default (csa_fuse + conv1): <= 1e-4 px."""
+    import os
+    from aanet_b200.pipeline import HotPath
+    torch.manual_seed(9)
+    hp = HotPath(192, num_deform_blocks=1, num_fusions=3).cuda().eval()
+    for name, m in hp.named_modules():
+        if name.endswith("offset_conv"):
+            torch.nn.init.normal_(m.weight, std=0.05)
+    L = [torch.relu(torch.randn(1, 32, 40 // 2 ** s, 88 // 2 ** s, device="cuda")) for s in range(3)]
+    R = [torch.relu(torch.randn(1, 32, 40 // 2 ** s, 88 // 2 ** s, device="cuda")) for s in range(3)]
+    old = os.environ.get("AANET_CSA_CONV1")
+    try:
+        os.environ["AANET_CSA_CONV1"] = "1"
+        with torch.no_grad():
+            a = hp(L, R)
+        os.environ["AANET_CSA_CONV1"] = "0"
+        with torch.no_grad():
+            b = hp(L, R)
+    finally:
+        if old is None:
+            os.environ.pop("AANET_CSA_CONV1", None)
+        else:
+            os.environ["AANET_CSA_CONV1"] = old
+    assert float((a[-1] - b[-1]).abs().max()) < 1e-4
