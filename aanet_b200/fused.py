@@ -71,8 +71,12 @@ class _Conv:
     def tmem_eligible(self):
         """Multi-tap convolution over 32-channel blocks (stride 1 or 2): runs as its own launch of the TMEM-A kernel
         (TMA-staged input patch, no per-K-block L2 round trips) instead of inside a multi-problem engine launch."""
-        return (self.kh * self.kw >= 3 and self.stride in (1, 2) and (self._w.shape[1] % 32) == 0
-                and os.environ.get("AANET_DENSE_TMEM", "1") != "0" and os.environ.get("AANET_EXCHANGE_TMEM", "1") != "0")
+        if os.environ.get("AANET_DENSE_TMEM", "1") == "0" or os.environ.get("AANET_EXCHANGE_TMEM", "1") == "0":
+            return False
+        if self.kh * self.kw == 1:       # 1x1 exchange convs as own TMEM-A launches: measured neutral (1194 vs 1191 pairs/s), opt-in
+            return (self.stride == 1 and self.pad == 0 and (self._w.shape[1] % 32) == 0 and self.groups == 1
+                    and os.environ.get("AANET_POINTWISE_TMEM", "0") == "1")
+        return self.kh * self.kw >= 3 and self.stride in (1, 2) and (self._w.shape[1] % 32) == 0
 
     def single(self, x):
         """Own launch; the N tile is at least 32 wide so that narrow outputs (the 16-channel scale) qualify too."""
