@@ -71,6 +71,7 @@ struct DeformTmemParams {
     int HH, HWd, lines, slot_bytes;    // halo box (rows, pixels per row), lines = HH * HWd, bytes rounded to 1024
     int margin_y, margin_x, n_cb, prof;   // pixels of offset the halo covers above/below and left/right
     int spin;                             // experiment: the MMA thread polls its barriers instead of sleeping on them
+    int ns_log2;                          // patch slots: 2 (log2 = 1) or 4 (log2 = 2; the 1x1 layers, whose slots hold ONE K block)
     int sb;                               // weight-ring slots: S (a block is requested when its stage frees) or 2 S
                                           // (requested one use of the stage earlier: hides the ~1500-cycle L2 fetch)
     int rot;                              // CTA b walks the taps of a channel block starting at tap b % T: the CTAs of a
@@ -208,7 +209,8 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
     constexpr int kBTile = 2 * BN * 32 * 4;                   // [B_hi | B_lo] of one K block
     static_assert(2 * BN <= 128, "accumulator stride is 128 columns");
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_halo_full[2], bar_halo_empty[2];
+    __shared__ __align__(8) uint64_t bar_halo_full[4], bar_halo_empty[4];
+    const uint32_t ns_log2 = (uint32_t)hp.ns_log2, ns_mask = (1u << ns_log2) - 1u;      // patch slot = hs & mask, phase = hs >> log2
     // Stage barriers come in PAIRS, indexed [stage + S * (use & 1)]: use p of stage s signals full / empty barrier
     // (s, p & 1), whose own phase is p >> 1.  One wait and one commit per K block for the MMA warp as before, but a
     // barrier now completes every second use of its stage, so the weight loader can wait for use p - 2 (and request
@@ -230,7 +232,7 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t *smem = smem_raw + ((1024 - (umma::smem_u32(smem_raw) & 1023)) & 1023);
     uint8_t *halo0 = smem + (size_t)hp.sb * kBTile;           // two halo slots behind the weight ring
-    uint8_t *tailw = halo0 + 2 * (size_t)hp.slot_bytes;       // TAIL: resident packed weights of the 1x1 convolution
+    uint8_t *tailw = halo0 + ((size_t)hp.slot_bytes << hp.ns_log2);       // TAIL: resident packed weights of the 1x1 convolution
     if (tid < d.K) s_tapoff[tid] = make_int2((tid / d.kw) * d.dil - d.pad, (tid % d.kw) * d.dil - d.pad);
     if (!DENSE && tid < 64) s_dgk[tid] = ((tid * 32) / max(d.Cd, 1)) * d.K;     // SUB == 2: the block's second group follows at + K
     const int T = d.K, n_cb = hp.n_cb, total = p.total_tiles;
@@ -238,7 +240,7 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
     auto phys = [&](int t_) { const int q_ = t_ + rot; return q_ >= T ? q_ - T : q_; };   // walk position -> tap
 
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < 4; ++s) {
             umma::mbar_init(&bar_halo_full[s], 1);            // expect_tx + TMA bytes
             // every producer warp, after its last tap of the slot -- or, with fewer taps than groups (the 1x1
             // convolutions), when it passes a slot it has no tap in: all groups then see every phase of both slot
@@ -491,9 +493,9 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
         for (int t = blockIdx.x; t < total; t += gridDim.x) n_my += n_cb;
         auto pass_slot = [&](uint32_t h) {                    // a slot I have no tap in: see it filled, release it
             if ((int)h >= n_my) return;
-            umma::mbar_wait(&bar_halo_full[h & 1], (h >> 1) & 1);
+            umma::mbar_wait(&bar_halo_full[h & ns_mask], (h >> ns_log2) & 1);
             __syncwarp();
-            if (lane == 0) umma::mbar_arrive(&bar_halo_empty[h & 1]);
+            if (lane == 0) umma::mbar_arrive(&bar_halo_empty[h & ns_mask]);
         };
         while (tap >= T) {                                    // ... or, with fewer taps than groups, a later block / tile
             pass_slot(hs);
@@ -510,13 +512,13 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
             // offsets / mask of my NEXT K block: each (tap, deformable group) plane is touched once per tile, so
             // these loads are DRAM misses and must be in flight while the current K block is produced
             const bool last_in_slot = tap + G >= T;           // my last tap inside this halo slot
-            const int hslot = hs & 1;
+            const int hslot = (int)(hs & ns_mask);
             const uint32_t halo = umma::smem_u32(halo0 + (size_t)hslot * hp.slot_bytes);
             if (DENSE) {
                 // the tap's input pixel of my output pixel: always inside the staged patch (margin 0); out-of-image
                 // pixels were zero-filled by the TMA unit (= the convolution's zero padding)
                 if (ready_hs != hs) {
-                    umma::mbar_wait(&bar_halo_full[hslot], (hs >> 1) & 1);
+                    umma::mbar_wait(&bar_halo_full[hslot], (hs >> ns_log2) & 1);
                     ready_hs = hs;
                 }
                 // the line is read into registers BEFORE the stage is awaited: the stage (tensor memory) is then held
@@ -651,7 +653,7 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
             }
             if (ready_hs != hs) {
                 TP(const long long t0 = clock64();)
-                umma::mbar_wait(&bar_halo_full[hslot], (hs >> 1) & 1);
+                umma::mbar_wait(&bar_halo_full[hslot], (hs >> ns_log2) & 1);
                 TP(c_wait_halo += clock64() - t0;)
                 ready_hs = hs;
             }
@@ -778,8 +780,8 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 const TItem it = t_item(p, t);
                 for (int cb = 0; cb < n_cb; ++cb, ++hs) {
-                    const int s = hs & 1;
-                    umma::mbar_wait_sleep(&bar_halo_empty[s], ((hs >> 1) & 1) ^ 1);
+                    const int s = (int)(hs & ns_mask);
+                    umma::mbar_wait_sleep(&bar_halo_empty[s], ((hs >> ns_log2) & 1) ^ 1);
                     if (FUSE) {
                         const FuseGeom &fz = hp.fz;
                         umma::mbar_expect_tx(&bar_halo_full[s], fz.bytes);
@@ -951,7 +953,7 @@ static size_t tail_bytes(const ConvParams &p, int BN) {
 template <int BN, bool DENSE, bool LEAN, int G, bool TAIL = false, int SUB = 1, bool FUSE = false>
 static int tmem_launch_g(const DeformTmemParams &hp, const CUtensorMap &tm, cudaStream_t stream,
                          const CUtensorMap *tm1 = nullptr, const CUtensorMap *tm2 = nullptr) {
-    const size_t smem = (size_t)hp.sb * 2 * BN * 32 * 4 + 2 * (size_t)hp.slot_bytes + tail_bytes(hp.p, BN) + 1024;
+    const size_t smem = (size_t)hp.sb * 2 * BN * 32 * 4 + ((size_t)hp.slot_bytes << hp.ns_log2) + tail_bytes(hp.p, BN) + 1024;
     cudaFuncSetAttribute(deform_tmem_kernel<BN, DENSE, LEAN, G, TAIL, SUB, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int rounds = ceil_div(hp.p.total_tiles, num_sms());
     const int grid = ceil_div(hp.p.total_tiles, rounds);
@@ -1017,7 +1019,12 @@ static int tmem_plan(const ConvParams &src, int BN, int margin_req, int groups, 
         const char *ed = getenv("AANET_TMEM_DEEP");
         const size_t extra = (size_t)groups * 2 * BN * 32 * 4;
         hp.sb = groups;
-        if (!(ed && ed[0] == '0') && ring + extra + 2 * (size_t)hp.slot_bytes <= (size_t)kTSmemBudget) hp.sb = 2 * groups;
+        hp.ns_log2 = 1;
+        // fewer taps than producer groups (1x1): a slot holds one K block, so two slots mean two K blocks in flight per
+        // CTA -- take four
+        const char *e4 = getenv("AANET_TMEM_SLOTS4");
+        if (d.K < groups && !(e4 && e4[0] == '0') && ring + 4 * (size_t)hp.slot_bytes <= (size_t)kTSmemBudget) hp.ns_log2 = 2;
+        if (!(ed && ed[0] == '0') && ring + extra + ((size_t)hp.slot_bytes << hp.ns_log2) <= (size_t)kTSmemBudget) hp.sb = 2 * groups;
     }
     hp.n_cb = d.Cg / 32;
     { const char *ep = getenv("AANET_HALO_PROF"); hp.prof = ep ? atoi(ep) : 0; }
@@ -1143,6 +1150,8 @@ int csa_conv1_tmem_launch(const float *const *terms, const int *th, const int *t
     hp.margin_y = hp.margin_x = 0; hp.n_cb = d.Cin / 32;
     hp.prof = 0; hp.spin = 0; hp.rot = 0; hp.sb = 3;
     if ((size_t)3 * 2 * BN * 32 * 4 + 2 * (size_t)off > (size_t)kTSmemBudget) return AANET_ERR_UNSUPPORTED;
+    { const char *e4 = getenv("AANET_TMEM_SLOTS4");
+      hp.ns_log2 = (!(e4 && e4[0] == '0') && (size_t)3 * 2 * BN * 32 * 4 + 4 * (size_t)off <= (size_t)kTSmemBudget) ? 2 : 1; }
     ConvParams &p = hp.p;
     p.n_tiles_n = 1;
     p.K = d.Cin; p.KB = p.K / 32;
