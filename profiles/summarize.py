@@ -118,8 +118,55 @@ The kernel is latency-bound in its producers (ENGINE_NOTES.md: role profile, sta
     print("traffic MB for bench.py NCU_TRAFFIC_MB: %.1f (read %.2f + written %.2f)" % (rd + wr, rd, wr))
 
 
+def write_report_r02(here):
+    """profiles/r02_launches_and_kernels.md from profiles/r02/{launches_r02.csv, step_r02_raw.csv, bench_1gpu.json}
+    (python profiles/summarize.py --write-r02)."""
+    import contextlib
+    import json
+    r = here + "/r02/"
+    buf1, buf2 = io.StringIO(), io.StringIO()
+    with contextlib.redirect_stdout(buf1):
+        launch_table(r + "launches_r02.csv")
+    with contextlib.redirect_stdout(buf2):
+        kernel_table(r + "step_r02_raw.csv", n=84)
+    t1, t2 = buf1.getvalue().rstrip("\n"), buf2.getvalue().rstrip("\n")
+    head, table = t1.split("\n", 1)
+    b = json.loads(open(r + "bench_1gpu.json").read().strip().splitlines()[-1])
+    ro = b["roofline"]
+    roof = json.load(open(here + "/ncu_roofline.json"))["mdconv"]
+    md = """# Round 2 -- ncu launch list and kernel metrics of one hot-path step (KITTI 384x1248, B = 1, eager)
+
+Generated by `python profiles/summarize.py --write-r02` from `profiles/r02/launches_r02.csv` (`ncu --metrics
+gpu__time_duration.sum --clock-control none --csv python profiles/profile_step.py --steps 3`, after the same command
+exited 0 without ncu) and `profiles/r02/step_r02_raw.csv` (`ncu --set full --clock-control none --import-source on -k
+regex:"deform_tmem|conv_umma_kernel|corr_tma|csa_fuse|softargmin" -s 228 -c 84`, exported with `--page raw --csv`; the
+.ncu-rep is ~150 MB and stays out of the repo).  Per-launch times under ncu are cold-cache and serialised (no overlap
+between the scale streams, no programmatic dependent launch): compare SHARES.  The concurrent picture is the CUPTI
+kernel timeline `r02/timeline_graph_final.txt` (`profiles/timeline.py --graph`).
+
+Last step: %s.  The same step as a CUDA-graph replay: %.3f ms (`r02/bench_1gpu.json`, %.0f pairs/s).
+
+%s
+
+Dominant kernel (`roofline` of the bench line): `%s`
+-- %d launches in the capture, %.1f us each under ncu (%.1f us live, CUDA events), DRAM %.1f MB read + %.2f MB written
+per launch (algorithmic %.1f MB incl. the output that stays in L2), tensor pipe %.1f %%, issue active %.1f %%,
+warps active %.1f %%, %d registers; tensor-pipe floor of the launch from the measured instruction times %.1f us.
+
+## `ncu --set full` rows (84 launches of step 3: modules 1-5, final stage)
+
+%s
+""" % (head, b["ms_per_step"], b["value"], table, roof["kernel"], roof["launches"], roof["duration_us"],
+       ro["us_per_launch"], roof["dram_read_mb"], roof["dram_write_mb"], ro["algorithmic_mb"], roof["tensor_pipe_pct"],
+       roof["issue_active_pct"], roof["warps_active_pct"], int(roof["registers"]), ro.get("mma_floor_us", 0.0), t2)
+    open(here + "/r02_launches_and_kernels.md", "w").write(md)
+    print("wrote", here + "/r02_launches_and_kernels.md")
+
+
 if __name__ == "__main__":
-    if "--write" in sys.argv:
+    if "--write-r02" in sys.argv:
+        write_report_r02(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+    elif "--write" in sys.argv:
         here = __import__("os").path.dirname(__import__("os").path.abspath(__file__))
         write_report(here + "/launches_r01.csv", here + "/step_r01_raw.csv", here + "/bench_r01.json",
                      here + "/r01_launches_and_engine.md")
