@@ -147,7 +147,10 @@ class HostPipeline:
     next pair on the copy stream.  `submit()` enqueues one pair and returns; `result(i)` synchronises on
     that pair's event and returns its pinned disparity."""
 
-    def __init__(self, hot_path, shapes, device, n_slots=2):
+    def __init__(self, hot_path, shapes, device, n_slots=2, dtype=torch.float32):
+        """dtype: element type of the feature pyramids on the host and across PCIe.  torch.float32 is the parity
+        path; torch.bfloat16 halves the bytes per pair (the cost volume is then computed from bf16 features,
+        ops.correlation_bf16 -- a named NON-parity mode, its end-point error is reported by bench.py)."""
         self.hp, self.device, self.n = hot_path, device, n_slots
         # pinned blocks are allocated with the process bound to the GPU's NUMA node; the caller's CPU affinity is
         # restored afterwards (first-touch placement keeps the pages node-local)
@@ -169,8 +172,8 @@ class HostPipeline:
         for _ in range(n_slots):
             # One flat device block and one flat pinned staging block per slot: a pair that is written into
             # `staging()` crosses PCIe as ONE DMA (six separate copies cost ~3 % of the transfer in set-up gaps).
-            dev_flat = torch.zeros(total, device=device)
-            host_flat = torch.zeros(total).pin_memory()
+            dev_flat = torch.zeros(total, device=device, dtype=dtype)
+            host_flat = torch.zeros(total, dtype=dtype).pin_memory()
             L, R = views(dev_flat)
             hL, hR = views(host_flat)
             with torch.cuda.stream(self.compute_stream):
@@ -184,7 +187,7 @@ class HostPipeline:
             self.slots[-1]["free"].record(self.compute_stream)
         os.sched_setaffinity(0, affinity)
         self.i = 0
-        self.h2d_bytes = 4 * total
+        self.h2d_bytes = self.slots[0]["host_flat"].element_size() * total
         self.d2h_bytes = 4 * self.slots[0]["out"].numel()
 
     def staging(self):

@@ -432,6 +432,42 @@ def run_gpu(args):
                "runs_pairs_per_s": [total_pairs_per_step * args.steps / t for t in e2e_runs],
                "stat": "median of 3 x K steps"}
 
+    # ---- the same end-to-end loop with the features crossing PCIe as bf16 (half the bytes; the cost volume is then
+    # computed from bf16 features): a named NON-parity mode, reported next to `e2e` with its end-point error
+    e2e_bf16 = None
+    if not args.no_e2e and args.config == 2 and B == 1 and world == 1 and not args.bf16_cost:
+        del pipe
+        torch.cuda.empty_cache()
+        (L32, R32), = make_inputs(1, 1, device, seed=327)
+        with torch.no_grad():
+            d32 = hp(L32, R32)[-1]
+            d16 = hp([t.bfloat16() for t in L32], [t.bfloat16() for t in R32])[-1]
+        epe16 = float((d32 - d16).abs().mean())
+        pipe16 = HostPipeline(hp, pyramid_shapes(1), device, dtype=torch.bfloat16)
+        for k, (L, R) in enumerate(make_inputs(1, pipe16.n, None, seed=327)):
+            for dst, src in zip(pipe16.slots[k]["host_L"] + pipe16.slots[k]["host_R"], L + R):
+                dst.copy_(src)
+        for i in range(max(args.warmup, 4) + args.steps):
+            HostPipeline.result(pipe16.submit())
+        runs = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            pending = []
+            for i in range(args.steps):
+                pending.append(pipe16.submit())
+                if len(pending) >= pipe16.n:
+                    HostPipeline.result(pending.pop(0))
+            for sl in pending:
+                HostPipeline.result(sl)
+            torch.cuda.synchronize(device)
+            runs.append(time.perf_counter() - t0)
+        e2e_bf16 = {"value": args.steps / statistics.median(runs), "unit": UNIT,
+                    "h2d_bytes_per_step": pipe16.h2d_bytes, "d2h_bytes_per_step": pipe16.d2h_bytes,
+                    "mean_abs_disparity_error_px_vs_fp32_features": epe16,
+                    "note": "NOT the parity path: feature pyramids are bf16 on the host and over PCIe, the cost volume is "
+                            "computed from them (ops.correlation_bf16), aggregation and regression stay fp32"}
+        del pipe16
+
     out = None
     if rank == 0:
         hbm, bf16, peak_src = load_peaks()
@@ -490,6 +526,8 @@ def run_gpu(args):
                "cpu_baseline": cpu}
         if epe is not None:
             out["bf16_cost_volume"] = epe
+        if e2e_bf16 is not None:
+            out["e2e_bf16_transport"] = e2e_bf16
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
