@@ -12,6 +12,6 @@ for (C, D, H, W) in [(128, 64, 128, 416), (128, 32, 64, 208), (128, 16, 32, 104)
     L = torch.relu(torch.randn(1, C, H, W, device="cuda"))
     R = torch.relu(torch.randn(1, C, H, W, device="cuda"))
     for _ in range(2):
-        out = ops.correlation(L, R, D)
+        out = ops.correlation_nhwc(L, R, D)
 torch.cuda.synchronize()
 print("ok", float(out.sum()))
