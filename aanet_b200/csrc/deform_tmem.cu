@@ -415,6 +415,20 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                     acc[i] = fmaf(acc[i] + acc2[i], sc.x, sh.x); acc[i + 1] = fmaf(acc[i + 1] + acc2[i + 1], sc.y, sh.y);
                     acc[i + 2] = fmaf(acc[i + 2] + acc2[i + 2], sc.z, sh.z); acc[i + 3] = fmaf(acc[i + 3] + acc2[i + 3], sc.w, sh.w);
                 }
+                if (p.residual) {                   // channels-last, same shape as the output (host-checked)
+                    if (full) {
+                        const float4 *rp = reinterpret_cast<const float4 *>(p.residual + pix_g * d.Cout + o_base + n0);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 r4 = __ldg(rp + i);
+                            acc[4 * i] += r4.x; acc[4 * i + 1] += r4.y; acc[4 * i + 2] += r4.z; acc[4 * i + 3] += r4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (n0 + i < n_valid) acc[i] += __ldg(p.residual + pix_g * d.Cout + o_base + n0 + i);
+                    }
+                }
                 if (p.act == ACT_RELU) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) acc[i] = fmaxf(acc[i], 0.f);
@@ -1077,7 +1091,9 @@ int deform_tmem_launch(const ConvParams &src, int BN, cudaStream_t stream) {
 int dense_tmem_launch(const ConvParams &src, int BN, cudaStream_t stream) {
     { const char *e = getenv("AANET_DENSE_TMEM"); if (e && e[0] == '0') return AANET_ERR_UNSUPPORTED; }   // A/B switch
     const MdcnDims &d = src.d;
-    if ((d.stride != 1 && d.stride != 2) || d.Cg % 32 || !aligned16(src.x) || src.residual || src.offset) return AANET_ERR_UNSUPPORTED;
+    if ((d.stride != 1 && d.stride != 2) || d.Cg % 32 || !aligned16(src.x) || src.offset) return AANET_ERR_UNSUPPORTED;
+    // residual: channels-last only, added after the affine and before the activation (as the round-1 engine)
+    if (src.residual && (src.out_nchw || src.tail_wpack || !aligned16(src.residual) || (d.Cout & 3))) return AANET_ERR_UNSUPPORTED;
     if (BN != 32 && BN != 48 && BN != 64) return AANET_ERR_UNSUPPORTED;
     const bool tail = src.tail_wpack != nullptr;
     if (tail && !tmem_tail_ok(src, BN)) return AANET_ERR_UNSUPPORTED;

@@ -78,10 +78,17 @@ class _Conv:
                     and os.environ.get("AANET_POINTWISE_TMEM", "0") == "1")
         return self.kh * self.kw >= 3 and self.stride in (1, 2) and (self._w.shape[1] % 32) == 0
 
-    def single(self, x):
+    def single(self, x, residual=None, act=None, slope=None):
         """Own launch; the N tile is at least 32 wide so that narrow outputs (the 16-channel scale) qualify too."""
         bn = max(32, ops.natural_bn(self.Cout // self.groups))
-        return ops.conv_batch([self.problem(x, bn)], bn=bn)[0]
+        q = self.problem(x, bn)
+        if residual is not None:
+            q["residual"] = residual
+        if act is not None:
+            q["act"] = act
+        if slope is not None:
+            q["slope"] = slope
+        return ops.conv_batch([q], bn=bn)[0]
 
     def as_tail(self, residual, act=None):
         """This (1x1) convolution as the fused tail of the preceding one (ops.conv_batch "tail")."""
@@ -179,6 +186,8 @@ class _Bottleneck:
 # One multi-problem launch for the last conv of all exchange chains of a CSA row (A/B on one box: 913 vs 910
 # pairs/s, 10 launches fewer per pair).  AANET_BATCH_EXCHANGE=0 restores one launch per conv.
 BATCH_EXCHANGE = os.environ.get("AANET_BATCH_EXCHANGE", "1") == "1"
+# Coarsest CSA row without a csa_fuse launch (sum folded into the exchange convolutions' epilogues); =0: A/B switch
+FOLD_LAST_ROW = os.environ.get("AANET_FOLD_LAST_ROW", "1") == "1"
 
 
 def _exchange(seq):
@@ -281,6 +290,24 @@ class FusedAggregation:
             nxt = self.stages[si + 1][0] if si + 1 < len(self.stages) else None
             # CSA: output scale i needs every input scale; the output scales are independent
             def fuse_row(i, row, xs=xs, nxt=nxt):
+                def go_folded():
+                    # coarsest output scale: every term has the output's size, so the sum needs no resize kernel --
+                    # each exchange chain's last convolution adds the running sum as its residual and the last one
+                    # applies the LeakyReLU (aggregation.py:387-400; (t0 + t1) + t2 is evaluated as t0 + (t1 + t2)).
+                    # The stage's critical chain (1/3 -> 1/6 -> 1/12) runs last and loses the csa_fuse launch.
+                    acc = xs[i]
+                    chains = sorted([(j, c) for j, c in enumerate(row) if c], key=lambda jc: len(jc[1]))
+                    for n, (j, chain) in enumerate(chains):
+                        t = xs[j]
+                        for conv in chain[:-1]:
+                            t = conv.single(t) if conv.tmem_eligible() else conv(t)
+                        act = ops.ACT_LEAKY if n == len(chains) - 1 else ops.ACT_NONE
+                        acc = chain[-1].single(t, residual=acc, act=act, slope=slope)
+                    return acc, None
+                if FOLD_LAST_ROW and i == len(row) - 1 and i > 0 and not row[i] and \
+                        all(c and c[-1].act == ops.ACT_NONE and c[-1].bias is None for j, c in enumerate(row) if j != i):
+                    return go_folded
+
                 def go():
                     # the last conv of every exchange chain of this row in ONE multi-problem launch (they are
                     # independent and all produce this row's channel count); longer chains run their head first

@@ -250,3 +250,25 @@ def test_csa_conv1_matches_two_launches(cfg):
     assert fused.shape == ref_sum.shape and y1.shape == ref_y1.shape
     assert rel_err(npy(fused), npy(ref_sum)) < 1e-6
     assert rel_err(npy(y1), npy(ref_y1)) < 1e-5
+
+
+@pytest.mark.parametrize("cfg", [(1, 64, 16, 64, 208), (2, 32, 16, 17, 35), (1, 64, 64, 24, 52)])
+def test_strided_dense_tmem_residual_vs_float64(cfg):
+    """out = LeakyReLU(bn(conv3x3 stride 2) + residual) in the TMEM-A kernel's epilogue: how the coarsest CSA row folds
+    its sum into the exchange convolutions (aggregation.py:387-400)."""
+    import aanet_b200.ops as ops
+    B, Ci, Co, H, W = cfg
+    torch.manual_seed(43)
+    x = torch.randn(B, H, W, Ci, device="cuda")
+    w = torch.randn(Co, Ci, 3, 3, device="cuda") / (Ci * 9) ** 0.5
+    sc, sh = torch.rand(Co, device="cuda") + 0.5, torch.randn(Co, device="cuda")
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    res = torch.randn(B, Ho, Wo, Co, device="cuda")
+    bn = max(32, ops.natural_bn(Co))
+    q = dict(x=x, wpack=ops.pack_conv_weight(w, 1, bn), Cout=Co, kh=3, kw=3, scale=sc, shift=sh, act=ops.ACT_LEAKY,
+             slope=0.2, stride=2, pad=1, dil=1, groups=1, residual=res)
+    got = ops.conv_batch([q], bn=bn)[0]
+    ref = torch.nn.functional.leaky_relu(
+        torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), None, 2, 1) * sc.view(1, -1, 1, 1)
+        + sh.view(1, -1, 1, 1) + res.permute(0, 3, 1, 2), 0.2)
+    assert rel_err(npy(got.permute(0, 3, 1, 2)), npy(ref)) < 1e-5
