@@ -188,6 +188,7 @@ class _Bottleneck:
 BATCH_EXCHANGE = os.environ.get("AANET_BATCH_EXCHANGE", "1") == "1"
 # Coarsest CSA row without a csa_fuse launch (sum folded into the exchange convolutions' epilogues); =0: A/B switch
 FOLD_LAST_ROW = os.environ.get("AANET_FOLD_LAST_ROW", "1") == "1"
+FOLD_PARALLEL = os.environ.get("AANET_FOLD_PARALLEL", "0") == "1"      # measured slower (1199 vs 1222 pairs/s)
 
 
 def _exchange(seq):
@@ -295,15 +296,26 @@ class FusedAggregation:
                     # each exchange chain's last convolution adds the running sum as its residual and the last one
                     # applies the LeakyReLU (aggregation.py:387-400; (t0 + t1) + t2 is evaluated as t0 + (t1 + t2)).
                     # The stage's critical chain (1/3 -> 1/6 -> 1/12) runs last and loses the csa_fuse launch.
-                    acc = xs[i]
                     chains = sorted([(j, c) for j, c in enumerate(row) if c], key=lambda jc: len(jc[1]))
-                    for n, (j, chain) in enumerate(chains):
-                        t = xs[j]
+
+                    def head(chain, x):                 # everything but the last convolution of a chain
                         for conv in chain[:-1]:
-                            t = conv.single(t) if conv.tmem_eligible() else conv(t)
-                        act = ops.ACT_LEAKY if n == len(chains) - 1 else ops.ACT_NONE
-                        acc = chain[-1].single(t, residual=acc, act=act, slope=slope)
-                    return acc, None
+                            x = conv.single(x) if conv.tmem_eligible() else conv(x)
+                        return x
+
+                    def shorter():                      # the shorter chains, summed onto the identity term
+                        acc = xs[i]
+                        for j, chain in chains[:-1]:
+                            acc = chain[-1].single(head(chain, xs[j]), residual=acc, act=ops.ACT_NONE)
+                        return acc
+                    jl, longest = chains[-1]
+                    if len(longest) > 1 and len(chains) > 1 and FOLD_PARALLEL:
+                        # the long chain's head does not need the running sum: next to the shorter chains
+                        t, acc = fork_join(dev, [lambda: head(longest, xs[jl]), shorter], first=len(fuse))
+                    else:
+                        acc = shorter()
+                        t = head(longest, xs[jl])
+                    return longest[-1].single(t, residual=acc, act=ops.ACT_LEAKY, slope=slope), None
                 if FOLD_LAST_ROW and i == len(row) - 1 and i > 0 and not row[i] and \
                         all(c and c[-1].act == ops.ACT_NONE and c[-1].bias is None for j, c in enumerate(row) if j != i):
                     return go_folded

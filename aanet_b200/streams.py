@@ -23,20 +23,22 @@ import torch
 _side = {}
 
 
-def side_streams(device, n):
+def side_streams(device, n, first=0):
     key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
     pool = _side.setdefault(key, [])
-    while len(pool) < n:
+    while len(pool) < first + n:
         pool.append(torch.cuda.Stream(device))
-    return pool[:n]
+    return pool[first:first + n]
 
 
 # A/B switch: AANET_FORK_ORDER=1 enqueues the main branch before the side branches
 LEAD_FIRST = os.environ.get("AANET_FORK_ORDER", "0") == "1"
 
 
-def fork_join(device, fns):
-    """Run fns[0] on the current stream and fns[1:] on side streams; returns their results in order."""
+def fork_join(device, fns, first=0):
+    """Run fns[0] on the current stream and fns[1:] on side streams; returns their results in order.
+    first: index of the first side stream of the pool to use (a fork nested inside a branch of another fork must
+    not share its side streams)."""
     if len(fns) == 1:
         return [fns[0]()]
     main = torch.cuda.current_stream(device)
@@ -46,7 +48,7 @@ def fork_join(device, fns):
     done = []
     if LEAD_FIRST:
         results[0] = fns[0]()
-    for i, (fn, s) in enumerate(zip(fns[1:], side_streams(device, len(fns) - 1)), 1):
+    for i, (fn, s) in enumerate(zip(fns[1:], side_streams(device, len(fns) - 1, first)), 1):
         s.wait_event(start)
         with torch.cuda.stream(s):
             results[i] = fn()
