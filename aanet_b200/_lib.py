@@ -40,7 +40,7 @@ SIGNATURES = {
     "aanet_conv_batch_nhwc": (_i, [_vp, _i, _i, _i, _vp]),
     "aanet_conv_tail_supported": (_i, [_vp, _i]),
     "aanet_csa_fuse_nhwc": (_i, [_vp, _vp, _vp, _i, _vp] + [_i] * 4 + [_f, _vp]),
-    "aanet_csa_conv1_nhwc": (_i, [_vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _i, _vp] + [_i] * 5 + [_vp]),
+    "aanet_csa_conv1_nhwc": (_i, [_vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp] + [_i] * 5 + [_vp]),
     "aanet_csa_fuse_fwd": (_i, [_vp, _vp, _vp, _i, _vp] + [_i] * 4 + [_f, _vp]),
     "aanet_csa_fuse_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i] + [_i] * 4 + [_f, _vp]),
 }

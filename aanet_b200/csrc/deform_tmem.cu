@@ -401,6 +401,7 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
             const bool vec_ok = !p.out_nchw && ((d.Cout | o_base) & 3) == 0;
             umma::mbar_wait_sleep(&bar_acc_full[a], (ti >> 1) & 1);
             umma::tc_fence_after();
+            float sm_m = -INFINITY, sm_s = 0.f, sm_w = 0.f;   // ACT_SOFTARGMIN: running max / sum / weighted sum
 #pragma unroll 1
             for (int n0 = 0; n0 < BN; n0 += 16) {
                 float acc[16], acc2[16];
@@ -439,6 +440,22 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
                         if (o_base + n0 + i >= p.n_offset_ch) acc[i] = __fdividef(p.mask_scale, 1.f + __expf(-acc[i]));
+                } else if (!LEAN && p.act == ACT_SOFTARGMIN) {
+                    // online softmax over my pixel's disparity candidates (= output channels, one N tile), as the
+                    // round-1 engine's epilogue and softargmin_fwd_kernel
+                    float cm = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (n0 + i < n_valid) cm = fmaxf(cm, acc[i]);
+                    const float nm = fmaxf(sm_m, cm), r = __expf(sm_m - nm);
+                    sm_s *= r; sm_w *= r; sm_m = nm;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (n0 + i < n_valid) {
+                            const float e = __expf(acc[i] - nm);
+                            sm_s += e; sm_w = fmaf(e, (float)(o_base + n0 + i), sm_w);
+                        }
+                    continue;
                 }
                 if (full) {
                     float4 *dst = reinterpret_cast<float4 *>(p.out + pix_g * d.Cout + o_base + n0);
@@ -455,6 +472,7 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                         if (n0 + i < n_valid) dst[i] = acc[i];
                 }
             }
+            if (!LEAN && p.act == ACT_SOFTARGMIN && p_ok) p.out[pix_g] = __fdividef(sm_w, sm_s);
             umma::tc_fence_before();
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(&bar_acc_empty[a]);
@@ -591,7 +609,7 @@ deform_tmem_kernel(const __grid_constant__ DeformTmemParams hp, const __grid_con
                     for (int c = 0; c < 8; ++c) {
                         qd[c].x = qd[c].x > 0.f ? qd[c].x : qd[c].x * fz.slope; qd[c].y = qd[c].y > 0.f ? qd[c].y : qd[c].y * fz.slope;
                         qd[c].z = qd[c].z > 0.f ? qd[c].z : qd[c].z * fz.slope; qd[c].w = qd[c].w > 0.f ? qd[c].w : qd[c].w * fz.slope;
-                        if (tl.ok) dst[c] = qd[c];
+                        if (tl.ok && fz.out) dst[c] = qd[c];
                     }
                 } else {
                 const int l0 = (tl.oh * d.stride + tapo.x - tl.hy0) * hp.HWd + (tl.ow * d.stride + tapo.y - tl.hx0);
@@ -1134,8 +1152,10 @@ int csa_conv1_tmem_launch(const float *const *terms, const int *th, const int *t
     const MdcnDims &d = conv.d;
     if (n_terms < 1 || n_terms > kFuseMaxTerms || d.K != 1 || d.stride != 1 || d.pad != 0 || d.groups != 1) return AANET_ERR_UNSUPPORTED;
     if (d.Cin % 32 || d.Cin > 64 * 32 || (d.Cout != 32 && d.Cout != 64) || conv.out_nchw || conv.residual || conv.tail_wpack ||
-        conv.act == ACT_OFFSET_MASK || conv.act == ACT_SOFTARGMIN || !fused_out)
+        conv.act == ACT_OFFSET_MASK)
         return AANET_ERR_UNSUPPORTED;
+    // fused_out == NULL: the sum is only consumed by the convolution (the last module: final 1x1 + soft-argmin)
+    if (fused_out && !aligned16(fused_out)) return AANET_ERR_UNSUPPORTED;
     DeformTmemParams hp;
     hp.p = conv;
     hp.p.x = terms[0];
@@ -1177,6 +1197,9 @@ int csa_conv1_tmem_launch(const float *const *terms, const int *th, const int *t
     if ((long)p.n_ptiles > 0x3fffffffL) return AANET_ERR_UNSUPPORTED;
     p.total_tiles = p.n_ptiles;
     const CUtensorMap *t1 = n_terms > 1 ? &tms[1] : nullptr, *t2 = n_terms > 2 ? &tms[2] : nullptr;
+    if (conv.act == ACT_SOFTARGMIN)     // non-lean epilogue: reduces the candidates to one disparity per pixel
+        return BN == 64 ? tmem_launch_g<64, true, false, 3, false, 1, true>(hp, tms[0], stream, t1, t2)
+                        : tmem_launch_g<32, true, false, 3, false, 1, true>(hp, tms[0], stream, t1, t2);
     return BN == 64 ? tmem_launch_g<64, true, true, 3, false, 1, true>(hp, tms[0], stream, t1, t2)
                     : tmem_launch_g<32, true, true, 3, false, 1, true>(hp, tms[0], stream, t1, t2);
 }

@@ -199,18 +199,19 @@ extern "C" int aanet_conv_batch_nhwc(const aanet_conv_desc *descs, int n, int de
 }
 
 extern "C" int aanet_csa_conv1_nhwc(const float *const *terms, const int *th, const int *tw, int n_terms, float slope,
-                                    float *fused_out, const void *wpack, const float *scale, const float *shift,
-                                    int act, float *out, int B, int C, int Cout, int H, int W, void *stream) {
-    if (!terms || !th || !tw || !fused_out || !wpack || !out) return AANET_ERR_NULL;
+                                    float *fused_out, const void *wpack, const float *bias, const float *scale,
+                                    const float *shift, int act, float *out, int B, int C, int Cout, int H, int W,
+                                    void *stream) {
+    if (!terms || !th || !tw || !wpack || !out) return AANET_ERR_NULL;
     if ((scale == nullptr) != (shift == nullptr)) return AANET_ERR_NULL;
     if (n_terms < 1 || n_terms > AANET_CSA_MAX_TERMS) return AANET_ERR_SHAPE;
-    if (act < ACT_NONE || act > ACT_LEAKY) return AANET_ERR_UNSUPPORTED;
+    if ((act < ACT_NONE || act > ACT_LEAKY) && act != ACT_SOFTARGMIN) return AANET_ERR_UNSUPPORTED;
     MdcnDims d;
     const int rc = mdcn_make_dims(d, B, C, H, W, Cout, 1, 1, 1, 0, 1, 1, 1);
     if (rc) return rc;
-    if (!aligned16(wpack) || !aligned16(out) || !aligned16(fused_out)) return AANET_ERR_UNSUPPORTED;
+    if (!aligned16(wpack) || (act != ACT_SOFTARGMIN && !aligned16(out))) return AANET_ERR_UNSUPPORTED;
     ConvParams p{};
-    p.wpack = static_cast<const float *>(wpack); p.out = out; p.scale = scale; p.shift = shift;
+    p.wpack = static_cast<const float *>(wpack); p.out = out; p.bias = bias; p.scale = scale; p.shift = shift;
     p.act = act; p.slope = slope; p.mask_scale = 1.f;
     p.d = d;
     return csa_conv1_tmem_launch(terms, th, tw, n_terms, slope, fused_out, p, as_stream(stream));

@@ -188,6 +188,8 @@ class _Bottleneck:
 BATCH_EXCHANGE = os.environ.get("AANET_BATCH_EXCHANGE", "1") == "1"
 # Coarsest CSA row without a csa_fuse launch (sum folded into the exchange convolutions' epilogues); =0: A/B switch
 FOLD_LAST_ROW = os.environ.get("AANET_FOLD_LAST_ROW", "1") == "1"
+# last module: sum + final 1x1 + soft-argmin as one launch (ops.csa_conv1_nhwc, ACT_SOFTARGMIN); =0: A/B switch
+FUSE_FINAL = os.environ.get("AANET_FUSE_FINAL", "1") == "1"
 FOLD_PARALLEL = os.environ.get("AANET_FOLD_PARALLEL", "0") == "1"      # measured slower (1199 vs 1222 pairs/s)
 
 
@@ -289,8 +291,12 @@ class FusedAggregation:
             if fuse is None:
                 continue
             nxt = self.stages[si + 1][0] if si + 1 < len(self.stages) else None
+            # last module + disparity requested: its sum, the final 1x1 convolution and the soft-argmin in ONE launch
+            # (nothing else runs at that point, so the whole-SM CTAs of the fused kernel cost nothing)
+            to_disp = (disparity and nxt is None and len(fuse) == 1 and len(self.final) == 1 and FUSE_FINAL
+                       and self.disparity_fusable())
             # CSA: output scale i needs every input scale; the output scales are independent
-            def fuse_row(i, row, xs=xs, nxt=nxt):
+            def fuse_row(i, row, xs=xs, nxt=nxt, to_disp=to_disp):
                 def go_folded():
                     # coarsest output scale: every term has the output's size, so the sum needs no resize kernel --
                     # each exchange chain's last convolution adds the running sum as its residual and the last one
@@ -345,6 +351,10 @@ class FusedAggregation:
                     else:
                         for j, (c, t) in zip(where, last):
                             terms[j] = c(t)
+                    if to_disp and ops.csa_conv1_supported(terms, self.final[0].Cout, force=True):
+                        f = self.final[0]
+                        return ops.csa_conv1_nhwc(terms, slope, f.wpack, f.Cout, f.scale, f.shift,
+                                                  ops.ACT_SOFTARGMIN, bias=f.bias, keep_sum=False)    # (None, disparity)
                     if nxt is not None and i < len(nxt) and nxt[i][0].conv1_fusable() and \
                             ops.csa_conv1_supported(terms, nxt[i][0].c1.Cout):
                         c1 = nxt[i][0].c1           # the next module's conv1 consumes the sum inside the same launch
@@ -352,6 +362,8 @@ class FusedAggregation:
                     return ops.csa_fuse_nhwc(terms, slope), None
                 return go
             got = fork_join(dev, [fuse_row(i, row) for i, row in enumerate(fuse)])
+            if to_disp and got[0][0] is None:
+                return [got[0][1]]                  # the disparity of the finest scale
             xs, pre = [g[0] for g in got], [g[1] for g in got]
             pre += [None] * (len(branches) - len(pre))
         if disparity:

@@ -546,9 +546,11 @@ def csa_fuse_nhwc(terms, slope=0.2):
     return out
 
 
-def csa_conv1_supported(terms, Cout):
-    """Can csa_conv1_nhwc run these terms (first one sets the output size) and a 1x1 convolution to Cout channels?"""
-    if os.environ.get("AANET_CSA_CONV1", "0") != "1" or not 1 <= len(terms) <= 3 or Cout not in (32, 64):
+def csa_conv1_supported(terms, Cout, force=False):
+    """Can csa_conv1_nhwc run these terms (first one sets the output size) and a 1x1 convolution to Cout channels?
+    Inside the aggregation stages the fused launch is opt-in (AANET_CSA_CONV1=1: it measured slower there, DESIGN 4c);
+    force=True asks for the shape check only (the last module, where nothing runs next to it)."""
+    if (not force and os.environ.get("AANET_CSA_CONV1", "0") != "1") or not 1 <= len(terms) <= 3 or Cout not in (32, 64):
         return False
     B, H, W, C = terms[0].shape
     if C % 32:
@@ -556,10 +558,10 @@ def csa_conv1_supported(terms, Cout):
     return all((t.shape[1] == H and t.shape[2] == W) or (t.shape[1] < H and t.shape[2] < W) for t in terms)
 
 
-def csa_conv1_nhwc(terms, slope, wpack, Cout, scale=None, shift=None, act=ACT_RELU):
+def csa_conv1_nhwc(terms, slope, wpack, Cout, scale=None, shift=None, act=ACT_RELU, bias=None, keep_sum=True):
     """CSA resize-and-sum + LeakyReLU (aggregation.py:387-400) and the following 1x1 convolution + folded BN +
-    activation (conv1 of the next bottleneck, deform.py:164-170) as one launch.  Returns (sum [B,H,W,C],
-    conv output [B,H,W,Cout])."""
+    activation (conv1 of the next bottleneck, deform.py:164-170) as one launch.  Returns (sum [B,H,W,C] or None when
+    keep_sum is False, conv output [B,H,W,Cout] -- or the soft-argmin disparity [B,H,W] for act = ACT_SOFTARGMIN)."""
     B, H, W, C = terms[0].shape
     n = len(terms)
     dev = terms[0].device
@@ -567,16 +569,16 @@ def csa_conv1_nhwc(terms, slope, wpack, Cout, scale=None, shift=None, act=ACT_RE
         _cl(t, "csa term", dev)
         if t.dim() != 4 or t.shape[0] != B or t.shape[3] != C:
             raise ValueError("csa_conv1_nhwc: all terms must be [B,h,w,C] with the same B and C")
-    for nm, v in (("scale", scale), ("shift", shift)):
+    for nm, v in (("bias", bias), ("scale", scale), ("shift", shift)):
         _cl(v, nm, dev, (Cout,))
     th = (ctypes.c_int * n)(*[t.shape[1] for t in terms])
     tw = (ctypes.c_int * n)(*[t.shape[2] for t in terms])
-    fused = terms[0].new_empty(B, H, W, C)
-    out = terms[0].new_empty(B, H, W, Cout)
+    fused = terms[0].new_empty(B, H, W, C) if keep_sum else None
+    out = terms[0].new_empty((B, H, W) if int(act) == ACT_SOFTARGMIN else (B, H, W, Cout))
     with torch.cuda.device(dev):
-        _lib.check(_lib.load().aanet_csa_conv1_nhwc(_term_arrays(terms), th, tw, n, float(slope), _ptr(fused),
-                                                    wpack.data_ptr(), _dp(scale), _dp(shift), int(act), _ptr(out),
-                                                    B, C, Cout, H, W, _stream(out)), "aanet_csa_conv1_nhwc")
+        _lib.check(_lib.load().aanet_csa_conv1_nhwc(_term_arrays(terms), th, tw, n, float(slope), _dp(fused),
+                                                    wpack.data_ptr(), _dp(bias), _dp(scale), _dp(shift), int(act),
+                                                    _ptr(out), B, C, Cout, H, W, _stream(out)), "aanet_csa_conv1_nhwc")
     _count()
     return fused, out
 

@@ -230,14 +230,18 @@ AANET_API int aanet_csa_fuse_nhwc(const float *const *terms, const int *th, cons
 /* aanet_csa_fuse_nhwc fused with the 1x1 convolution that follows it -- the tail of AdaptiveAggregationModule.forward
  * (nets/aggregation.py:387-400) and conv1 + bn1 + ReLU of the next module's bottleneck (nets/deform.py:164-170,
  * :216-222) as ONE launch:
- *   fused_out = LeakyReLU_slope( sum_k resize(terms[k]) )                       [B][H*W][C], written once
- *   out       = act( conv1x1(fused_out, wpack) * scale + shift )                [B][H*W][Cout]
+ *   fused_out = LeakyReLU_slope( sum_k resize(terms[k]) )                       [B][H*W][C], written once; may be
+ *                                                                               NULL (only the convolution needs it)
+ *   out       = act( (conv1x1(fused_out, wpack) + bias) * scale + shift )       [B][H*W][Cout]
  * terms[k] is (H, W)-sized or smaller in both axes (bilinear, align_corners = False); C % 32 == 0, Cout 32 or 64,
- * wpack from aanet_conv_pack_weights (kh = kw = 1).  act: 0 none, 1 ReLU, 2 LeakyReLU(slope).
- * AANET_ERR_UNSUPPORTED otherwise (the caller then issues aanet_csa_fuse_nhwc and the convolution). */
+ * wpack from aanet_conv_pack_weights (kh = kw = 1); bias / scale+shift optional.  act: 0 none, 1 ReLU,
+ * 2 LeakyReLU(slope), 4 soft-argmin over the Cout channels (`out` is then [B][H*W]: the last aggregation module's
+ * sum, the final 1x1 convolution (nets/aggregation.py:443-450) and DisparityEstimation (nets/estimation.py:19-28)
+ * in one launch).  AANET_ERR_UNSUPPORTED otherwise (the caller then issues aanet_csa_fuse_nhwc and the convolution). */
 AANET_API int aanet_csa_conv1_nhwc(const float *const *terms, const int *th, const int *tw, int n_terms, float slope,
-                                   float *fused_out, const void *wpack, const float *scale, const float *shift,
-                                   int act, float *out, int B, int C, int Cout, int H, int W, void *stream);
+                                   float *fused_out, const void *wpack, const float *bias, const float *scale,
+                                   const float *shift, int act, float *out, int B, int C, int Cout, int H, int W,
+                                   void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Cross-scale aggregation fuse.  Replaces the resize + sum + LeakyReLU tail of

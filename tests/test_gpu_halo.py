@@ -272,3 +272,24 @@ def test_strided_dense_tmem_residual_vs_float64(cfg):
         torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), None, 2, 1) * sc.view(1, -1, 1, 1)
         + sh.view(1, -1, 1, 1) + res.permute(0, 3, 1, 2), 0.2)
     assert rel_err(npy(got.permute(0, 3, 1, 2)), npy(ref)) < 1e-5
+
+
+@pytest.mark.parametrize("cfg", [(1, 64, 128, 416, [(128, 416), (64, 208), (32, 104)]), (2, 32, 33, 47, [(33, 47), (17, 24)])])
+def test_csa_final_softargmin_matches_three_kernels(cfg):
+    """Last aggregation module: resize-and-sum + LeakyReLU, the final 1x1 convolution (with bias) and the soft-argmin
+    as ONE launch (ops.csa_conv1_nhwc, ACT_SOFTARGMIN, the sum is not written) against csa_fuse_nhwc + conv2d_nhwc +
+    soft_argmin: <= 1e-4 px."""
+    import aanet_b200.ops as ops
+    B, C, H, W, sizes = cfg
+    torch.manual_seed(47)
+    terms = [torch.randn(B, h, w, C, device="cuda") for h, w in sizes]
+    w1 = torch.randn(C, C, 1, 1, device="cuda") / C ** 0.5
+    bias = torch.randn(C, device="cuda")
+    wp = ops.pack_conv_weight(w1)
+    assert ops.csa_conv1_supported(terms, C, force=True)
+    none, disp = ops.csa_conv1_nhwc(terms, 0.2, wp, C, None, None, ops.ACT_SOFTARGMIN, bias=bias, keep_sum=False)
+    assert none is None and disp.shape == (B, H, W)
+    vol = ops.conv2d_nhwc(ops.csa_fuse_nhwc(terms, 0.2), wp, C, 1, 1, bias, None, None, None, ops.ACT_NONE, 0.0, 1, 0, 1, 1,
+                          out_nchw=True)
+    ref = ops.soft_argmin(vol, True)
+    assert float((disp - ref).abs().max()) < 1e-4
