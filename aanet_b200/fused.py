@@ -190,6 +190,8 @@ BATCH_EXCHANGE = os.environ.get("AANET_BATCH_EXCHANGE", "1") == "1"
 FOLD_LAST_ROW = os.environ.get("AANET_FOLD_LAST_ROW", "1") == "1"
 # last module: sum + final 1x1 + soft-argmin as one launch (ops.csa_conv1_nhwc, ACT_SOFTARGMIN); =0: A/B switch
 FUSE_FINAL = os.environ.get("AANET_FUSE_FINAL", "1") == "1"
+# opt-in: exchange convolutions that only need a coarse scale's output run inside that scale's ISA branch
+EARLY_EXCHANGE = os.environ.get("AANET_EARLY_EXCHANGE", "0") == "1"     # measured slower (1188 vs 1231 pairs/s): SM-time is the currency
 FOLD_PARALLEL = os.environ.get("AANET_FOLD_PARALLEL", "0") == "1"      # measured slower (1199 vs 1222 pairs/s)
 
 
@@ -271,11 +273,45 @@ class FusedAggregation:
         ~6 volumes of the 1/3-scale size per pair instead of the ~70 a keep-everything plan holds."""
         dev = cost_volume[0].device
 
-        def branch(blocks, x, y1=None):
+        def folded(i, row):
+            """Row i of a CSA stage whose sum is folded into the exchange convolutions' epilogues (see go_folded)."""
+            return (FOLD_LAST_ROW and i == len(row) - 1 and i > 0 and not row[i] and
+                    all(c and c[-1].act == ops.ACT_NONE and c[-1].bias is None for j, c in enumerate(row) if j != i))
+
+        def run_chain(chain, x, **last):
+            for conv in chain[:-1]:
+                x = conv.single(x) if conv.tmem_eligible() else conv(x)
+            c = chain[-1]
+            return c.single(x, **last) if (last or c.tmem_eligible()) else c(x)
+
+        def branch(s, blocks, x, y1, fuse, early):
+            """ISA branch of scale s, followed -- for the coarser scales, which finish long before the 1/3 scale --
+            by the exchange convolutions of the coming CSA stage that only need this scale's output
+            (aggregation.py:346-371): they leave the CSA stage's critical path.  The coarsest row's running sum
+            (go_folded) travels from stream to stream with an event."""
             def go():
                 y = blocks[0](x, y1)
                 for blk in blocks[1:]:
                     y = blk(y)
+                if fuse is None or s == 0 or not EARLY_EXCHANGE:
+                    return y
+                for i, row in enumerate(fuse):
+                    chain = row[s] if s < len(row) else ()
+                    if folded(i, row):
+                        if s == i:                                  # identity term starts the running sum
+                            ev = torch.cuda.Event()
+                            ev.record(torch.cuda.current_stream(dev))
+                            early[("acc", i)] = (y, ev)
+                        elif chain and ("acc", i) in early:
+                            acc, ev = early[("acc", i)]
+                            torch.cuda.current_stream(dev).wait_event(ev)
+                            acc = run_chain(chain, y, residual=acc, act=ops.ACT_NONE)
+                            ev = torch.cuda.Event()
+                            ev.record(torch.cuda.current_stream(dev))
+                            early[("acc", i)] = (acc, ev)
+                            early[(i, s)] = True
+                    elif chain:
+                        early[(i, s)] = run_chain(chain, y)
                 return y
             return go
 
@@ -286,7 +322,11 @@ class FusedAggregation:
         pre = [None] * len(xs)                  # conv1 outputs of the next stage, where the CSA launch produced them
         for si, (branches, fuse, slope) in enumerate(self.stages):
             # ISA: the scales are independent -> one stream each
-            xs = fork_join(dev, [branch(blocks, xs[s], pre[s]) for s, blocks in enumerate(branches)])
+            # (coarsest scale first in program order: the folded row's running sum starts there)
+            early = {}
+            order = [0] + list(range(len(branches) - 1, 0, -1))
+            got = fork_join(dev, [branch(s, branches[s], xs[s], pre[s], fuse, early) for s in order])
+            xs = [got[order.index(s)] for s in range(len(branches))]
             pre = [None] * len(xs)
             if fuse is None:
                 continue
@@ -296,13 +336,14 @@ class FusedAggregation:
             to_disp = (disparity and nxt is None and len(fuse) == 1 and len(self.final) == 1 and FUSE_FINAL
                        and self.disparity_fusable())
             # CSA: output scale i needs every input scale; the output scales are independent
-            def fuse_row(i, row, xs=xs, nxt=nxt, to_disp=to_disp):
+            def fuse_row(i, row, xs=xs, nxt=nxt, to_disp=to_disp, early=early):
                 def go_folded():
                     # coarsest output scale: every term has the output's size, so the sum needs no resize kernel --
                     # each exchange chain's last convolution adds the running sum as its residual and the last one
                     # applies the LeakyReLU (aggregation.py:387-400; (t0 + t1) + t2 is evaluated as t0 + (t1 + t2)).
                     # The stage's critical chain (1/3 -> 1/6 -> 1/12) runs last and loses the csa_fuse launch.
-                    chains = sorted([(j, c) for j, c in enumerate(row) if c], key=lambda jc: len(jc[1]))
+                    chains = sorted([(j, c) for j, c in enumerate(row) if c and (i, j) not in early],
+                                    key=lambda jc: len(jc[1]))
 
                     def head(chain, x):                 # everything but the last convolution of a chain
                         for conv in chain[:-1]:
@@ -310,7 +351,7 @@ class FusedAggregation:
                         return x
 
                     def shorter():                      # the shorter chains, summed onto the identity term
-                        acc = xs[i]
+                        acc = early[("acc", i)][0] if ("acc", i) in early else xs[i]
                         for j, chain in chains[:-1]:
                             acc = chain[-1].single(head(chain, xs[j]), residual=acc, act=ops.ACT_NONE)
                         return acc
@@ -322,8 +363,7 @@ class FusedAggregation:
                         acc = shorter()
                         t = head(longest, xs[jl])
                     return longest[-1].single(t, residual=acc, act=ops.ACT_LEAKY, slope=slope), None
-                if FOLD_LAST_ROW and i == len(row) - 1 and i > 0 and not row[i] and \
-                        all(c and c[-1].act == ops.ACT_NONE and c[-1].bias is None for j, c in enumerate(row) if j != i):
+                if folded(i, row):
                     return go_folded
 
                 def go():
@@ -331,6 +371,9 @@ class FusedAggregation:
                     # independent and all produce this row's channel count); longer chains run their head first
                     terms, last, where = [], [], []
                     for j, chain in enumerate(row):
+                        if (i, j) in early:                         # computed inside the ISA branch of scale j
+                            terms.append(early[(i, j)])
+                            continue
                         t = xs[j]
                         for conv in chain[:-1]:
                             t = conv.single(t) if conv.tmem_eligible() else conv(t)
