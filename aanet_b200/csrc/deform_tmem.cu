@@ -22,11 +22,21 @@
 // 128 B/clk (profiles/r02: deform_halo 50 % LSU + tensor reads).  Keeping A in TMEM removes 88 KB of the 180 KB.
 //
 // Roles (640 threads): warps 0-3 epilogue (TMEM lane quarters), 4-15 producers (3 groups x 4 warps, warp % 4 =
-// lane quarter; group g owns A stage g), 16 halo TMA, 17 weight loader, 18 MMA issuer, 19 idle.
-// TMEM (512 columns): two accumulators of 2 BN columns, three A stages of 64 columns (32 hi + 32 lo).
-// Requirements: stride 1, channels per conv group and per deformable group multiples of 32, channels-last output
-// with a multiple of 16 channels per group, no residual -- the ISA layer of nets/deform.py:216-236 as the fused
-// executor calls it.  Everything else takes the round-1 engine.
+// lane quarter; group g owns A stage g), 16 halo TMA, 17 weight loader, 18 MMA warp (warp-uniform loop, one elected
+// lane issues), 19 idle.  setmaxnreg: producers 112, epilogue 96, control warps 40.
+// TMEM (512 columns): two accumulators of 2 BN columns, three A stages of 64 columns (32 hi + 32 lo), 64 columns for
+// the fused tail's accumulator.
+// What the template covers (round 2):
+//   DENSE = false  DCNv2, stride 1, deformable groups of >= 32 channels (SUB = 1) or of 16 (SUB = 2: two samples per
+//                  K block -- the 1/6 scale); offsets / mask of the next K block arrive through cp.async slots
+//   DENSE = true   ordinary convolutions over 32-channel blocks: stride 1 or 2, any tap count including 1x1 (fewer
+//                  taps than producer groups: the groups pass every patch slot in order), optional channels-last
+//                  residual, the offset / mask head epilogue, the soft-argmin epilogue (non-LEAN)
+//   TAIL           + the bottleneck's trailing 1x1 convolution + bn + identity + activation from the activated tile
+//   FUSE           the 1x1 convolution's input is the CSA cross-scale sum, produced by the A producers from TMA boxes
+//                  of the terms (csa_conv1_tmem_launch)
+// Everything else (channel counts that are not multiples of 32, NCHW output of the DCN, multi-problem launches)
+// takes the round-1 engine.
 #include <stdio.h>
 #include <stdlib.h>
 #include "conv_engine.cuh"
