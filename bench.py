@@ -504,6 +504,12 @@ def run_gpu(args):
                     # MMAs, 3 tiles per CTA (416 tiles on 148 SMs), at the SM clock sampled during the run
                     "mma_floor_us": 3 * (72 * (64 + 48) + (8 * 3 * 48 if "tail" in k_what else 0))
                                     / (((clocks or {}).get("sm_mhz") or 1965.0) * 1e6) * 1e6,
+                    # shared-memory-port floor of the same launch: per 128-pixel tile the producers read 4 corner lines
+                    # x 128 B per pixel and K block (18 x 64 KB), the tensor core reads the weight blocks (18 x 16 KB) and
+                    # the TMA unit writes two patch slots (2 x 70 KB) -- through one 128 B/clk port per SM.  This, not
+                    # the tensor pipe, is what the kernel runs against (ncu: data pipe ~60 % busy incl. bank conflicts)
+                    "smem_port_floor_us": 3 * (18 * (64 + 16) + 2 * 70) * 1024 / 128.0
+                                          / (((clocks or {}).get("sm_mhz") or 1965.0) * 1e6) * 1e6,
                     "us_per_launch": k_ms * 1e3, "algorithmic_mb": k_bytes / 1e6,
                     "hbm_frac_if_memory_bound": k_bytes / (k_ms * 1e-3) / 1e9 / hbm,
                     "peak_source": peak_src + "; TF32 dense taken as bf16_tflops/2 (burst, kernel timed alone); "
