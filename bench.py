@@ -379,7 +379,6 @@ def run_gpu(args):
     e1.record(stream)
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1), device)
-    clocks = sampler.summary() if sampler else None
     value = total_pairs_per_step * args.steps / (ms_total / 1e3)
 
     # ---- end to end: pinned host buffers -> HostPipeline -> pinned disparity
@@ -468,6 +467,11 @@ def run_gpu(args):
                             "computed from them (ops.correlation_bf16), aggregation and regression stay fp32"}
         del pipe16
 
+    # the sampler (one nvidia-smi query per 0.1 s) has run through the device-timed loop AND the end-to-end loops: the
+    # K device-timed steps alone last ~25 ms
+    clocks = sampler.summary() if sampler else None
+    if clocks is not None:
+        clocks["regions"] = "device-timed loop + end-to-end loops"
     out = None
     if rank == 0:
         hbm, bf16, peak_src = load_peaks()
