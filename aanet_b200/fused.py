@@ -3,9 +3,12 @@
 Same arithmetic as AdaptiveAggregation.forward in eval mode (reference nets/aggregation.py:452-464 and
 the modules below it), but every convolution -- the 1x1 / 3x3 convs of the bottlenecks (deform.py:164-184,
 :216-236), the offset/mask head (deform.py:80-89), the CSA exchange convs (aggregation.py:346-371) and the
-final 1x1 (aggregation.py:443-450) -- runs on the tcgen05 engine with eval-mode BatchNorm folded into a
-per-channel (scale, shift) epilogue, ReLU / LeakyReLU / residual add fused, and activations kept
-channels-last between kernels.  ~125 launches per stereo pair instead of ~320.
+final 1x1 (aggregation.py:443-450) -- runs on the tcgen05 kernels (TMEM-A kernel deform_tmem.cu where the layer has
+32-channel blocks, round-1 engine otherwise) with eval-mode BatchNorm folded into a per-channel (scale, shift)
+epilogue, ReLU / LeakyReLU / residual add fused, and activations kept channels-last between kernels.  Launches per
+stereo pair at config 2: 96 (module-by-module path: ~320).  Fusions beyond single layers: conv3 inside conv2's
+launch (_Bottleneck), the coarsest CSA row's sum inside its exchange convolutions (go_folded), the last module's
+sum + final 1x1 + soft-argmin as one launch (to_disp).
 
 This is SURVEY.md 8(f) ranks 1-2.  It is used automatically by AdaptiveAggregation.forward when the module
 is in eval mode, autograd is off and every channel count is a multiple of 4; otherwise the module-by-module
