@@ -21,6 +21,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--graph", action="store_true")
 ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--steps", type=int, default=4)
+ap.add_argument("--all", action="store_true", help="include memset / memcpy activities")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 hp = bench.make_hot_path().to(dev)
@@ -48,7 +49,7 @@ with torch.no_grad():
             torch.cuda.synchronize()
 
 ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range is not None
-      and "memcpy" not in e.name.lower() and "memset" not in e.name.lower()]
+      and (args.all or ("memcpy" not in e.name.lower() and "memset" not in e.name.lower()))]
 ev.sort(key=lambda e: e.time_range.start)
 # split into steps at gaps > 200 us and keep the last one
 steps, cur = [], [ev[0]]
